@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the LSDM denoising hot path (BASELINE.json metric: denoising-steps/sec = batch x timesteps / s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode strict|hoisted] [--batch B]
+
+Workload (config.workload): BASELINE configs[1] -- "SDM full 1000-step DDPM p_sample_loop, batch=64, 1xB200": T=1000
+cosine schedule, B=64 samples per GPU, 9 clouds x 1024 points per sample, synthetic seeded inputs / random-init
+(well-conditioned) weights.  One bench "step" = one denoising step of the whole batch (one pass of the hot path:
+condition encode incl. PointNet++ on 9B clouds, x0 network, posterior + ancestral noise), K consecutive timesteps
+999, 998, ...  STRICT mode (default) re-encodes the conditions every step from fresh FPS start draws, exactly the
+per-step work of the reference; ``--mode hoisted`` encodes once (an algorithmic optimisation, reported separately).
+
+value : device-timed (CUDA events on the launching stream), all inputs already resident in HBM.
+e2e   : same metric through the reference-shaped public API (p_sample_loop over the same K timesteps) with HOST
+        (pinned) condition buffers: host->device copies of conditions and per-step FPS starts and the final
+        device->host read of the samples are inside the timed region.
+N > 1 : weak scaling, B samples per GPU, samples sharded across ranks (global mask replicated), one NCCL all-gather of
+        the outputs at the end of the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoising-steps/sec (batch x timesteps)"
+UNIT = "sample-steps/s"
+WORKLOAD = "SDM 1000-step DDPM p_sample_loop, batch=64 per GPU, 9x1024-pt clouds (BASELINE configs[1])"
+# algorithmic work per sample-step
+FLOP_STRICT = 14.51e9
+FLOP_HOISTED = 0.185e9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="strict", choices=["strict", "hoisted"])
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's p_sample, "as written" (materialised point attention), all host threads
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(steps, warmup, micro_batch=4):
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lsdm_oracle as O
+    from lsdm_b200 import synthetic as syn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = syn.make_state_dict(0, "wellcond")
+    tables = O.diffusion_tables(O.cosine_betas(1000))
+    inp = syn.make_inputs(1234, micro_batch)
+    fps, noise = syn.make_step_randoms(4321, micro_batch, steps + warmup)
+    x = inp["x_T"].clone()
+    times = []
+    with torch.no_grad():
+        for k in range(steps + warmup):
+            t = torch.full((micro_batch,), 999 - k, dtype=torch.long)
+            t0 = time.perf_counter()
+            out = O.p_sample(sd, tables, x, inp["mask"], t, inp["given_objs"], inp["given_cats"], inp["text_emb"], list(fps[k]),
+                             noise[k], as_written=True)
+            x = out["sample"]
+            times.append(time.perf_counter() - t0)
+    timed = times[warmup:]
+    sec = sum(timed)
+    return {"value": micro_batch * len(timed) / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port of the reference p_sample (as written, fp32 torch CPU, {cores} threads): micro-batch {micro_batch} x "
+                      f"{len(timed)} timed steps after {warmup} warm-up; full B=64 x 1000-step workload is a linear extrapolation",
+            "sec_per_step": sec / len(timed)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 1))
+    cb = cpu_port_rate(steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": cb["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "mode": "strict", "note": "CPU port; bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from lsdm_b200 import synthetic as syn
+    from lsdm_b200.model.sdm import SceneDiffusionModel
+    from lsdm_b200.util.model_util import create_gaussian_diffusion, get_default_diffusion, get_default_model_proxd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K, W = args.batch, args.steps, args.warmup
+    Bg = B * world
+    off = rank * B
+    hoisted = args.mode == "hoisted"
+    T = 1000
+
+    model = SceneDiffusionModel(**get_default_model_proxd())
+    model.load_state_dict(syn.make_state_dict(0, "wellcond"))
+    model.eval()
+    diff = create_gaussian_diffusion(get_default_diffusion())
+    model.set_shard(Bg, off)
+
+    # seeded synthetic inputs at GLOBAL shape (every rank generates the same tensors and slices its shard; the global
+    # mask is replicated because the reference's mask scrambles index it by global sample -- SURVEY.md 8e)
+    inp = syn.make_inputs(1234, Bg)
+    fps_all, noise_all = syn.make_step_randoms(4321, Bg, W + K)
+    sl = slice(off, off + B)
+    fps_loc = fps_all.view(W + K, 4, Bg, 9)[:, :, sl].reshape(W + K, 4, B * 9).contiguous()
+    host = {"mask": inp["mask"].pin_memory(), "given_objs": inp["given_objs"][sl].contiguous().pin_memory(),
+            "given_cats": inp["given_cats"][sl].contiguous().pin_memory(), "text_emb": inp["text_emb"][sl].contiguous().pin_memory(),
+            "x_T": inp["x_T"][sl].contiguous().pin_memory()}
+    g = {k: v.to(dev) for k, v in host.items()}
+    fps_dev = fps_loc.to(dev)
+    noise_dev = noise_all[:, sl].contiguous().to(dev)
+
+    eng = diff._engine(model, B, dev)
+    x = g["x_T"].clone()
+    gather_buf = torch.empty(world, B, 1024, 3, device=dev) if world > 1 else None
+
+    def run_steps(first_k, n, xbuf):
+        return eng.sample_loop(xbuf, g["text_emb"], g["given_objs"], g["given_cats"], g["mask"], fps_dev[first_k:first_k + n],
+                               noise_dev[first_k:first_k + n], T - 1 - first_k, hoisted)
+
+    # warm-up (untimed)
+    run_steps(0, W, x)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_steps(W, K, x)
+    if world > 1:
+        dist.all_gather_into_tensor(gather_buf.view(-1), x.view(-1))  # the path's single exchange step
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = Bg * K / (ms * 1e-3)
+
+    # ---- per-kernel-class shares + roofline numerator: separate profiled pass (CUDA events around every launch) ----
+    xp = g["x_T"].clone()
+    eng.profile_begin()
+    run_steps(W, min(K, 3), xp)
+    cls_ms, cls_n, gemm_flops = eng.profile_end()
+    prof_steps = min(K, 3)
+    tot_ms = sum(cls_ms.values())
+    peaks, peak_src = measured_peaks()
+    gemm_ms = cls_ms["gemm"]
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # fp32 CUDA-core GEMM today; the tensor roofline it is judged against is TF32 dense = half the measured bf16 rate
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    roofline = {"bound": "tensor", "kernel": "gemm (all dense layers)", "achieved": gemm_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": gemm_tflops / tf32_peak, "traffic": None,
+                "peak_source": f"{peak_src} bf16_tflops_sustained/2 (TF32 dense runs at half the bf16 rate)",
+                "flops_per_launch_avg": gemm_flops / max(1, cls_n["gemm"]), "launches_per_step": cls_n["gemm"] / prof_steps,
+                "avg_launch_ms": gemm_ms / max(1, cls_n["gemm"]), "share_of_step": gemm_ms / tot_ms if tot_ms else None,
+                "algorithmic_tflops_whole_step": (FLOP_HOISTED if hoisted else FLOP_STRICT) * Bg * K / (ms * 1e-3) / 1e12}
+    shares = {k: (v / tot_ms if tot_ms else 0.0) for k, v in cls_ms.items()}
+
+    # ---- e2e through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        from lsdm_b200.diffusion import gaussian_diffusion as gdm
+
+        torch.manual_seed(7)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        # the reference's call: diffusion.p_sample_loop(model, shape, mask, given_objs, given_cats, y, clip_denoised=False);
+        # skip_timesteps leaves K timesteps; host tensors are uploaded inside (Engine._f32), result read back
+        out = diff.p_sample_loop_fused(model, (B, 1024, 3), host["mask"], host["given_objs"], host["given_cats"], host["text_emb"],
+                                       noise=None, clip_denoised=False, device=dev, skip_timesteps=T - K, hoisted=hoisted, chunk=K)
+        out_host = out.cpu()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tdt = torch.tensor([dt], device=dev)
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            dt = float(tdt.item())
+        cond_bytes = sum(host[k].numel() * 4 for k in ("mask", "given_objs", "given_cats", "text_emb"))
+        fps_bytes = 4 * 9 * B * 8
+        e2e = {"value": Bg * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(cond_bytes / K + fps_bytes),
+               "d2h_bytes_per_step": int(out_host.numel() * 4 / K),
+               "note": "p_sample_loop_fused over the same K timesteps via the reference-shaped API; conditions (pinned host) uploaded once per "
+                       "call, FPS starts drawn on the CPU generator and uploaded per chunk, noise drawn on the device generator "
+                       "(as the reference does), final samples read back"}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_port_rate(2, 1)
+            cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "mode": args.mode, "global_batch": Bg, "per_gpu_batch": B, "timesteps_timed": K,
+                       "parallelism": f"dp{world} (samples sharded, no data-path collective; one all-gather of outputs)",
+                       "l2": "per-step working set (GBs of intermediates over 9*B clouds) is far larger than the 126 MB L2; no flush needed",
+                       "weights": "seeded well-conditioned random init (lsdm_b200.synthetic)"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernel_time_shares": shares,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/*
+ * lsdm_b200 -- C ABI of the B200-native LSDM multi-conditional denoising path.
+ *
+ * The reference (andvg3/LSDM) has no plugin / operator / FFI layer: its boundary is the Python
+ * surface of util/model_util.py, model/sdm.py and diffusion/{gaussian_diffusion,respace}.py.  This
+ * header is the C boundary UNDER that surface: each entry point names the reference Python
+ * function(s) it replaces (paths relative to the reference tree).  The Python mirror of the
+ * reference API (lsdm_b200/) binds these symbols with ctypes; see INTEGRATION.md for the binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; no torch / pybind types.  `stream` is a cudaStream_t passed as void*.
+ *  - every pointer is a DEVICE pointer unless the parameter is documented "host or device"
+ *    (those are copied with cudaMemcpyDefault on `stream`).
+ *  - no entry point synchronises the stream or allocates caller-visible memory; the caller
+ *    provides one workspace of lsdm_workspace_bytes() bytes (256-byte aligned) per handle.
+ *  - return value: 0 on success, a negative LSDM_E* code on failure; lsdm_last_error() returns a
+ *    thread-local message.  One stream per handle at a time; distinct handles are independent.
+ *  - all floating-point tensors are fp32, row-major, contiguous.
+ */
+#ifndef LSDM_B200_H
+#define LSDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LSDM_API __attribute__((visibility("default")))
+#else
+#define LSDM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSDM_OK 0
+#define LSDM_EINVAL (-1)   /* bad argument / shape / unknown key */
+#define LSDM_ESTATE (-2)   /* call order violated (weights not finalised, conditions not encoded ...) */
+#define LSDM_ECUDA (-3)    /* CUDA runtime error (message has cudaGetErrorString) */
+#define LSDM_ENOMEM (-4)
+
+#define LSDM_N_POINTS 1024 /* points per cloud (reference posa/dataset.py:456-474) */
+#define LSDM_N_OBJ 9       /* object slots per scene, slot 0 = human */
+#define LSDM_CLIP_DIM 512  /* text-embedding width fed to embed_text (util/model_util.py:31) */
+
+typedef struct lsdm_handle lsdm_handle;
+
+typedef struct lsdm_config {
+  int32_t batch_local;  /* samples this handle processes per call (<= batch_global) */
+  int32_t batch_global; /* global batch B: the scrambles of model/sdm.py:180-182,199-201 index the mask by it */
+  int32_t batch_offset; /* global index of local sample 0 (data-parallel shard offset) */
+  int32_t n_cats;       /* 13 (proxd) or 11 (humanise): util/model_util.py:26-73 */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t reserved;
+} lsdm_config;
+
+/* Library / build identification ("lsdm_b200 <ver> sm_100a"). */
+LSDM_API const char* lsdm_version(void);
+LSDM_API const char* lsdm_last_error(void);
+
+/* Replaces SceneDiffusionModel.__init__ + .to(device) (model/sdm.py:19-129). */
+LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg);
+LSDM_API void lsdm_destroy(lsdm_handle* h);
+/* Re-shard an existing handle (same weights): changes batch_local/global/offset only. */
+LSDM_API int lsdm_set_batch(lsdm_handle* h, int32_t batch_local, int32_t batch_global, int32_t batch_offset);
+
+/* Replaces nn.Module.load_state_dict (run/test_sdm.py:123-124): one call per state-dict entry, with
+ * the reference's exact key and shape.  `data`: host or device, fp32
+ * (num_batches_tracked entries are accepted and ignored).  Unknown `clip_model.*` keys are ignored. */
+LSDM_API int lsdm_load_weight(lsdm_handle* h, const char* key, const void* data, const int64_t* shape, int32_t ndim,
+                     void* stream);
+/* Number of state-dict entries the handle expects / i-th expected key (for the Python mirror). */
+LSDM_API int lsdm_num_weights(const lsdm_handle* h);
+LSDM_API const char* lsdm_weight_key(const lsdm_handle* h, int i);
+/* Folds eval-mode BatchNorm into the 1x1 convs, splits the first SA/FP layers into their
+ * coordinate / feature halves.  Must follow the last lsdm_load_weight. */
+LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream);
+
+/* Replaces GaussianDiffusion.__init__'s tables + _extract_into_tensor (diffusion/gaussian_diffusion.py:
+ * 166-202,1585-1598): fp32 casts of the float64 tables, length T each (host or device). */
+LSDM_API int lsdm_set_schedule(lsdm_handle* h, const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                      const float* posterior_log_variance_clipped, const float* sqrt_alphas_cumprod,
+                      const float* sqrt_one_minus_alphas_cumprod, int32_t T, void* stream);
+
+LSDM_API size_t lsdm_workspace_bytes(const lsdm_handle* h);
+LSDM_API int lsdm_set_workspace(lsdm_handle* h, void* workspace, size_t bytes);
+
+/* Replaces the x/t-independent part of SceneDiffusionModel.forward (model/sdm.py:147-203): text / category
+ * MLPs, object attention weights, PointNet++ on the 9 clouds, POSA human decoder, collapsed point attention,
+ * pointwise translation, masked sum.  Leaves pcd_out / enc / out_cat in the workspace.
+ *   text_emb[Bl,512]  given_objs[Bl,9,1024,3]  given_cats[Bl,9,C]  mask_global[Bg,9]
+ *   fps_start[4][9*Bl] int64 (host or device): the four torch.randint(0,N,(9B,)) draws of
+ *   farthest_point_sample (model/pcd_backbone/pointnet2_utils.py:72), LOCAL slice, N = 1024,1024,256,64. */
+LSDM_API int lsdm_encode_conditions(lsdm_handle* h, const float* text_emb, const float* given_objs, const float* given_cats,
+                           const float* mask_global, const int64_t* fps_start, void* stream);
+
+/* Replaces one GaussianDiffusion.p_sample (diffusion/gaussian_diffusion.py:501-561) given encoded conditions:
+ * timestep embedding, upsampler, x += pcd_out (IN PLACE, model/sdm.py:204), Input/OutputProcess, posterior
+ * mean with the mutated x, ancestral noise.  t[Bl] int64 (host or device) indexes the schedule tables AND the
+ * positional table.  x[Bl,1024,3] in-out; noise[Bl,1024,3]; sample_out[Bl,1024,3] (may alias x);
+ * x0_out, guiding_out nullable.  clip_denoised != 0 clamps x0 to [-1,1] before the posterior mean
+ * (process_xstart, gaussian_diffusion.py:359-365; every reference caller passes False). */
+LSDM_API int lsdm_denoise_step(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,
+                      float* guiding_out, int32_t clip_denoised, void* stream);
+
+/* Replaces SceneDiffusionModel.forward given encoded conditions (model/sdm.py:131-218): like lsdm_denoise_step
+ * without the posterior.  x is mutated in place; out_cat[Bl,C], x0[Bl,1024,3], guiding[Bl,1024,3] (nullable). */
+LSDM_API int lsdm_forward(lsdm_handle* h, float* x, const int64_t* t, float* out_cat, float* x0, float* guiding, void* stream);
+
+/* Replaces the loop body of p_sample_loop_progressive (diffusion/gaussian_diffusion.py:736-759) for `n_steps`
+ * consecutive timesteps t_first, t_first-1, ...: STRICT mode re-encodes the conditions every step from
+ * fps_start_all[n_steps][4][9*Bl] (what the reference does); hoisted != 0 encodes once.
+ * noise_all[n_steps][Bl,1024,3].  x in-out.  All pointers device. */
+LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text_emb, const float* given_objs, const float* given_cats,
+                     const float* mask_global, const int64_t* fps_start_all, const float* noise_all, int32_t t_first,
+                     int32_t n_steps, int32_t hoisted, int32_t clip_denoised, float* x0_out, float* guiding_out, void* stream);
+
+/* Copies of cached per-loop outputs: out_cat[Bl,C] (model.saved_cat), pcd_out[Bl,1024,3]. */
+LSDM_API int lsdm_get_out_cat(lsdm_handle* h, float* out_cat, void* stream);
+LSDM_API int lsdm_get_pcd_out(lsdm_handle* h, float* pcd_out, void* stream);
+
+/* Replaces q_sample (diffusion/gaussian_diffusion.py:238-256): x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) noise. */
+LSDM_API int lsdm_q_sample(lsdm_handle* h, const float* x_start, const int64_t* t, const float* noise, float* x_t, void* stream);
+
+/* Replaces pytorch3d.loss.chamfer_distance with default arguments as called at diffusion/gaussian_diffusion.py:1334:
+ * sums[0] += sum_b mean_p min_q |x-y|^2, sums[1] += the y->x direction (caller zeroes sums, divides by B). */
+LSDM_API int lsdm_chamfer(lsdm_handle* h, const float* x, const float* y, int32_t batch, int32_t n, int32_t m, float* sums,
+                 void* stream);
+
+/* Replaces the categorical term of training_losses (diffusion/gaussian_diffusion.py:1297-1301):
+ * sum_b CrossEntropy(probs[b,:] treated as logits, argmax(target_cat[b,:])) accumulated into *sum. */
+LSDM_API int lsdm_cat_loss(lsdm_handle* h, const float* probs, const float* target_cat, int32_t batch, float* sum, void* stream);
+
+/* Debug / parity taps: copy a named intermediate of the last encode/forward into `dst` (device).
+ * Returns the element count, or a negative error.  Names: "backbone" [9Bl,1024,3], "hm" [Bl,1024,3],
+ * "attn_w" [Bl,9], "tr" [Bl,9,12], "enc" [Bl,128], "pa" [Bl,9,12], "pw" [Bl,9,1024,3], "emb" [Bl,1024,128],
+ * "fps_idx0..3", "ball_idx0..3" (int32), "l1_feat".. */
+LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, size_t dst_bytes, void* stream);
+
+/* Number of kernels this library has launched on behalf of `h` since creation (bench.py's gpu_launches). */
+LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h);
+
+/* Per-kernel-class timing with CUDA events on the launching stream (measurement aid for bench.py; adds two event
+ * records per launch, so it is used in a separate pass, never inside the timed region).  Classes, in order:
+ * gemm, fps, ball_query, sa_gather, three_nn, fp_combine, head3, cond, scene, denoise, other (LSDM_N_KCLASS = 11).
+ * lsdm_profile_end synchronises the recorded events; gemm_flops = sum of 2*M*N*K over the profiled GEMM launches. */
+#define LSDM_N_KCLASS 11
+LSDM_API int lsdm_profile_begin(lsdm_handle* h);
+LSDM_API int lsdm_profile_end(lsdm_handle* h, double* ms_by_class, int64_t* launches_by_class, int32_t n_class,
+                              double* gemm_flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSDM_B200_H */

@@ -1,0 +1,81 @@
+"""ctypes binding of ``liblsdm_b200.so`` (C ABI declared in ``include/lsdm_b200.h``).
+
+The product path has NO fallback: if the CUDA library is missing or fails to load, every
+entry point raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C lsdm_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblsdm_b200.so")
+
+OK, EINVAL, ESTATE, ECUDA, ENOMEM = 0, -1, -2, -3, -4
+
+
+class LsdmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lsdm_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("batch_local", C.c_int32), ("batch_global", C.c_int32), ("batch_offset", C.c_int32),
+                ("n_cats", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+_P = C.c_void_p
+# name -> (restype, argtypes); exactly the prototypes of include/lsdm_b200.h
+PROTOTYPES = {
+    "lsdm_version": (C.c_char_p, []),
+    "lsdm_last_error": (C.c_char_p, []),
+    "lsdm_create": (C.c_int, [C.POINTER(_P), C.POINTER(Config)]),
+    "lsdm_destroy": (None, [_P]),
+    "lsdm_set_batch": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "lsdm_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int32, _P]),
+    "lsdm_num_weights": (C.c_int, [_P]),
+    "lsdm_weight_key": (C.c_char_p, [_P, C.c_int]),
+    "lsdm_finalize_weights": (C.c_int, [_P, _P]),
+    "lsdm_set_schedule": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, _P]),
+    "lsdm_workspace_bytes": (C.c_size_t, [_P]),
+    "lsdm_set_workspace": (C.c_int, [_P, _P, C.c_size_t]),
+    "lsdm_encode_conditions": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "lsdm_denoise_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
+    "lsdm_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "lsdm_sample_loop": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "lsdm_get_out_cat": (C.c_int, [_P, _P, _P]),
+    "lsdm_get_pcd_out": (C.c_int, [_P, _P, _P]),
+    "lsdm_q_sample": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "lsdm_chamfer": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "lsdm_cat_loss": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
+    "lsdm_debug_tensor": (C.c_int64, [_P, C.c_char_p, _P, C.c_size_t, _P]),
+    "lsdm_launch_count": (C.c_int64, [_P]),
+    "lsdm_profile_begin": (C.c_int, [_P]),
+    "lsdm_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every prototype.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LsdmError(ESTATE, f"{LIB_PATH} not built: the CUDA path is the only path (no CPU fallback). "
+                                "Run `make -C lsdm_b200/csrc` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != OK:
+        raise LsdmError(code, load().lsdm_last_error().decode())

@@ -1,0 +1,775 @@
+// C ABI of lsdm_b200 (include/lsdm_b200.h): handle, weight registry, workspace carving and the
+// orchestration of the kernels for encode_conditions / denoise_step / forward / sample_loop.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/lsdm_b200.h"
+#include "kernels.cuh"
+
+using namespace lsdm;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(LSDM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                      \
+  } while (0)
+
+struct WEntry {
+  std::string key;
+  std::vector<int64_t> shape;
+  int64_t numel;
+  int64_t off;  // float offset into the raw arena; -1 for ignored (int64) entries
+  bool loaded;
+};
+
+struct SASpec { const char* name; int npoint; double radius; int cin; int mlp[3]; int N; };
+struct FPSpec { const char* name; int cin; int nl; int mlp[3]; int Ca; int Cb; };
+const SASpec kSA[4] = {{"sa1", 1024, 0.1, 6, {32, 32, 64}, 1024},
+                       {"sa2", 256, 0.2, 67, {64, 64, 128}, 1024},
+                       {"sa3", 64, 0.4, 131, {128, 128, 256}, 256},
+                       {"sa4", 16, 0.8, 259, {256, 256, 512}, 64}};
+const FPSpec kFP[4] = {{"fp4", 768, 2, {256, 256, 0}, 256, 512},
+                       {"fp3", 384, 2, {256, 256, 0}, 128, 256},
+                       {"fp2", 320, 2, {256, 128, 0}, 64, 256},
+                       {"fp1", 128, 3, {128, 128, 128}, 0, 128}};
+
+struct Bump {
+  char* base;
+  size_t off;
+  explicit Bump(void* b) : base(static_cast<char*>(b)), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Workspace {
+  // conditions
+  float *enc, *out_cat, *attn_w, *tr, *qq, *hm, *human_scratch;
+  int64_t *fps_start, *t_dev;
+  int *idx[4], *grp[4], *nn_idx[4];
+  float *xyz[5], *feat[5], *nn_w[4];
+  float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out;
+  // step
+  float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
+  size_t bytes;
+};
+
+}  // namespace
+
+struct lsdm_handle {
+  lsdm_config cfg;
+  std::vector<WEntry> entries;
+  std::unordered_map<std::string, int> index;
+  float* arena = nullptr;    // raw state-dict tensors
+  float* derived = nullptr;  // folded / split tensors
+  int64_t arena_floats = 0, derived_floats = 0;
+  bool finalized = false, have_sched = false, have_cond = false;
+  // folded weights
+  float *sa_w[4][3], *sa_b[4][3], *sa_wx[4], *sa_wf[4];
+  float *fp_w[4][3], *fp_b[4][3], *fp_wa[4], *fp_wb[4];
+  float *head_w, *head_b;
+  // schedule
+  float* sched = nullptr;  // 5 x T
+  int T = 0;
+  Workspace ws{};
+  bool have_ws = false;
+  int64_t launches = 0;
+  // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
+  bool profiling = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  double gemm_flops = 0.0;
+
+  const float* W(const std::string& k) const { return arena + entries[index.at(k)].off; }
+};
+
+namespace {
+
+void add_entry(lsdm_handle* h, const std::string& key, std::vector<int64_t> shape, bool ignored = false) {
+  WEntry e;
+  e.key = key;
+  e.shape = shape;
+  e.numel = 1;
+  for (auto s : shape) e.numel *= s;
+  e.loaded = false;
+  if (ignored) {
+    e.off = -1;
+  } else {
+    e.off = h->arena_floats;
+    h->arena_floats += (e.numel + 63) & ~int64_t(63);  // 256-byte aligned slots
+  }
+  h->index[key] = (int)h->entries.size();
+  h->entries.push_back(e);
+}
+
+void add_linear(lsdm_handle* h, const std::string& p, int64_t o, int64_t i) {
+  add_entry(h, p + ".weight", {o, i});
+  add_entry(h, p + ".bias", {o});
+}
+void add_bn(lsdm_handle* h, const std::string& p, int64_t c) {
+  add_entry(h, p + ".weight", {c});
+  add_entry(h, p + ".bias", {c});
+  add_entry(h, p + ".running_mean", {c});
+  add_entry(h, p + ".running_var", {c});
+  add_entry(h, p + ".num_batches_tracked", {}, true);
+}
+
+// The reference's model_state_dict contract (model/sdm.py:19-129).
+void build_registry(lsdm_handle* h) {
+  const int64_t C = h->cfg.n_cats;
+  add_entry(h, "sequence_pos_encoder.pe", {5000, 1, LAT});
+  add_entry(h, "embed_timestep.sequence_pos_encoder.pe", {5000, 1, LAT});
+  add_linear(h, "embed_timestep.time_embed.0", LAT, LAT);
+  add_linear(h, "embed_timestep.time_embed.2", LAT, LAT);
+  add_linear(h, "embed_text.0", CLIP / 2, CLIP);
+  add_linear(h, "embed_text.2", 2 * LAT, CLIP / 2);
+  add_linear(h, "embed_text.4", LAT, 2 * LAT);
+  add_linear(h, "embed_cat.0", CATEMB, C);
+  add_linear(h, "predict_cat.0", LAT / 2, LAT);
+  add_linear(h, "predict_cat.2", LAT / 4, LAT / 2);
+  add_linear(h, "predict_cat.4", C, LAT / 4);
+  add_entry(h, "attn_layer.q_proj_weight", {LAT, LAT});
+  add_entry(h, "attn_layer.k_proj_weight", {LAT, CATEMB});
+  add_entry(h, "attn_layer.v_proj_weight", {LAT, NPTS * 3});  // dead in the reference forward; kept for strict loading
+  add_entry(h, "attn_layer.in_proj_bias", {3 * LAT});
+  add_linear(h, "attn_layer.out_proj", LAT, LAT);
+  add_linear(h, "translation_layer.0", LAT, LAT + CATEMB);
+  add_linear(h, "translation_layer.2", TRANS, LAT);
+  add_linear(h, "point_wise_trans_layer.0", 3, TRANS + 3);
+  add_entry(h, "pcd_attention.q_proj_weight", {TRANS, TRANS});
+  add_entry(h, "pcd_attention.k_proj_weight", {TRANS, 3});
+  add_entry(h, "pcd_attention.v_proj_weight", {TRANS, 3});
+  add_entry(h, "pcd_attention.in_proj_bias", {3 * TRANS});
+  add_linear(h, "pcd_attention.out_proj", TRANS, TRANS);
+  for (const auto& s : kSA) {
+    int last = s.cin;
+    for (int i = 0; i < 3; ++i) {
+      std::string p = std::string("pcd_backbone.") + s.name + ".mlp_convs." + std::to_string(i);
+      add_entry(h, p + ".weight", {s.mlp[i], last, 1, 1});
+      add_entry(h, p + ".bias", {s.mlp[i]});
+      last = s.mlp[i];
+    }
+    for (int i = 0; i < 3; ++i) add_bn(h, std::string("pcd_backbone.") + s.name + ".mlp_bns." + std::to_string(i), s.mlp[i]);
+  }
+  for (const auto& s : kFP) {
+    int last = s.cin;
+    for (int i = 0; i < s.nl; ++i) {
+      std::string p = std::string("pcd_backbone.") + s.name + ".mlp_convs." + std::to_string(i);
+      add_entry(h, p + ".weight", {s.mlp[i], last, 1});
+      add_entry(h, p + ".bias", {s.mlp[i]});
+      last = s.mlp[i];
+    }
+    for (int i = 0; i < s.nl; ++i) add_bn(h, std::string("pcd_backbone.") + s.name + ".mlp_bns." + std::to_string(i), s.mlp[i]);
+  }
+  add_entry(h, "pcd_backbone.conv1.weight", {128, 128, 1});
+  add_entry(h, "pcd_backbone.conv1.bias", {128});
+  add_bn(h, "pcd_backbone.bn1", 128);
+  add_entry(h, "pcd_backbone.conv2.weight", {3, 128, 1});
+  add_entry(h, "pcd_backbone.conv2.bias", {3});
+  const int hc[3][2] = {{64, 3}, {64, 64}, {64, 64}};
+  for (int i = 0; i < 3; ++i) {
+    std::string p = "human_backbone.de_spiral." + std::to_string(i);
+    add_linear(h, p + ".conv.layer", hc[i][0], hc[i][1]);
+    add_entry(h, p + ".norm.weight", {64});
+    add_entry(h, p + ".norm.bias", {64});
+  }
+  add_linear(h, "human_backbone.de_spiral.3.layer", 3, 64);
+  add_linear(h, "upsampling_layer.0", 128, 1);
+  add_linear(h, "upsampling_layer.2", 512, 128);
+  add_linear(h, "upsampling_layer.4", NPTS, 512);
+  add_linear(h, "combine_extraction.0", LAT, 2 * LAT);
+  add_linear(h, "input_process.pose_embedding.0", LAT / 2, 3);
+  add_linear(h, "input_process.pose_embedding.2", LAT, LAT / 2);
+  add_linear(h, "input_process.combination_extraction.0", 192, 2 * LAT);
+  add_linear(h, "input_process.combination_extraction.2", LAT, 192);
+  add_linear(h, "output_process.pose_final.0", LAT / 2, LAT);
+  add_linear(h, "output_process.pose_final.2", 3, LAT / 2);
+}
+
+size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
+  const size_t B = (size_t)h->cfg.batch_local, C = B * NOBJ, nc = (size_t)h->cfg.n_cats;
+  Bump a(base);
+  w->enc = a.take<float>(B * LAT);
+  w->out_cat = a.take<float>(B * nc);
+  w->attn_w = a.take<float>(B * NOBJ);
+  w->tr = a.take<float>(C * TRANS);
+  w->qq = a.take<float>(C * TRANS);
+  w->hm = a.take<float>(B * NPTS * 3);
+  w->human_scratch = a.take<float>(B * 2 * NPTS * 64);
+  w->fps_start = a.take<int64_t>(4 * C);
+  w->t_dev = a.take<int64_t>(B);
+  const size_t np[5] = {1024, 1024, 256, 64, 16};
+  const size_t fc[5] = {3, 64, 128, 256, 512};
+  w->xyz[0] = nullptr;
+  w->feat[0] = nullptr;
+  for (int l = 1; l <= 4; ++l) {
+    w->idx[l - 1] = a.take<int>(C * np[l]);
+    w->grp[l - 1] = a.take<int>(C * np[l] * 32);
+    w->xyz[l] = a.take<float>(C * np[l] * 3);
+    w->feat[l] = a.take<float>(C * np[l] * fc[l]);
+  }
+  const size_t fn[4] = {64, 256, 1024, 1024};  // fine-point count of fp4, fp3, fp2, fp1
+  for (int l = 0; l < 4; ++l) {
+    w->nn_idx[l] = a.take<int>(C * fn[l] * 3);
+    w->nn_w[l] = a.take<float>(C * fn[l] * 3);
+  }
+  w->tA = a.take<float>(C * 1048576);
+  w->tB = a.take<float>(C * 1048576);
+  w->tP = a.take<float>(C * 262144);
+  w->g3 = a.take<float>(C * 64 * 256);
+  w->g2 = a.take<float>(C * 256 * 256);
+  w->g1 = a.take<float>(C * 1024 * 128);
+  w->backbone = a.take<float>(C * NPTS * 3);
+  w->pa = a.take<float>(C * TRANS);
+  w->pw = a.take<float>(C * NPTS * 3);
+  w->pcd_out = a.take<float>(B * NPTS * 3);
+  const size_t rows = B * NPTS;
+  w->s256 = a.take<float>(B * 256);
+  w->H1 = a.take<float>(B * 256 * 128);
+  w->H2 = a.take<float>(B * 256 * 512);
+  w->embpre = a.take<float>(rows * 256);
+  w->cat = a.take<float>(2 * rows * 256);
+  w->h1 = a.take<float>(2 * rows * 64);
+  w->c1 = a.take<float>(2 * rows * 192);
+  w->c2 = a.take<float>(2 * rows * 128);
+  w->f1 = a.take<float>(2 * rows * 64);
+  w->x0 = a.take<float>(rows * 3);
+  w->guiding = a.take<float>(rows * 3);
+  w->loss_scratch = a.take<float>(64);
+  a.take<char>(256);
+  w->bytes = a.off;
+  return a.off;
+}
+
+enum KClass { K_GEMM = 0, K_FPS, K_BALL, K_GATHER, K_3NN, K_FPCOMB, K_HEAD, K_COND, K_SCENE, K_DENOISE, K_OTHER, K_NCLASS };
+
+template <typename F>
+int prof_launch(lsdm_handle* h, cudaStream_t st, int cls, F&& f) {
+  if (!h->profiling) {
+    int r = f();
+    if (r > 0) h->launches += r;
+    return r;
+  }
+  lsdm_handle::ProfRec rec;
+  rec.cls = cls;
+  cudaEventCreate(&rec.a);
+  cudaEventCreate(&rec.b);
+  cudaEventRecord(rec.a, st);
+  int r = f();
+  cudaEventRecord(rec.b, st);
+  h->prof.push_back(rec);
+  if (r > 0) h->launches += r;
+  return r;
+}
+
+int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const float* W, int64_t ldw, float* C,
+         int64_t ldc, const float* bias, int M, int N, int K, int act, int group_max = 0) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.strideA = 0;
+  g.W = W; g.ldw = ldw; g.strideW = 0;
+  g.C = C; g.ldc = ldc; g.strideC = 0;
+  g.bias = bias; g.bias_mode = bias ? 1 : 0;
+  g.M = M; g.N = N; g.K = K; g.batch = 1;
+  g.act = act; g.group_max = group_max;
+  int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
+  if (r < 0) return fail(LSDM_EINVAL, "gemm: unsupported shape M=" + std::to_string(M) + " N=" + std::to_string(N) +
+                                          " K=" + std::to_string(K));
+  if (h->profiling) h->gemm_flops += 2.0 * M * (double)N * K;
+  return LSDM_OK;
+}
+#define GE(x)                  \
+  do {                         \
+    int r__ = (x);             \
+    if (r__ != LSDM_OK) return r__; \
+  } while (0)
+
+int check_ready(lsdm_handle* h, bool need_cond) {
+  if (!h) return fail(LSDM_EINVAL, "null handle");
+  if (!h->finalized) return fail(LSDM_ESTATE, "weights not finalised (lsdm_finalize_weights)");
+  if (!h->have_ws) return fail(LSDM_ESTATE, "no workspace (lsdm_set_workspace)");
+  if (need_cond && !h->have_cond) return fail(LSDM_ESTATE, "conditions not encoded (lsdm_encode_conditions)");
+  return LSDM_OK;
+}
+
+int pointnet2(lsdm_handle* h, const float* clouds, cudaStream_t st) {
+  Workspace& w = h->ws;
+  const int C = h->cfg.batch_local * NOBJ;
+  prof_launch(h, st, K_FPS, [&] { return launch_fps4(clouds, w.fps_start, C, w.idx[0], w.idx[1], w.idx[2], w.idx[3], w.xyz[1], w.xyz[2], w.xyz[3],
+                             w.xyz[4], st); });
+  const float* xyz[5] = {clouds, w.xyz[1], w.xyz[2], w.xyz[3], w.xyz[4]};
+  const float* feat[5] = {clouds, w.feat[1], w.feat[2], w.feat[3], w.feat[4]};
+  for (int l = 0; l < 4; ++l) {
+    const SASpec& s = kSA[l];
+    const int N = s.N, S = s.npoint, C1 = s.mlp[0], C2 = s.mlp[1], C3 = s.mlp[2];
+    prof_launch(h, st, K_BALL, [&] { return launch_ball_query(xyz[l], xyz[l + 1], C, N, S, s.radius, w.grp[l], st); });
+    const float* P = nullptr;
+    if (l > 0) {  // first conv, feature half, once per source point
+      GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE));
+      P = w.tP;
+    }
+    prof_launch(h, st, K_GATHER, [&] { return launch_sa_gather(P, h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0], xyz[l], xyz[l + 1], w.grp[l], C, N, S, C1,
+                                    w.tA, st); });
+    const int rows = C * S * 32;
+    GE(gemm(h, st, w.tA, C1, h->sa_w[l][1], C1, w.tB, C2, h->sa_b[l][1], rows, C2, C1, ACT_RELU));
+    GE(gemm(h, st, w.tB, C2, h->sa_w[l][2], C2, w.feat[l + 1], C3, h->sa_b[l][2], rows, C3, C2, ACT_RELU, 1));
+  }
+  // feature propagation: fine level <- coarse level
+  const int fine[4] = {3, 2, 1, 0}, coarse[4] = {4, 3, 2, 1};
+  const int fineN[4] = {64, 256, 1024, 1024}, coarseN[4] = {16, 64, 256, 1024};
+  const float* coarse_feat = w.feat[4];
+  float* outs[4] = {w.g3, w.g2, w.g1, nullptr};
+  for (int l = 0; l < 4; ++l) {
+    const FPSpec& s = kFP[l];
+    const int N = fineN[l], S = coarseN[l], C1 = s.mlp[0];
+    prof_launch(h, st, K_3NN, [&] { return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, N, S, w.nn_idx[l], w.nn_w[l], st); });
+    const float* Pa = nullptr;
+    if (s.Ca > 0) {
+      GE(gemm(h, st, feat[fine[l]], s.Ca, h->fp_wa[l], s.Ca, w.tA, C1, h->fp_b[l][0], C * N, C1, s.Ca, ACT_NONE));
+      Pa = w.tA;
+    }
+    GE(gemm(h, st, coarse_feat, s.Cb, h->fp_wb[l], s.Cb, w.tB, C1, nullptr, C * S, C1, s.Cb, ACT_NONE));
+    prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, h->fp_b[l][0], w.tB, w.nn_idx[l], w.nn_w[l], C, N, S, C1, w.tP, st); });
+    if (l < 3) {
+      GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU));
+      coarse_feat = outs[l];
+    } else {
+      GE(gemm(h, st, w.tP, 128, h->fp_w[l][1], 128, w.tA, 128, h->fp_b[l][1], C * N, 128, 128, ACT_RELU));
+      GE(gemm(h, st, w.tA, 128, h->fp_w[l][2], 128, w.tP, 128, h->fp_b[l][2], C * N, 128, 128, ACT_RELU));
+      GE(gemm(h, st, w.tP, 128, h->head_w, 128, w.tA, 128, h->head_b, C * N, 128, 128, ACT_RELU));
+      prof_launch(h, st, K_HEAD, [&] { return launch_head3(w.tA, h->W("pcd_backbone.conv2.weight"), h->W("pcd_backbone.conv2.bias"),
+                                  (int64_t)C * N, w.backbone, st); });
+    }
+  }
+  return LSDM_OK;
+}
+
+// x/t-dependent part: timestep embedding, upsampler, x += pcd_out, Input/OutputProcess, optional posterior.
+int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,
+              float* guiding_out, bool want_guiding, int clip, cudaStream_t st) {
+  Workspace& w = h->ws;
+  const int B = h->cfg.batch_local;
+  const int rows = B * NPTS;
+  if (t != w.t_dev) CK(cudaMemcpyAsync(w.t_dev, t, sizeof(int64_t) * B, cudaMemcpyDefault, st));
+  prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
+                                   h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
+                                   h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.enc, h->W("upsampling_layer.0.weight"),
+                                   h->W("upsampling_layer.0.bias"), B, w.s256, w.H1, st); });
+  GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), B * 256, 512,
+          128, ACT_GELU));
+  {
+    // embpre[b][p][s] = gelu(sum_k U4[p][k] H2[b][s][k] + b4[p]): the upsampler's last layer written point-major
+    GemmArgs g{};
+    g.A = h->W("upsampling_layer.4.weight"); g.lda = 512; g.strideA = 0;
+    g.W = w.H2; g.ldw = 512; g.strideW = 256 * 512;
+    g.C = w.embpre; g.ldc = 256; g.strideC = (int64_t)NPTS * 256;
+    g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
+    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0;
+    int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
+    if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
+    if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
+  }
+  GE(gemm(h, st, w.embpre, 256, h->W("combine_extraction.0.weight"), 256, w.cat + 128, 256,
+          h->W("combine_extraction.0.bias"), rows, 128, 256, ACT_GELU));
+  const int M = want_guiding ? 2 * rows : rows;
+  if (want_guiding)
+    CK(cudaMemcpy2DAsync(w.cat + (size_t)rows * 256 + 128, 256 * sizeof(float), w.cat + 128, 256 * sizeof(float),
+                         128 * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+  prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(x, w.pcd_out, h->W("input_process.pose_embedding.0.weight"),
+                                    h->W("input_process.pose_embedding.0.bias"), rows, w.h1, st); });
+  if (want_guiding)
+    prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(w.pcd_out, nullptr, h->W("input_process.pose_embedding.0.weight"),
+                                      h->W("input_process.pose_embedding.0.bias"), rows, w.h1 + (size_t)rows * 64, st); });
+  GE(gemm(h, st, w.h1, 64, h->W("input_process.pose_embedding.2.weight"), 64, w.cat, 256,
+          h->W("input_process.pose_embedding.2.bias"), M, 128, 64, ACT_SIGMOID));
+  GE(gemm(h, st, w.cat, 256, h->W("input_process.combination_extraction.0.weight"), 256, w.c1, 192,
+          h->W("input_process.combination_extraction.0.bias"), M, 192, 256, ACT_SIGMOID));
+  GE(gemm(h, st, w.c1, 192, h->W("input_process.combination_extraction.2.weight"), 192, w.c2, 128,
+          h->W("input_process.combination_extraction.2.bias"), M, 128, 192, ACT_SIGMOID));
+  GE(gemm(h, st, w.c2, 128, h->W("output_process.pose_final.0.weight"), 128, w.f1, 64,
+          h->W("output_process.pose_final.0.bias"), M, 64, 128, ACT_GELU));
+  float* x0 = x0_out ? x0_out : w.x0;
+  prof_launch(h, st, K_DENOISE, [&] { return launch_final3(w.f1, h->W("output_process.pose_final.2.weight"), h->W("output_process.pose_final.2.bias"), rows,
+                               x0, x, w.t_dev, h->sched, h->sched ? h->sched + h->T : nullptr, h->sched ? h->sched + 2 * h->T : nullptr, noise,
+                               sample_out, clip, st); });
+  if (want_guiding) {
+    float* gd = guiding_out ? guiding_out : w.guiding;
+    prof_launch(h, st, K_DENOISE, [&] { return launch_final3(w.f1 + (size_t)rows * 64, h->W("output_process.pose_final.2.weight"),
+                                 h->W("output_process.pose_final.2.bias"), rows, gd, nullptr, nullptr, nullptr, nullptr,
+                                 nullptr, nullptr, nullptr, 0, st); });
+  }
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+__global__ void fill_t_kernel(int64_t* t, int n, int64_t v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+LSDM_API const char* lsdm_version(void) { return "lsdm_b200 0.1 sm_100a"; }
+LSDM_API const char* lsdm_last_error(void) { return g_err.c_str(); }
+
+LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
+  if (!out || !cfg) return fail(LSDM_EINVAL, "null argument");
+  if (cfg->batch_local <= 0 || cfg->batch_global < cfg->batch_local || cfg->batch_offset < 0 ||
+      cfg->batch_offset + cfg->batch_local > cfg->batch_global)
+    return fail(LSDM_EINVAL, "bad batch configuration");
+  if (cfg->n_cats <= 0 || cfg->n_cats > 32) return fail(LSDM_EINVAL, "n_cats must be in 1..32");
+  CK(cudaSetDevice(cfg->device));
+  lsdm_handle* h = new lsdm_handle();
+  h->cfg = *cfg;
+  build_registry(h);
+  // derived (folded) weights: generous upper bound = all backbone conv weights + biases again
+  h->derived_floats = 2000000;
+  cudaError_t e = cudaMalloc(&h->arena, sizeof(float) * (h->arena_floats + h->derived_floats));
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(LSDM_ENOMEM, std::string("cudaMalloc weights: ") + cudaGetErrorString(e));
+  }
+  h->derived = h->arena + h->arena_floats;
+  *out = h;
+  return LSDM_OK;
+}
+
+LSDM_API void lsdm_destroy(lsdm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->arena) cudaFree(h->arena);
+  if (h->sched) cudaFree(h->sched);
+  delete h;
+}
+
+LSDM_API int lsdm_set_batch(lsdm_handle* h, int32_t bl, int32_t bg, int32_t off) {
+  if (!h) return fail(LSDM_EINVAL, "null handle");
+  if (bl <= 0 || bg < bl || off < 0 || off + bl > bg) return fail(LSDM_EINVAL, "bad batch configuration");
+  if (bl != h->cfg.batch_local) h->have_ws = false;
+  h->cfg.batch_local = bl;
+  h->cfg.batch_global = bg;
+  h->cfg.batch_offset = off;
+  h->have_cond = false;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_num_weights(const lsdm_handle* h) { return h ? (int)h->entries.size() : 0; }
+LSDM_API const char* lsdm_weight_key(const lsdm_handle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->entries.size()) return nullptr;
+  return h->entries[i].key.c_str();
+}
+
+LSDM_API int lsdm_load_weight(lsdm_handle* h, const char* key, const void* data, const int64_t* shape, int32_t ndim, void* stream) {
+  if (!h || !key) return fail(LSDM_EINVAL, "null argument");
+  if (strncmp(key, "clip_model.", 11) == 0) return LSDM_OK;  // external text tower, out of scope
+  auto it = h->index.find(key);
+  if (it == h->index.end()) return fail(LSDM_EINVAL, std::string("unexpected state-dict key: ") + key);
+  WEntry& e = h->entries[it->second];
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  bool same = (int)e.shape.size() == ndim;
+  for (int i = 0; same && i < ndim; ++i) same = e.shape[i] == shape[i];
+  if (!same) return fail(LSDM_EINVAL, std::string("shape mismatch for ") + key);
+  if (e.off >= 0) {
+    if (!data) return fail(LSDM_EINVAL, "null data");
+    CK(cudaMemcpyAsync(h->arena + e.off, data, sizeof(float) * n, cudaMemcpyDefault, (cudaStream_t)stream));
+  }
+  e.loaded = true;
+  h->finalized = false;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
+  if (!h) return fail(LSDM_EINVAL, "null handle");
+  for (const auto& e : h->entries)
+    if (!e.loaded && e.off >= 0) return fail(LSDM_ESTATE, "missing state-dict key: " + e.key);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t off = 0;
+  auto take = [&](int64_t n) {
+    float* p = h->derived + off;
+    off += (n + 63) & ~int64_t(63);
+    return p;
+  };
+  const float eps = 1e-5f;
+  auto fold = [&](const std::string& conv, const std::string& bn, int N, int K, float** Wf, float** bf) {
+    *Wf = take((int64_t)N * K);
+    *bf = take(N);
+    prof_launch(h, st, K_OTHER, [&] { return launch_fold_bn(h->W(conv + ".weight"), h->W(conv + ".bias"), h->W(bn + ".weight"), h->W(bn + ".bias"),
+                                  h->W(bn + ".running_mean"), h->W(bn + ".running_var"), N, K, eps, *Wf, *bf, st); });
+  };
+  for (int l = 0; l < 4; ++l) {
+    const SASpec& s = kSA[l];
+    int last = s.cin;
+    for (int i = 0; i < 3; ++i) {
+      std::string p = std::string("pcd_backbone.") + s.name;
+      fold(p + ".mlp_convs." + std::to_string(i), p + ".mlp_bns." + std::to_string(i), s.mlp[i], last, &h->sa_w[l][i],
+           &h->sa_b[l][i]);
+      last = s.mlp[i];
+    }
+    h->sa_wx[l] = take((int64_t)s.mlp[0] * 3);
+    h->sa_wf[l] = take((int64_t)s.mlp[0] * (s.cin - 3));
+    prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(h->sa_w[l][0], s.cin, 0, 3, s.mlp[0], h->sa_wx[l], st); });
+    prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(h->sa_w[l][0], s.cin, 3, s.cin - 3, s.mlp[0], h->sa_wf[l], st); });
+  }
+  for (int l = 0; l < 4; ++l) {
+    const FPSpec& s = kFP[l];
+    int last = s.cin;
+    for (int i = 0; i < s.nl; ++i) {
+      std::string p = std::string("pcd_backbone.") + s.name;
+      fold(p + ".mlp_convs." + std::to_string(i), p + ".mlp_bns." + std::to_string(i), s.mlp[i], last, &h->fp_w[l][i],
+           &h->fp_b[l][i]);
+      last = s.mlp[i];
+    }
+    h->fp_wa[l] = nullptr;
+    if (s.Ca > 0) {
+      h->fp_wa[l] = take((int64_t)s.mlp[0] * s.Ca);
+      prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(h->fp_w[l][0], s.cin, 0, s.Ca, s.mlp[0], h->fp_wa[l], st); });
+    }
+    h->fp_wb[l] = take((int64_t)s.mlp[0] * s.Cb);
+    prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(h->fp_w[l][0], s.cin, s.Ca, s.Cb, s.mlp[0], h->fp_wb[l], st); });
+  }
+  fold("pcd_backbone.conv1", "pcd_backbone.bn1", 128, 128, &h->head_w, &h->head_b);
+  if (off > h->derived_floats) return fail(LSDM_ENOMEM, "derived weight arena too small");
+  CK(cudaPeekAtLastError());
+  h->finalized = true;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_set_schedule(lsdm_handle* h, const float* c1, const float* c2, const float* logvar, const float* sa, const float* s1a,
+                      int32_t T, void* stream) {
+  if (!h || !c1 || !c2 || !logvar || !sa || !s1a || T <= 0) return fail(LSDM_EINVAL, "bad schedule");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->sched && h->T != T) {
+    CK(cudaFree(h->sched));
+    h->sched = nullptr;
+  }
+  if (!h->sched) CK(cudaMalloc(&h->sched, sizeof(float) * 5 * T));
+  h->T = T;
+  const float* src[5] = {c1, c2, logvar, sa, s1a};
+  for (int i = 0; i < 5; ++i) CK(cudaMemcpyAsync(h->sched + (size_t)i * T, src[i], sizeof(float) * T, cudaMemcpyDefault, st));
+  h->have_sched = true;
+  return LSDM_OK;
+}
+
+LSDM_API size_t lsdm_workspace_bytes(const lsdm_handle* h) {
+  if (!h) return 0;
+  Workspace w;
+  return carve(h, nullptr, &w);
+}
+
+LSDM_API int lsdm_set_workspace(lsdm_handle* h, void* workspace, size_t bytes) {
+  if (!h || !workspace) return fail(LSDM_EINVAL, "null argument");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(LSDM_EINVAL, "workspace must be 256-byte aligned");
+  size_t need = carve(h, workspace, &h->ws);
+  if (bytes < need) {
+    h->have_ws = false;
+    return fail(LSDM_EINVAL, "workspace too small: need " + std::to_string(need));
+  }
+  h->have_ws = true;
+  h->have_cond = false;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_encode_conditions(lsdm_handle* h, const float* text, const float* objs, const float* cats, const float* mask_global,
+                           const int64_t* fps_start, void* stream) {
+  GE(check_ready(h, false));
+  if (!text || !objs || !cats || !mask_global || !fps_start) return fail(LSDM_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace& w = h->ws;
+  const int B = h->cfg.batch_local, C = B * NOBJ;
+  CK(cudaMemcpyAsync(w.fps_start, fps_start, sizeof(int64_t) * 4 * C, cudaMemcpyDefault, st));
+  CondWeights cw{h->W("embed_text.0.weight"), h->W("embed_text.0.bias"), h->W("embed_text.2.weight"), h->W("embed_text.2.bias"),
+                 h->W("embed_text.4.weight"), h->W("embed_text.4.bias"), h->W("predict_cat.0.weight"), h->W("predict_cat.0.bias"),
+                 h->W("predict_cat.2.weight"), h->W("predict_cat.2.bias"), h->W("predict_cat.4.weight"), h->W("predict_cat.4.bias"),
+                 h->W("embed_cat.0.weight"), h->W("embed_cat.0.bias"), h->W("attn_layer.q_proj_weight"),
+                 h->W("attn_layer.k_proj_weight"), h->W("attn_layer.in_proj_bias"), h->W("translation_layer.0.weight"),
+                 h->W("translation_layer.0.bias"), h->W("translation_layer.2.weight"), h->W("translation_layer.2.bias"),
+                 h->W("pcd_attention.q_proj_weight"), h->W("pcd_attention.in_proj_bias")};
+  prof_launch(h, st, K_COND, [&] { return launch_cond(cw, text, cats, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, h->cfg.n_cats, w.enc,
+                             w.out_cat, w.attn_w, w.tr, w.qq, st); });
+  HumanWeights hw{};
+  hw.w0 = h->W("human_backbone.de_spiral.0.conv.layer.weight"); hw.b0 = h->W("human_backbone.de_spiral.0.conv.layer.bias");
+  hw.g0 = h->W("human_backbone.de_spiral.0.norm.weight"); hw.be0 = h->W("human_backbone.de_spiral.0.norm.bias");
+  hw.w1 = h->W("human_backbone.de_spiral.1.conv.layer.weight"); hw.b1 = h->W("human_backbone.de_spiral.1.conv.layer.bias");
+  hw.g1 = h->W("human_backbone.de_spiral.1.norm.weight"); hw.be1 = h->W("human_backbone.de_spiral.1.norm.bias");
+  hw.w2 = h->W("human_backbone.de_spiral.2.conv.layer.weight"); hw.b2 = h->W("human_backbone.de_spiral.2.conv.layer.bias");
+  hw.g2 = h->W("human_backbone.de_spiral.2.norm.weight"); hw.be2 = h->W("human_backbone.de_spiral.2.norm.bias");
+  hw.w3 = h->W("human_backbone.de_spiral.3.layer.weight"); hw.b3 = h->W("human_backbone.de_spiral.3.layer.bias");
+  prof_launch(h, st, K_COND, [&] { return launch_human(hw, objs, B, w.human_scratch, w.hm, st); });
+  GE(pointnet2(h, objs, st));
+  SceneWeights sw{h->W("pcd_attention.k_proj_weight"), h->W("pcd_attention.v_proj_weight"), h->W("pcd_attention.in_proj_bias"),
+                  h->W("pcd_attention.out_proj.weight"), h->W("pcd_attention.out_proj.bias"),
+                  h->W("point_wise_trans_layer.0.weight"), h->W("point_wise_trans_layer.0.bias")};
+  prof_launch(h, st, K_SCENE, [&] { return launch_point_attention(sw, w.backbone, w.attn_w, w.qq, B, w.pa, w.pw, st); });
+  prof_launch(h, st, K_SCENE, [&] { return launch_scene_mix(w.pw, w.hm, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, w.pcd_out, st); });
+  CK(cudaPeekAtLastError());
+  h->have_cond = true;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_denoise_step(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,
+                      float* guiding_out, int32_t clip_denoised, void* stream) {
+  GE(check_ready(h, true));
+  if (!h->have_sched) return fail(LSDM_ESTATE, "no schedule (lsdm_set_schedule)");
+  if (!x || !t || !noise || !sample_out) return fail(LSDM_EINVAL, "null argument");
+  return step_core(h, x, t, noise, sample_out, x0_out, guiding_out, true, clip_denoised, (cudaStream_t)stream);
+}
+
+LSDM_API int lsdm_forward(lsdm_handle* h, float* x, const int64_t* t, float* out_cat, float* x0, float* guiding, void* stream) {
+  GE(check_ready(h, true));
+  if (!x || !t || !x0) return fail(LSDM_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GE(step_core(h, x, t, nullptr, nullptr, x0, guiding, true, 0, st));
+  if (out_cat)
+    CK(cudaMemcpyAsync(out_cat, h->ws.out_cat, sizeof(float) * h->cfg.batch_local * h->cfg.n_cats, cudaMemcpyDeviceToDevice, st));
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const float* objs, const float* cats, const float* mask_global,
+                     const int64_t* fps_start_all, const float* noise_all, int32_t t_first, int32_t n_steps, int32_t hoisted,
+                     int32_t clip_denoised, float* x0_out, float* guiding_out, void* stream) {
+  GE(check_ready(h, false));
+  if (!h->have_sched) return fail(LSDM_ESTATE, "no schedule (lsdm_set_schedule)");
+  if (!x || !fps_start_all || !noise_all) return fail(LSDM_EINVAL, "null argument");
+  if (n_steps <= 0 || t_first >= h->T || t_first - n_steps + 1 < 0) return fail(LSDM_EINVAL, "bad timestep range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = h->cfg.batch_local, C = B * NOBJ;
+  const size_t per = (size_t)B * NPTS * 3;
+  // device-side timestep vector (the reference builds th.tensor([i]*B) on the host every step, gaussian_diffusion.py:737)
+  int64_t* tvec = h->ws.t_dev;
+  for (int k = 0; k < n_steps; ++k) {
+    if (!hoisted || k == 0)
+      GE(lsdm_encode_conditions(h, text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, stream));
+    prof_launch(h, st, K_OTHER, [&] {
+      fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(tvec, B, (int64_t)(t_first - k));
+      return 1;
+    });
+    const bool last = (k == n_steps - 1);
+    // STRICT recomputes the guiding points every step like the reference; hoisted only needs them at the end
+    const bool want_guiding = !hoisted || last;
+    GE(step_core(h, x, tvec, noise_all + (size_t)k * per, x, last ? x0_out : nullptr, last ? guiding_out : nullptr,
+                 want_guiding, clip_denoised, st));
+  }
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_get_out_cat(lsdm_handle* h, float* out_cat, void* stream) {
+  GE(check_ready(h, true));
+  CK(cudaMemcpyAsync(out_cat, h->ws.out_cat, sizeof(float) * h->cfg.batch_local * h->cfg.n_cats, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
+  return LSDM_OK;
+}
+LSDM_API int lsdm_get_pcd_out(lsdm_handle* h, float* pcd_out, void* stream) {
+  GE(check_ready(h, true));
+  CK(cudaMemcpyAsync(pcd_out, h->ws.pcd_out, sizeof(float) * h->cfg.batch_local * NPTS * 3, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_q_sample(lsdm_handle* h, const float* x_start, const int64_t* t, const float* noise, float* x_t, void* stream) {
+  GE(check_ready(h, false));
+  if (!h->have_sched) return fail(LSDM_ESTATE, "no schedule (lsdm_set_schedule)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(h->ws.t_dev, t, sizeof(int64_t) * h->cfg.batch_local, cudaMemcpyDefault, st));
+  prof_launch(h, st, K_DENOISE, [&] { return launch_q_sample(x_start, h->ws.t_dev, noise, h->sched + 3 * h->T, h->sched + 4 * h->T, h->cfg.batch_local, x_t, st); });
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_chamfer(lsdm_handle* h, const float* x, const float* y, int32_t batch, int32_t n, int32_t m, float* sums, void* stream) {
+  if (!h || !x || !y || !sums || batch <= 0 || n <= 0 || m <= 0 || n > 4096 || m > 4096) return fail(LSDM_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_launch(h, st, K_OTHER, [&] { return launch_chamfer(x, y, batch, n, m, sums, st); });
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_cat_loss(lsdm_handle* h, const float* probs, const float* target_cat, int32_t batch, float* sum, void* stream) {
+  if (!h || !probs || !target_cat || !sum || batch <= 0) return fail(LSDM_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_launch(h, st, K_OTHER, [&] { return launch_cat_loss(probs, target_cat, batch, h->cfg.n_cats, sum, st); });
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, size_t dst_bytes, void* stream) {
+  if (!h || !name || !h->have_ws) return fail(LSDM_EINVAL, "bad argument");
+  const Workspace& w = h->ws;
+  const int64_t B = h->cfg.batch_local, C = B * NOBJ;
+  struct Tap { const char* n; const void* p; int64_t count; size_t esz; };
+  const Tap taps[] = {
+      {"backbone", w.backbone, C * NPTS * 3, 4}, {"hm", w.hm, B * NPTS * 3, 4}, {"attn_w", w.attn_w, B * NOBJ, 4},
+      {"tr", w.tr, C * TRANS, 4}, {"enc", w.enc, B * LAT, 4}, {"pa", w.pa, C * TRANS, 4}, {"pw", w.pw, C * NPTS * 3, 4},
+      {"emb_cat", w.cat, B * NPTS * 256, 4}, {"pcd_out", w.pcd_out, B * NPTS * 3, 4}, {"out_cat", w.out_cat, B * h->cfg.n_cats, 4},
+      {"fps_idx0", w.idx[0], C * 1024, 4}, {"fps_idx1", w.idx[1], C * 256, 4}, {"fps_idx2", w.idx[2], C * 64, 4},
+      {"fps_idx3", w.idx[3], C * 16, 4}, {"ball_idx0", w.grp[0], C * 1024 * 32, 4}, {"ball_idx1", w.grp[1], C * 256 * 32, 4},
+      {"ball_idx2", w.grp[2], C * 64 * 32, 4}, {"ball_idx3", w.grp[3], C * 16 * 32, 4}, {"l1_feat", w.feat[1], C * 1024 * 64, 4},
+      {"l2_feat", w.feat[2], C * 256 * 128, 4}, {"l3_feat", w.feat[3], C * 64 * 256, 4}, {"l4_feat", w.feat[4], C * 16 * 512, 4},
+      {"fp4_feat", w.g3, C * 64 * 256, 4}, {"fp3_feat", w.g2, C * 256 * 256, 4}, {"fp2_feat", w.g1, C * 1024 * 128, 4},
+      {"nn_idx3", w.nn_idx[3], C * 1024 * 3, 4}, {"nn_w3", w.nn_w[3], C * 1024 * 3, 4}, {"nn_idx0", w.nn_idx[0], C * 64 * 3, 4},
+      {"x0", w.x0, B * NPTS * 3, 4}, {"guiding", w.guiding, B * NPTS * 3, 4}, {"s256", w.s256, B * 256, 4},
+  };
+  for (const Tap& t : taps) {
+    if (strcmp(t.n, name) == 0) {
+      size_t bytes = (size_t)t.count * t.esz;
+      if (dst) {
+        if (dst_bytes < bytes) return fail(LSDM_EINVAL, "destination too small");
+        cudaError_t e = cudaMemcpyAsync(dst, t.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(LSDM_ECUDA, cudaGetErrorString(e));
+      }
+      return t.count;
+    }
+  }
+  return fail(LSDM_EINVAL, std::string("unknown tap: ") + name);
+}
+
+LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h) { return h ? h->launches : 0; }
+
+LSDM_API int lsdm_profile_begin(lsdm_handle* h) {
+  if (!h) return fail(LSDM_EINVAL, "null handle");
+  for (auto& r : h->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->prof.clear();
+  h->gemm_flops = 0.0;
+  h->profiling = true;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_profile_end(lsdm_handle* h, double* ms_by_class, int64_t* launches_by_class, int32_t n_class,
+                              double* gemm_flops) {
+  if (!h || !ms_by_class || !launches_by_class || n_class < K_NCLASS) return fail(LSDM_EINVAL, "bad argument");
+  h->profiling = false;
+  for (int i = 0; i < n_class; ++i) ms_by_class[i] = 0.0, launches_by_class[i] = 0;
+  for (auto& r : h->prof) {
+    CK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_class[r.cls] += ms;
+    launches_by_class[r.cls] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->prof.clear();
+  if (gemm_flops) *gemm_flops = h->gemm_flops;
+  return LSDM_OK;
+}
+
+}  // extern "C"

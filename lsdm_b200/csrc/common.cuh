@@ -1,0 +1,67 @@
+// Shared device/host helpers for the lsdm_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace lsdm {
+
+constexpr int NPTS = 1024;  // points per cloud
+constexpr int NOBJ = 9;     // object slots per scene
+constexpr int CLIP = 512;
+constexpr int LAT = 128;
+constexpr int CATEMB = 32;
+constexpr int TRANS = 12;
+constexpr int NHEAD = 8;
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SILU = 4 };
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.0f);
+  if (ACT == ACT_GELU) return gelu_erf(x);
+  if (ACT == ACT_SIGMOID) return sigmoidf_(x);
+  if (ACT == ACT_SILU) return x * sigmoidf_(x);
+  return x;
+}
+
+__device__ __forceinline__ float apply_act_rt(float x, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    case ACT_GELU: return gelu_erf(x);
+    case ACT_SIGMOID: return sigmoidf_(x);
+    case ACT_SILU: return x * sigmoidf_(x);
+    default: return x;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Squared distance in the reference's expanded form (model/pcd_backbone/pointnet2_utils.py:19-38):
+// d = (-2 * (a.b)) + |a|^2 + |b|^2, accumulated in that order, no re-association.
+__device__ __forceinline__ float sqdist_expanded(float ax, float ay, float az, float a2, float bx, float by, float bz,
+                                                 float b2) {
+  float dot = __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
+  float d = __fmul_rn(-2.0f, dot);
+  d = __fadd_rn(d, a2);
+  d = __fadd_rn(d, b2);
+  return d;
+}
+// |p|^2 as torch.sum(p**2, -1): (x*x + y*y) + z*z without FMA contraction.
+__device__ __forceinline__ float sqnorm3(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+}  // namespace lsdm

@@ -1,0 +1,27 @@
+// Generic "linear layer" GEMM interface used by every dense layer of the path:
+//   C[M,N] = act(A[M,K] . W[N,K]^T + bias)       (A and W row-major, K contiguous: PyTorch's layout)
+// optionally batched (blockIdx.z) and optionally reduced by max over groups of 32 consecutive rows
+// (the PointNet++ set-abstraction pooling, reference pointnet2_utils.py:197).
+#pragma once
+#include "common.cuh"
+
+namespace lsdm {
+
+struct GemmArgs {
+  const float* A;
+  int64_t lda, strideA;
+  const float* W;
+  int64_t ldw, strideW;
+  float* C;
+  int64_t ldc, strideC;
+  const float* bias;
+  int bias_mode;  // 0 none, 1 per output column, 2 per output row
+  int M, N, K, batch;
+  int act;        // lsdm::Act
+  int group_max;  // 1: C has M/32 rows, row g = max over rows [32g, 32g+32) of the activated tile
+};
+
+// Launches the GEMM on `stream`; returns the number of kernels launched (1) or a negative value on bad arguments.
+int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+
+}  // namespace lsdm

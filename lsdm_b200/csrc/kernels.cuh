@@ -1,0 +1,88 @@
+// Launch prototypes of every non-GEMM kernel on the path.  Each launcher enqueues on `st` and
+// returns the number of kernels launched.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace lsdm {
+
+// ---- pointnet_select.cu ---------------------------------------------------------------------
+int launch_fps4(const float* xyz0, const int64_t* start, int n_clouds, int* idx1, int* idx2, int* idx3, int* idx4,
+                float* xyz1, float* xyz2, float* xyz3, float* xyz4, cudaStream_t st);
+int launch_ball_query(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group,
+                      cudaStream_t st);
+int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, int S, int* nn_idx, float* nn_w,
+                    cudaStream_t st);
+
+// ---- pointnet_glue.cu -----------------------------------------------------------------------
+// h1[(c,s,k), ch] = relu(P[c*N + j, ch] + Wx[ch,:] . (xyz[c,j] - new_xyz[c,s])),  j = group[c,s,k]
+// P == nullptr (sa1): P is replaced by bias[ch] + Wf[ch,0:3] . xyz[c,j]   (features are the coordinates)
+int launch_sa_gather(const float* P, const float* Wx, const float* Wf3, const float* bias, const float* xyz,
+                     const float* new_xyz, const int* group, int n_clouds, int N, int S, int C1, float* h1,
+                     cudaStream_t st);
+// h[(c,n), ch] = relu(Pa[(c,n), ch] + sum_k w[c,n,k] * Pb[c*S + idx[c,n,k], ch]);  Pa == nullptr -> bias[ch]
+int launch_fp_combine(const float* Pa, const float* bias, const float* Pb, const int* nn_idx, const float* nn_w,
+                      int n_clouds, int N, int S, int C1, float* h, cudaStream_t st);
+// out[row, 0:3] = h[row, 0:128] . W[3,128]^T + b
+int launch_head3(const float* h, const float* W, const float* b, int64_t rows, float* out, cudaStream_t st);
+// eval-mode BatchNorm folded into the preceding 1x1 conv: Wf = W * s, bf = (b - mean) * s + beta, s = gamma / sqrt(var + eps)
+int launch_fold_bn(const float* W, const float* b, const float* gamma, const float* beta, const float* mean,
+                   const float* var, int N, int K, float eps, float* Wf, float* bf, cudaStream_t st);
+int launch_copy_cols(const float* src, int ld_src, int col0, int ncols, int rows, float* dst, cudaStream_t st);
+
+// ---- cond.cu --------------------------------------------------------------------------------
+struct CondWeights {
+  const float *et0_w, *et0_b, *et2_w, *et2_b, *et4_w, *et4_b;  // embed_text 512->256->256->128
+  const float *pc0_w, *pc0_b, *pc2_w, *pc2_b, *pc4_w, *pc4_b;  // predict_cat 128->64->32->C
+  const float *ec_w, *ec_b;                                    // embed_cat C->32
+  const float *aq_w, *ak_w, *a_inb;                            // attn_layer q_proj [128,128], k_proj [128,32], in_proj_bias [384]
+  const float *tl0_w, *tl0_b, *tl2_w, *tl2_b;                  // translation_layer 160->128->12
+  const float *pq_w, *p_inb;                                   // pcd_attention q_proj [12,12], in_proj_bias [36]
+};
+// one CTA per local sample: enc[B,128], out_cat[B,C], attn_w[B,9], tr[B,9,12], qq[B,9,12]
+int launch_cond(const CondWeights& w, const float* text, const float* cats, const float* mask_global, int B, int Bg,
+                int b_off, int n_cats, float* enc, float* out_cat, float* attn_w, float* tr, float* qq, cudaStream_t st);
+// ts[B,128] = W2 silu(W1 pe[t] + b1) + b2 ; also writes s[B,256] = [ts || enc] and H1[B*256,128] = gelu(s*w0 + b0)
+int launch_time_embed(const float* pe, const float* w1, const float* b1, const float* w2, const float* b2,
+                      const int64_t* t, const float* enc, const float* up0_w, const float* up0_b, int B, float* s256,
+                      float* H1, cudaStream_t st);
+struct HumanWeights {
+  const float *w0, *b0, *g0, *be0;  // 3->64 + GroupNorm(8)
+  const float *w1, *b1, *g1, *be1;  // 64->64
+  const float *w2, *b2, *g2, *be2;  // 64->64 on the first 655 points
+  const float *w3, *b3;             // 64->3
+};
+// POSA decoder, one CTA per sample; scratch[B,2,1024,64]; hm[B,1024,3]
+int launch_human(const HumanWeights& w, const float* objs /*[B,9,1024,3], slot 0 used*/, int B, float* scratch,
+                 float* hm, cudaStream_t st);
+
+// ---- scene.cu -------------------------------------------------------------------------------
+struct SceneWeights {
+  const float *pk_w, *pv_w, *p_inb;  // pcd_attention k_proj [12,3], v_proj [12,3], in_proj_bias [36]
+  const float *po_w, *po_b;          // out_proj [12,12]
+  const float *pt_w, *pt_b;          // point_wise_trans_layer [3,15]
+};
+// per (b,o'): scramble #1, collapsed 12-head attention, pointwise 15->3 GELU -> pw[B,9,1024,3], pa[B,9,12]
+int launch_point_attention(const SceneWeights& w, const float* backbone /*[9B,1024,3]*/, const float* attn_w,
+                           const float* qq, int B, float* pa, float* pw, cudaStream_t st);
+// scramble #2 (global mask), sum over objects, average with human feature -> pcd_out[B,1024,3]
+int launch_scene_mix(const float* pw, const float* hm, const float* mask_global, int B, int Bg, int b_off, float* pcd_out,
+                     cudaStream_t st);
+
+// ---- denoise.cu -----------------------------------------------------------------------------
+// xin = x (+ pcd_out, written back to x when add != nullptr); h1[row,64] = sigmoid(E0 xin + b)
+int launch_pose_embed0(float* x, const float* add, const float* w, const float* b, int64_t rows, float* h1,
+                       cudaStream_t st);
+// x0 = gelu(F2 f1 + b) (64->3); optional posterior + ancestral sample (gaussian_diffusion.py:266-269,545-560):
+// sample = c1[t] x0 + c2[t] xin + [t != 0] exp(0.5 logvar[t]) noise
+int launch_final3(const float* f1, const float* w, const float* b, int64_t rows, float* x0_out, const float* xin,
+                  const int64_t* t, const float* c1, const float* c2, const float* logvar, const float* noise,
+                  float* sample_out, int clip_denoised, cudaStream_t st);
+int launch_q_sample(const float* x0, const int64_t* t, const float* noise, const float* sa, const float* s1a, int B,
+                    float* xt, cudaStream_t st);
+
+// ---- loss.cu --------------------------------------------------------------------------------
+int launch_chamfer(const float* x, const float* y, int B, int n, int m, float* sums, cudaStream_t st);
+int launch_cat_loss(const float* probs, const float* target, int B, int C, float* sum, cudaStream_t st);
+
+}  // namespace lsdm

@@ -1,0 +1,264 @@
+"""``SceneDiffusionModel`` -- drop-in mirror of the reference's ``model/sdm.py:18-218``.
+
+Same constructor keywords, same ``state_dict`` keys and shapes, same
+``forward(x, mask, timesteps, given_objs, given_cats, y=None, force_mask=False) -> (out_cat, x0)``
+including its side effects: ``x`` is mutated in place (``x += pcd_out``, reference sdm.py:204),
+``saved_cat`` and ``saved_guiding_points`` are set, and the four ``torch.randint`` FPS start draws
+of ``farthest_point_sample`` (reference pointnet2_utils.py:72) are consumed from the CPU generator
+in the same order and shapes.
+
+The ``nn`` sub-modules below only HOLD parameters (so checkpoints load strictly and optimisers /
+``.parameters()`` work); none of their ``forward`` methods is ever called.  All arithmetic runs in
+``liblsdm_b200.so`` through :class:`lsdm_b200.engine.Engine`; without the CUDA library or a GPU,
+``forward`` raises -- there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..synthetic import positional_table
+
+N_POINTS, N_OBJ = 1024, 9
+FPS_LEVEL_N = (1024, 1024, 256, 64)
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter holder: the arithmetic of this layer runs in liblsdm_b200.so")
+
+
+class _PositionalEncoding(_Holder):
+    def __init__(self, d_model, max_len=5000):
+        super().__init__()
+        self.register_buffer("pe", positional_table(max_len, d_model))
+
+
+class _TimestepEmbedder(_Holder):
+    def __init__(self, latent_dim, sequence_pos_encoder):
+        super().__init__()
+        self.sequence_pos_encoder = sequence_pos_encoder
+        self.time_embed = nn.Sequential(nn.Linear(latent_dim, latent_dim), nn.SiLU(), nn.Linear(latent_dim, latent_dim))
+
+
+class _SetAbstraction(_Holder):
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for c in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, c, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(c))
+            last = c
+
+
+class _FeaturePropagation(_Holder):
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for c in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, c, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(c))
+            last = c
+
+
+class _PointNet2Backbone(_Holder):
+    """Parameter layout of reference model/pcd_backbone/pointnet2.py:43-59."""
+
+    def __init__(self, num_classes=3, dimension=3):
+        super().__init__()
+        self.sa1 = _SetAbstraction(dimension + 3, [32, 32, 64])
+        self.sa2 = _SetAbstraction(64 + 3, [64, 64, 128])
+        self.sa3 = _SetAbstraction(128 + 3, [128, 128, 256])
+        self.sa4 = _SetAbstraction(256 + 3, [256, 256, 512])
+        self.fp4 = _FeaturePropagation(768, [256, 256])
+        self.fp3 = _FeaturePropagation(384, [256, 256])
+        self.fp2 = _FeaturePropagation(320, [256, 128])
+        self.fp1 = _FeaturePropagation(128, [128, 128, 128])
+        self.conv1 = nn.Conv1d(128, 128, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.drop1 = nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(128, num_classes, 1)
+
+
+class _GraphBlock(_Holder):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = _Holder()
+        self.conv.layer = nn.Linear(cin, cout)
+        nn.init.xavier_uniform_(self.conv.layer.weight)
+        nn.init.constant_(self.conv.layer.bias, 0)
+        self.norm = nn.GroupNorm(8, cout)
+
+
+class _SpiralOut(_Holder):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.layer = nn.Linear(cin, cout)
+        nn.init.xavier_uniform_(self.layer.weight)
+        nn.init.constant_(self.layer.bias, 0)
+
+
+class _HumanDecoder(_Holder):
+    """Parameter layout of reference posa/posa_models.py:292-317 (seq_length=1)."""
+
+    def __init__(self):
+        super().__init__()
+        self.de_spiral = nn.Sequential(_GraphBlock(3, 64), _GraphBlock(64, 64), _GraphBlock(64, 64), _SpiralOut(64, 3))
+
+
+class _InputProcess(_Holder):
+    def __init__(self, input_feats, extract_dim):
+        super().__init__()
+        self.pose_embedding = nn.Sequential(nn.Linear(input_feats, extract_dim // 2), nn.Sigmoid(),
+                                            nn.Linear(extract_dim // 2, extract_dim), nn.Sigmoid())
+        self.combination_extraction = nn.Sequential(nn.Linear(extract_dim * 2, int(extract_dim * 1.5)), nn.Sigmoid(),
+                                                    nn.Linear(int(extract_dim * 1.5), extract_dim), nn.Sigmoid())
+
+
+class _OutputProcess(_Holder):
+    def __init__(self, input_feats, extract_dim):
+        super().__init__()
+        self.pose_final = nn.Sequential(nn.Linear(extract_dim, extract_dim // 2), nn.GELU(),
+                                        nn.Linear(extract_dim // 2, input_feats), nn.GELU())
+
+
+class SceneDiffusionModel(nn.Module):
+    def __init__(self, seg_len=256, modality='text', clip_version='ViT-B/32', clip_dim=768, dropout=0.1, n_layer=6,
+                 n_head=8, f_vert=64, dim_ff=512, cat_emb=32, mesh_ds_dir="data/mesh_ds", posa_path=None, latent_dim=128,
+                 cond_mask_prob=1.0, device=0, vert_dims=655, obj_cat=8, data_rep='rot6d', njoints=251, use_cuda=True,
+                 pcd_points=1024, pcd_dim=128, xyz_dim=3, max_cats=13, translation_params=12, pcd_backbone_type="PNT2",
+                 human_backbone_type="POSA", text_encoder_type="CLIP", **kwargs) -> None:
+        super().__init__()
+        # The kernels are specialised to the factory configuration of reference util/model_util.py:26-73.
+        if (latent_dim, clip_dim, pcd_points, pcd_dim, xyz_dim, n_head, cat_emb, translation_params) != (128, 512, 1024, 3, 3, 8, 32, 12):
+            raise NotImplementedError("lsdm_b200 implements the reference's factory configuration "
+                                      "(latent 128, clip 512, 1024 points, pcd_dim 3, 8 heads, cat_emb 32, 12 translation params)")
+        if pcd_backbone_type != "PNT2" or human_backbone_type != "POSA":
+            raise NotImplementedError("only the default PNT2 / POSA backbones are on the accelerated path")
+        if data_rep not in ('rot6d', 'xyz', 'hml_vec'):
+            raise ValueError(data_rep)
+        self.seg_len, self.pcd_points, self.clip_version, self.clip_dim = seg_len, pcd_points, clip_version, clip_dim
+        self.latent_dim, self.pcd_dim, self.xyz_dim, self.extract_dim = latent_dim, pcd_dim, xyz_dim, latent_dim
+        self.dropout, self.cond_mask_prob, self.data_rep = dropout, cond_mask_prob, data_rep
+        self.input_feats = vert_dims * obj_cat
+        self.n_head, self.translation_params, self.text_encoder_type = n_head, translation_params, text_encoder_type
+        self.max_cats = max_cats
+        self.device = "cuda:{}".format(device) if use_cuda else "cpu"
+        self.modality = modality
+        assert self.modality in ['text', 'audio', None]
+
+        self.sequence_pos_encoder = _PositionalEncoding(latent_dim)
+        self.embed_timestep = _TimestepEmbedder(latent_dim, self.sequence_pos_encoder)
+        self.saved_cat = None
+        self.embed_text = nn.Sequential(nn.Linear(clip_dim, clip_dim // 2), nn.GELU(), nn.Linear(clip_dim // 2, latent_dim * 2),
+                                        nn.GELU(), nn.Linear(latent_dim * 2, latent_dim), nn.GELU())
+        self.embed_cat = nn.Sequential(nn.Linear(max_cats, cat_emb), nn.GELU())
+        self.predict_cat = nn.Sequential(nn.Linear(latent_dim, latent_dim // 2), nn.GELU(), nn.Linear(latent_dim // 2, latent_dim // 4),
+                                         nn.GELU(), nn.Linear(latent_dim // 4, max_cats), nn.GELU(), nn.Softmax(dim=2))
+        self.attn_layer = nn.MultiheadAttention(embed_dim=latent_dim, num_heads=n_head, kdim=cat_emb, vdim=pcd_points * pcd_dim,
+                                                batch_first=True)
+        self.translation_layer = nn.Sequential(nn.Linear(latent_dim + cat_emb, latent_dim), nn.GELU(),
+                                               nn.Linear(latent_dim, translation_params), nn.GELU())
+        self.point_wise_trans_layer = nn.Sequential(nn.Linear(translation_params + xyz_dim, xyz_dim), nn.GELU())
+        self.pcd_attention = nn.MultiheadAttention(embed_dim=translation_params, num_heads=translation_params, kdim=xyz_dim,
+                                                   vdim=xyz_dim, batch_first=True)
+        self.pcd_backbone = _PointNet2Backbone(pcd_dim)
+        self.human_backbone = _HumanDecoder()
+        self.upsampling_layer = nn.Sequential(nn.Linear(1, 128), nn.GELU(), nn.Linear(128, 512), nn.GELU(),
+                                              nn.Linear(512, pcd_points), nn.GELU())
+        self.combine_extraction = nn.Sequential(nn.Linear(latent_dim * 2, latent_dim), nn.GELU())
+        self.input_process = _InputProcess(xyz_dim, latent_dim)
+        self.output_process = _OutputProcess(xyz_dim, latent_dim)
+        self.saved_guiding_points = None
+
+        # engine state (not part of the state dict)
+        self._engine = None
+        self._engine_sig = None
+        self._weights_sig = None
+        self._shard = None  # (batch_global, batch_offset)
+        self._text_encoder = None
+        if use_cuda and torch.cuda.is_available():
+            self.to(self.device)
+
+    # ------------------------------------------------------------------ reference-surface helpers
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts an unmodified reference checkpoint: ``clip_model.*`` (external CLIP tower) is dropped."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("clip_model.")}
+        out = super().load_state_dict(sd, strict=strict, **kw)
+        self._weights_sig = None
+        return out
+
+    def set_text_encoder(self, fn):
+        """``fn(list[str]) -> [B,512]`` float tensor; stands in for the frozen CLIP text tower (out of scope)."""
+        self._text_encoder = fn
+
+    def set_shard(self, batch_global=None, batch_offset=0):
+        """Data-parallel sharding: this process holds samples [offset, offset+B) of a global batch; ``mask`` arguments
+        must then be the GLOBAL ``[batch_global, 9]`` mask (the reference's mask scrambles index it)."""
+        self._shard = None if batch_global is None else (int(batch_global), int(batch_offset))
+
+    def _encode_text(self, y):
+        if torch.is_tensor(y):
+            return y.float()
+        if self._text_encoder is None:
+            raise NotImplementedError("text strings need a CLIP ViT-B/32 text tower, which is outside the accelerated path; "
+                                      "pass the [B,512] text embedding as `y` or install one with set_text_encoder()")
+        return self._text_encoder(list(y)).float()
+
+    def _sig(self):
+        return sum(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + 7919 * sum(
+            t.data_ptr() % 1000003 for t in self.parameters())
+
+    def engine(self, batch_local, device):
+        """The ``lsdm_handle`` owner for this batch size / shard; (re)uploads weights when they changed."""
+        from ..engine import Engine
+
+        bg, off = self._shard if self._shard is not None else (batch_local, 0)
+        sig = (int(batch_local), bg, off, str(device))
+        if self._engine is None or self._engine_sig[3] != sig[3]:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(batch_local, self.max_cats, device, bg, off)
+            self._weights_sig = None
+        elif self._engine_sig != sig:
+            self._engine.set_batch(batch_local, bg, off)
+        self._engine_sig = sig
+        ws = self._sig()
+        if self._weights_sig != ws:
+            self._engine.load_state_dict(self.state_dict())
+            self._weights_sig = ws
+        return self._engine
+
+    def draw_fps_starts(self, batch_local):
+        """The four CPU-generator draws of reference pointnet2_utils.py:72, at GLOBAL shape, sliced to the shard."""
+        bg, off = self._shard if self._shard is not None else (batch_local, 0)
+        draws = [torch.randint(0, n, (bg * N_OBJ,), dtype=torch.long) for n in FPS_LEVEL_N]
+        return torch.stack([d.view(bg, N_OBJ)[off:off + batch_local].reshape(-1) for d in draws])
+
+    def encode(self, mask, given_objs, given_cats, y, fps_start=None):
+        """Step-invariant part of forward (reference sdm.py:147-203).  Returns the engine."""
+        if self.training:
+            raise NotImplementedError("train-mode BatchNorm statistics / dropout are not on the accelerated path yet; call .eval()")
+        B = given_objs.shape[0]
+        eng = self.engine(B, given_objs.device if given_objs.is_cuda else torch.device(self.device))
+        if fps_start is None:
+            fps_start = self.draw_fps_starts(B)
+        eng.encode_conditions(self._encode_text(y), given_objs, given_cats, mask, fps_start)
+        return eng
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, mask, timesteps, given_objs, given_cats, y=None, force_mask=False):
+        """
+        x: [bs, 1024, 3] noisy target cloud (MUTATED in place); mask: [bs, 9] (global mask when sharded);
+        timesteps: [bs]; given_objs: [bs, 9, 1024, 3]; given_cats: [bs, 9, max_cats]; y: list[str] or [bs, 512] embedding.
+        Returns (out_cat [bs, 1, max_cats], x0 [bs, 1024, 3]).
+        """
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise ValueError("x must be a contiguous float32 CUDA tensor (it is updated in place)")
+        eng = self.encode(mask, given_objs, given_cats, y)
+        out_cat, x0, guiding = eng.forward(x, timesteps)
+        self.saved_cat = out_cat.unsqueeze(1)
+        self.saved_guiding_points = guiding
+        return self.saved_cat, x0

@@ -1,0 +1,157 @@
+"""CPU tests of the host side: C-ABI surface, reference-shaped Python API, schedule tables, sharding plan (gloo, world 2)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from lsdm_b200 import synthetic as syn
+from util import golden, rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    from lsdm_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "lsdm_b200.h")).read()
+    declared = set(re.findall(r"LSDM_API[^;()]*?\b(lsdm_\w+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = _lib.load()  # no compute calls: loading needs no GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert b"sm_100a" in lib.lsdm_version()
+
+
+def test_cabi_argument_errors_without_gpu():
+    from lsdm_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.lsdm_create(None, None) == _lib.EINVAL
+    assert b"null" in lib.lsdm_last_error()
+    assert lib.lsdm_num_weights(None) == 0
+    assert lib.lsdm_workspace_bytes(None) == 0
+    assert lib.lsdm_launch_count(None) == 0
+
+
+def test_state_dict_contract():
+    from lsdm_b200.util.model_util import create_model_and_diffusion
+
+    for datatype, cats in (("proxd", 13), ("humanise", 11)):
+        model, diffusion = create_model_and_diffusion(datatype)
+        sd = syn.make_state_dict(0, "wellcond", cats)
+        own = model.state_dict()
+        assert set(own) == set(sd)
+        for k in own:
+            assert own[k].shape == sd[k].shape, k
+        ckpt = dict(sd)
+        ckpt["clip_model.positional_embedding"] = torch.zeros(77, 512)  # reference checkpoints carry the CLIP tower
+        model.load_state_dict(ckpt)  # strict
+        assert diffusion.num_timesteps == 1000
+        assert hasattr(diffusion, "ddim_sample_loop")
+        assert sum(p.numel() for p in model.parameters()) == 2418986 - (13 - cats) * (32 + 32 + 1)
+
+
+def test_schedule_tables_match_reference():
+    from lsdm_b200.diffusion import gaussian_diffusion as gd
+    from lsdm_b200.diffusion.respace import SpacedDiffusion, space_timesteps
+
+    g = golden("tables")
+    cos = gd.get_named_beta_schedule("cosine", 1000)
+    for tag, sections, betas, T0 in (("full", [1000], cos, 1000), ("ddim100", "ddim100", cos, 1000), ("s100", [100], cos, 1000),
+                                     ("s10_15_20", [10, 15, 20], gd.get_named_beta_schedule("linear", 300), 300)):
+        keep = space_timesteps(T0, sections)
+        d = SpacedDiffusion(use_timesteps=keep, betas=betas, model_mean_type=gd.ModelMeanType.START_X,
+                            model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
+        assert sorted(keep) == list(g[tag + ".keep"])
+        assert d.timestep_map == list(g[tag + ".timestep_map"])
+        for k in ("betas", "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped", "posterior_variance",
+                  "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"):
+            np.testing.assert_allclose(getattr(d, k), g[tag + "." + k], rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        space_timesteps(1000, "ddim999")
+
+
+def test_unsupported_options_fail_loudly():
+    from lsdm_b200.diffusion import gaussian_diffusion as gd
+    from lsdm_b200.model.sdm import SceneDiffusionModel
+    from lsdm_b200.util.model_util import get_default_model_proxd
+
+    b = gd.get_named_beta_schedule("cosine", 10)
+    with pytest.raises(NotImplementedError):
+        gd.GaussianDiffusion(betas=b, model_mean_type=gd.ModelMeanType.EPSILON, model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
+    with pytest.raises(NotImplementedError):
+        gd.GaussianDiffusion(betas=b, model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.LEARNED, loss_type=gd.LossType.MSE)
+    with pytest.raises(NotImplementedError):
+        SceneDiffusionModel(**{**get_default_model_proxd(), "latent_dim": 256})
+    m = SceneDiffusionModel(**get_default_model_proxd())
+    inp = syn.make_inputs(1, 1)
+    with pytest.raises(ValueError):  # CPU tensors: no fallback
+        m(inp["x_T"], inp["mask"], torch.zeros(1, dtype=torch.long), inp["given_objs"], inp["given_cats"], inp["text_emb"])
+    with pytest.raises(NotImplementedError):
+        m._encode_text(["a chair"])
+
+
+def test_fps_start_draws_follow_reference_order_and_shard():
+    from lsdm_b200.model.sdm import SceneDiffusionModel
+    from lsdm_b200.util.model_util import get_default_model_proxd
+
+    m = SceneDiffusionModel(**get_default_model_proxd())
+    torch.manual_seed(5)
+    ref = [torch.randint(0, n, (4 * 9,), dtype=torch.long) for n in (1024, 1024, 256, 64)]
+    torch.manual_seed(5)
+    full = m.draw_fps_starts(4)
+    assert torch.equal(full, torch.stack(ref))
+    m.set_shard(4, 1)
+    torch.manual_seed(5)
+    part = m.draw_fps_starts(2)
+    assert torch.equal(part, torch.stack([r.view(4, 9)[1:3].reshape(-1) for r in ref]))
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lsdm_oracle as O
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    B = 4
+    per = B // world
+    lo = rank * per
+    sd = syn.make_state_dict(0, "wellcond")
+    inp = syn.make_inputs(9, B)  # every rank regenerates the global tensors and slices its shard
+    fps, _ = syn.make_step_randoms(10, B, 1)
+    starts = [s.view(B, 9)[lo:lo + per].reshape(-1) for s in fps[0]]
+    t = torch.full((per,), 37, dtype=torch.long)
+    x = inp["x_T"][lo:lo + per].clone()
+    _, x0, _ = O.forward(sd, x, inp["mask"][lo:lo + per], t, inp["given_objs"][lo:lo + per], inp["given_cats"][lo:lo + per],
+                         inp["text_emb"][lo:lo + per], starts, mask_global=inp["mask"], b_offset=lo)
+    out = [torch.empty_like(x0) for _ in range(world)]
+    dist.all_gather(out, x0.contiguous())  # the path's single exchange step
+    if rank == 0:
+        q.put(torch.cat(out).numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_plan_gloo():
+    """world_size 2 over gloo: shard -> local compute with global mask/offset -> one all-gather == global-batch reference."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = golden("shard_wellcond")
+    assert rel_l2(got, g["x0"]) < 2e-5

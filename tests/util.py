@@ -15,3 +15,33 @@ def rel_l2(a, b):
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def injected_rng(fps_starts=None, noises=None):
+    """Feed ``torch.randint`` (FPS starts, CPU) and ``torch.randn_like`` (sampling noise) from queues, in draw order,
+    so that the CUDA path, the oracle and the golden fixtures all see the same randoms."""
+    fq = list(fps_starts) if fps_starts is not None else None
+    nq = list(noises) if noises is not None else None
+    o_randint, o_randn_like = torch.randint, torch.randn_like
+
+    def randint(*a, **k):
+        if fq is not None:
+            assert fq, "FPS start queue exhausted"
+            return fq.pop(0).clone()
+        return o_randint(*a, **k)
+
+    def randn_like(x, **k):
+        if nq is not None:
+            assert nq, "noise queue exhausted"
+            return nq.pop(0).clone().to(x.device)
+        return o_randn_like(x, **k)
+
+    torch.randint, torch.randn_like = randint, randn_like
+    try:
+        yield
+    finally:
+        torch.randint, torch.randn_like = o_randint, o_randn_like
