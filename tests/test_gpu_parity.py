@@ -60,8 +60,13 @@ def test_forward_stages_vs_oracle(kind):
         assert torch.equal(got, tr[name + ".fps_idx"]), f"fps level {lvl}"
         got = eng.debug_tensor(f"ball_idx{lvl}", torch.int32).view(C, npnt, 32).cpu().long()
         assert torch.equal(got, tr[name + ".group_idx"]), f"ball query level {lvl}"
+    # 3-NN indices: exact on real clouds; absent (all-zero padded) clouds have every distance tied at 0, where the
+    # neighbour choice is arbitrary and irrelevant (all their points carry identical features)
+    present = (inp["given_objs"].abs().sum((2, 3)) > 0).reshape(-1)
     got = eng.debug_tensor("nn_idx0", torch.int32).view(C, 64, 3).cpu().long()
-    assert torch.equal(got, tr["fp4.nn_idx"])
+    assert torch.equal(got[present], tr["fp4.nn_idx"][present])
+    got = eng.debug_tensor("nn_idx3", torch.int32).view(C, 1024, 3).cpu().long()
+    assert torch.equal(got[present], tr["fp1.nn_idx"][present])
     # floating point stages
     def chk(name, ref, tol=TOL_STAGE, shape=None):
         got = eng.debug_tensor(name).cpu()
