@@ -141,6 +141,16 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
 /* Number of kernels this library has launched on behalf of `h` since creation (bench.py's gpu_launches). */
 LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h);
 
+/* Arithmetic of the dense layers: 0 = fp32 CUDA cores, 1 = TF32 tensor cores (tcgen05, fp32 accumulate) for every
+ * layer whose shape the tensor path supports.  Selection kernels (FPS, ball query, 3-NN) are always exact fp32. */
+LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision);
+
+/* Test hook: one linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) through the fp32 (precision 0) or tcgen05 TF32
+ * (precision 1) GEMM.  act: 0 none, 1 relu, 2 gelu, 3 sigmoid, 4 silu.  group_max: C[M/32,N] = max over 32-row groups. */
+LSDM_API int lsdm_debug_gemm(lsdm_handle* h, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                             const float* bias, int32_t bias_mode, int32_t M, int32_t N, int32_t K, int32_t act,
+                             int32_t group_max, int32_t precision, void* stream);
+
 /* Per-kernel-class timing with CUDA events on the launching stream (measurement aid for bench.py; adds two event
  * records per launch, so it is used in a separate pass, never inside the timed region).  Classes, in order:
  * gemm, fps, ball_query, sa_gather, three_nn, fp_combine, head3, cond, scene, denoise, other (LSDM_N_KCLASS = 11).

@@ -90,6 +90,7 @@ struct lsdm_handle {
   bool have_ws = false;
   int64_t launches = 0;
   // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
+  int precision = 0;  // lsdm_set_precision: 0 fp32, 1 tf32 tensor cores
   bool profiling = false;
   struct ProfRec { int cls; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -285,7 +286,7 @@ int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const flo
   g.C = C; g.ldc = ldc; g.strideC = 0;
   g.bias = bias; g.bias_mode = bias ? 1 : 0;
   g.M = M; g.N = N; g.K = K; g.batch = 1;
-  g.act = act; g.group_max = group_max;
+  g.act = act; g.group_max = group_max; g.precision = h->precision;
   int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
   if (r < 0) return fail(LSDM_EINVAL, "gemm: unsupported shape M=" + std::to_string(M) + " N=" + std::to_string(N) +
                                           " K=" + std::to_string(K));
@@ -378,7 +379,7 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
     g.W = w.H2; g.ldw = 512; g.strideW = 256 * 512;
     g.C = w.embpre; g.ldc = 256; g.strideC = (int64_t)NPTS * 256;
     g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
-    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0;
+    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0; g.precision = h->precision;
     int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
     if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
     if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
@@ -740,6 +741,27 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
 }
 
 LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h) { return h ? h->launches : 0; }
+
+LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision) {
+  if (!h || (precision != 0 && precision != 1)) return fail(LSDM_EINVAL, "precision must be 0 (fp32) or 1 (tf32)");
+  h->precision = precision;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_debug_gemm(lsdm_handle* h, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                             const float* bias, int32_t bias_mode, int32_t M, int32_t N, int32_t K, int32_t act,
+                             int32_t group_max, int32_t precision, void* stream) {
+  if (!h || !A || !W || !C) return fail(LSDM_EINVAL, "null argument");
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc;
+  g.bias = bias; g.bias_mode = bias ? bias_mode : 0;
+  g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act; g.group_max = group_max; g.precision = precision;
+  int r = precision == 1 ? launch_gemm_tc(g, (cudaStream_t)stream) : launch_gemm_simt(g, (cudaStream_t)stream);
+  if (r < 0) return fail(LSDM_EINVAL, "gemm shape not supported by the requested implementation");
+  h->launches += r;
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
 
 LSDM_API int lsdm_profile_begin(lsdm_handle* h) {
   if (!h) return fail(LSDM_EINVAL, "null handle");

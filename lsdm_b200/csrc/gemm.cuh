@@ -19,9 +19,13 @@ struct GemmArgs {
   int M, N, K, batch;
   int act;        // lsdm::Act
   int group_max;  // 1: C has M/32 rows, row g = max over rows [32g, 32g+32) of the activated tile
+  int precision;  // 0: fp32 CUDA cores (bit-faithful), 1: TF32 tensor cores (tcgen05) when the shape is eligible
 };
 
 // Launches the GEMM on `stream`; returns the number of kernels launched (1) or a negative value on bad arguments.
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t stream);
+bool gemm_tc_eligible(const GemmArgs& g);
 
 }  // namespace lsdm

@@ -7,6 +7,7 @@ tensors alive while kernels that read them are in flight.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -44,6 +45,8 @@ class Engine:
         self._keep = []
         self.T = 0
         self._alloc_workspace()
+        self.precision = os.environ.get("LSDM_PRECISION", "fp32")
+        self.set_precision(self.precision == "tf32")
 
     # ------------------------------------------------------------------ lifecycle
     def _alloc_workspace(self):
@@ -244,3 +247,15 @@ class Engine:
         fl = C.c_double()
         _lib.check(self.lib.lsdm_profile_end(self.h, ms, cnt, n, C.byref(fl)))
         return dict(zip(self.KCLASSES, ms)), dict(zip(self.KCLASSES, cnt)), fl.value
+
+    def set_precision(self, tf32: bool):
+        _lib.check(self.lib.lsdm_set_precision(self.h, 1 if tf32 else 0))
+
+    def debug_gemm(self, A, W, bias=None, act=0, group_max=False, tf32=False, bias_mode=1):
+        """One linear layer through the library's GEMM (test hook)."""
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M // 32 if group_max else M, N, device=self.device)
+        _lib.check(self.lib.lsdm_debug_gemm(self.h, _ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(out), out.stride(0), _ptr(bias),
+                                            bias_mode, M, N, K, act, 1 if group_max else 0, 1 if tf32 else 0, _stream(self.device)))
+        return out
