@@ -141,12 +141,19 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
 /* Number of kernels this library has launched on behalf of `h` since creation (bench.py's gpu_launches). */
 LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h);
 
-/* Arithmetic of the dense layers: 0 = fp32 CUDA cores, 1 = TF32 tensor cores (tcgen05, fp32 accumulate) for every
- * layer whose shape the tensor path supports.  Selection kernels (FPS, ball query, 3-NN) are always exact fp32. */
-LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision);
+/* Arithmetic of the dense layers: 0 = fp32 CUDA cores; 1 = TF32 tensor cores (tcgen05, operands rounded to nearest,
+ * fp32 accumulate in TMEM); 2 = 3xTF32 (hi/lo split of both operands on the tensor cores, ~fp32 accuracy).  Set separately
+ * for the condition encoder (PointNet++ etc., the bulk of the FLOPs) and for the per-step x0 network + upsampler (small,
+ * accuracy-critical).  Layers whose shape the tensor path does not support, and all selection kernels (FPS, ball query,
+ * 3-NN), are always exact fp32. */
+LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32_t precision_step);
 
-/* Test hook: one linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) through the fp32 (precision 0) or tcgen05 TF32
- * (precision 1) GEMM.  act: 0 none, 1 relu, 2 gelu, 3 sigmoid, 4 silu.  group_max: C[M/32,N] = max over 32-row groups. */
+/* Tuning knobs.  "sa_fused": 0 = set-abstraction blocks as gather + GEMM launches, 1 = fused tensor-core SA kernel with the
+ * activations staged in shared memory, 2 = fused with the activations kept in tensor memory (A-from-TMEM MMA). */
+LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value);
+
+/* Test hook: one linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) through the fp32 (precision 0) or tcgen05 TF32 / 3xTF32
+ * (precision 1 / 2) GEMM.  act: 0 none, 1 relu, 2 gelu, 3 sigmoid, 4 silu.  group_max: C[M/32,N] = max over 32-row groups. */
 LSDM_API int lsdm_debug_gemm(lsdm_handle* h, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                              const float* bias, int32_t bias_mode, int32_t M, int32_t N, int32_t K, int32_t act,
                              int32_t group_max, int32_t precision, void* stream);

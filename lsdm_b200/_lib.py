@@ -52,7 +52,8 @@ PROTOTYPES = {
     "lsdm_cat_loss": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "lsdm_debug_tensor": (C.c_int64, [_P, C.c_char_p, _P, C.c_size_t, _P]),
     "lsdm_launch_count": (C.c_int64, [_P]),
-    "lsdm_set_precision": (C.c_int, [_P, C.c_int32]),
+    "lsdm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "lsdm_set_precision": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "lsdm_debug_gemm": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, _P]),
     "lsdm_profile_begin": (C.c_int, [_P]),

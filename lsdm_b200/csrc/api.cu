@@ -90,7 +90,9 @@ struct lsdm_handle {
   bool have_ws = false;
   int64_t launches = 0;
   // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
-  int precision = 0;  // lsdm_set_precision: 0 fp32, 1 tf32 tensor cores
+  int precision = 0;       // dense layers of the condition encoder (PointNet++): 0 fp32, 1 tf32, 2 3xtf32
+  int precision_step = 0;
+  int sa_fused = 0;  // 0: gather + GEMMs; 1: fused SA kernel, A operands in smem; 2: fused, A operands in TMEM  // dense layers of the per-step x0 network + upsampler
   bool profiling = false;
   struct ProfRec { int cls; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -279,14 +281,14 @@ int prof_launch(lsdm_handle* h, cudaStream_t st, int cls, F&& f) {
 }
 
 int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const float* W, int64_t ldw, float* C,
-         int64_t ldc, const float* bias, int M, int N, int K, int act, int group_max = 0) {
+         int64_t ldc, const float* bias, int M, int N, int K, int act, int group_max = 0, int prec = -1) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.strideA = 0;
   g.W = W; g.ldw = ldw; g.strideW = 0;
   g.C = C; g.ldc = ldc; g.strideC = 0;
   g.bias = bias; g.bias_mode = bias ? 1 : 0;
   g.M = M; g.N = N; g.K = K; g.batch = 1;
-  g.act = act; g.group_max = group_max; g.precision = h->precision;
+  g.act = act; g.group_max = group_max; g.precision = prec >= 0 ? prec : h->precision;
   int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
   if (r < 0) return fail(LSDM_EINVAL, "gemm: unsupported shape M=" + std::to_string(M) + " N=" + std::to_string(N) +
                                           " K=" + std::to_string(K));
@@ -322,6 +324,16 @@ int pointnet2(lsdm_handle* h, const float* clouds, cudaStream_t st) {
     if (l > 0) {  // first conv, feature half, once per source point
       GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE));
       P = w.tP;
+    }
+    const int fused_max_level = h->sa_fused == 2 ? 2 : 1;
+    if (h->precision >= 1 && h->sa_fused > 0 && l <= fused_max_level) {
+      int r = prof_launch(h, st, K_GEMM, [&] {
+        return launch_sa_fused(l, h->sa_fused == 2, P, xyz[l], xyz[l + 1], w.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
+                               h->sa_w[l][1], h->sa_b[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], st);
+      });
+      if (r < 0) return fail(LSDM_EINVAL, "fused SA kernel unavailable for this level");
+      if (h->profiling) h->gemm_flops += 2.0 * C * S * 32 * ((double)C1 * C2 + (double)C2 * C3);
+      continue;
     }
     prof_launch(h, st, K_GATHER, [&] { return launch_sa_gather(P, h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0], xyz[l], xyz[l + 1], w.grp[l], C, N, S, C1,
                                     w.tA, st); });
@@ -371,7 +383,7 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
                                    h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.enc, h->W("upsampling_layer.0.weight"),
                                    h->W("upsampling_layer.0.bias"), B, w.s256, w.H1, st); });
   GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), B * 256, 512,
-          128, ACT_GELU));
+          128, ACT_GELU, 0, h->precision_step));
   {
     // embpre[b][p][s] = gelu(sum_k U4[p][k] H2[b][s][k] + b4[p]): the upsampler's last layer written point-major
     GemmArgs g{};
@@ -379,13 +391,13 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
     g.W = w.H2; g.ldw = 512; g.strideW = 256 * 512;
     g.C = w.embpre; g.ldc = 256; g.strideC = (int64_t)NPTS * 256;
     g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
-    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0; g.precision = h->precision;
+    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0; g.precision = h->precision_step;
     int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
     if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
     if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
   }
   GE(gemm(h, st, w.embpre, 256, h->W("combine_extraction.0.weight"), 256, w.cat + 128, 256,
-          h->W("combine_extraction.0.bias"), rows, 128, 256, ACT_GELU));
+          h->W("combine_extraction.0.bias"), rows, 128, 256, ACT_GELU, 0, h->precision_step));
   const int M = want_guiding ? 2 * rows : rows;
   if (want_guiding)
     CK(cudaMemcpy2DAsync(w.cat + (size_t)rows * 256 + 128, 256 * sizeof(float), w.cat + 128, 256 * sizeof(float),
@@ -396,13 +408,13 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
     prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(w.pcd_out, nullptr, h->W("input_process.pose_embedding.0.weight"),
                                       h->W("input_process.pose_embedding.0.bias"), rows, w.h1 + (size_t)rows * 64, st); });
   GE(gemm(h, st, w.h1, 64, h->W("input_process.pose_embedding.2.weight"), 64, w.cat, 256,
-          h->W("input_process.pose_embedding.2.bias"), M, 128, 64, ACT_SIGMOID));
+          h->W("input_process.pose_embedding.2.bias"), M, 128, 64, ACT_SIGMOID, 0, h->precision_step));
   GE(gemm(h, st, w.cat, 256, h->W("input_process.combination_extraction.0.weight"), 256, w.c1, 192,
-          h->W("input_process.combination_extraction.0.bias"), M, 192, 256, ACT_SIGMOID));
+          h->W("input_process.combination_extraction.0.bias"), M, 192, 256, ACT_SIGMOID, 0, h->precision_step));
   GE(gemm(h, st, w.c1, 192, h->W("input_process.combination_extraction.2.weight"), 192, w.c2, 128,
-          h->W("input_process.combination_extraction.2.bias"), M, 128, 192, ACT_SIGMOID));
+          h->W("input_process.combination_extraction.2.bias"), M, 128, 192, ACT_SIGMOID, 0, h->precision_step));
   GE(gemm(h, st, w.c2, 128, h->W("output_process.pose_final.0.weight"), 128, w.f1, 64,
-          h->W("output_process.pose_final.0.bias"), M, 64, 128, ACT_GELU));
+          h->W("output_process.pose_final.0.bias"), M, 64, 128, ACT_GELU, 0, h->precision_step));
   float* x0 = x0_out ? x0_out : w.x0;
   prof_launch(h, st, K_DENOISE, [&] { return launch_final3(w.f1, h->W("output_process.pose_final.2.weight"), h->W("output_process.pose_final.2.bias"), rows,
                                x0, x, w.t_dev, h->sched, h->sched ? h->sched + h->T : nullptr, h->sched ? h->sched + 2 * h->T : nullptr, noise,
@@ -742,9 +754,20 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
 
 LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h) { return h ? h->launches : 0; }
 
-LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision) {
-  if (!h || (precision != 0 && precision != 1)) return fail(LSDM_EINVAL, "precision must be 0 (fp32) or 1 (tf32)");
-  h->precision = precision;
+LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
+  if (!h || !name) return fail(LSDM_EINVAL, "null argument");
+  if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 2) {
+    h->sa_fused = value;
+    return LSDM_OK;
+  }
+  return fail(LSDM_EINVAL, std::string("unknown option or bad value: ") + name);
+}
+
+LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32_t precision_step) {
+  if (!h || precision_encoder < 0 || precision_encoder > 2 || precision_step < 0 || precision_step > 2)
+    return fail(LSDM_EINVAL, "precision must be 0 (fp32), 1 (tf32) or 2 (3xtf32)");
+  h->precision = precision_encoder;
+  h->precision_step = precision_step;
   return LSDM_OK;
 }
 
@@ -756,7 +779,7 @@ LSDM_API int lsdm_debug_gemm(lsdm_handle* h, const float* A, int64_t lda, const 
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc;
   g.bias = bias; g.bias_mode = bias ? bias_mode : 0;
   g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act; g.group_max = group_max; g.precision = precision;
-  int r = precision == 1 ? launch_gemm_tc(g, (cudaStream_t)stream) : launch_gemm_simt(g, (cudaStream_t)stream);
+  int r = precision >= 1 ? launch_gemm_tc(g, (cudaStream_t)stream) : launch_gemm_simt(g, (cudaStream_t)stream);
   if (r < 0) return fail(LSDM_EINVAL, "gemm shape not supported by the requested implementation");
   h->launches += r;
   CK(cudaPeekAtLastError());

@@ -19,7 +19,8 @@ struct GemmArgs {
   int M, N, K, batch;
   int act;        // lsdm::Act
   int group_max;  // 1: C has M/32 rows, row g = max over rows [32g, 32g+32) of the activated tile
-  int precision;  // 0: fp32 CUDA cores (bit-faithful), 1: TF32 tensor cores (tcgen05) when the shape is eligible
+  int precision;  // 0: fp32 CUDA cores (bit-faithful); 1: TF32 tensor cores (tcgen05, operands rounded-to-nearest);
+                  // 2: 3xTF32 (hi/lo split of both operands, ~fp32 accuracy on the tensor cores)
 };
 
 // Launches the GEMM on `stream`; returns the number of kernels launched (1) or a negative value on bad arguments.

@@ -168,7 +168,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
 
 // Dispatcher of the generic interface (gemm.cuh).
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
-  if (g.precision == 1 && gemm_tc_eligible(g)) return launch_gemm_tc(g, stream);
+  if (g.precision >= 1 && gemm_tc_eligible(g)) return launch_gemm_tc(g, stream);
   return launch_gemm_simt(g, stream);
 }
 

@@ -1,9 +1,9 @@
 // tcgen05 (5th-gen tensor core) implementation of the generic linear-layer GEMM (gemm.cuh):
 //   C[M,N] = act(A[M,K] . W[N,K]^T + bias),  TF32 operands read as fp32 from shared memory, fp32 accumulate in TMEM.
 // One CTA = one 128 x BN output tile (UMMA M=128, N=BN, K=8 per instruction).  K is consumed in 32-float
-// k-blocks (one 128-byte swizzle row per matrix row); A and W k-blocks are staged with cp.async into a 2-stage
-// ring in the canonical K-major SWIZZLE_128B layout, one elected thread issues the MMAs and tcgen05.commit
-// releases each stage through an mbarrier.  Epilogue: tcgen05.ld (thread = row) -> bias/activation ->
+// k-blocks (one 128-byte swizzle row per matrix row); A and W k-blocks are register-staged (rounded to TF32 with
+// cvt.rna, optionally split hi/lo for 3xTF32) into a 2-stage ring in the canonical K-major SWIZZLE_128B layout, one
+// elected thread issues the MMAs and tcgen05.commit releases each stage through an mbarrier.  Epilogue: tcgen05.ld (thread = row) -> bias/activation ->
 // either a shared-memory transpose for fully coalesced 128-bit stores, or the PointNet++ group max
 // (max over the 32 rows a warp owns == redux.sync on the non-negative float bit patterns).
 #include "gemm.cuh"
@@ -21,10 +21,10 @@ constexpr int TNT = 128;      // threads
 constexpr int A_STAGE = TBM * 128;  // bytes
 constexpr int STG_STRIDE = 36;      // floats; epilogue transpose row stride (conflict-free float4 both ways)
 
-template <int BN>
+template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(TNT) gemm_tc_kernel(GemmArgs g) {
   constexpr int W_STAGE = BN * 128;
-  constexpr int STAGE = A_STAGE + W_STAGE;
+  constexpr int STAGE = (A_STAGE + W_STAGE) * (SPLIT ? 2 : 1);  // [A_hi | W_hi | A_lo | W_lo]
   constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[3];  // mma_done[2], acc_done
@@ -57,37 +57,56 @@ __global__ void __launch_bounds__(TNT) gemm_tc_kernel(GemmArgs g) {
   const uint32_t tmem = s_tmem;
 
   const int nkb = g.K / TBK;
-  auto load_stage = [&](int kb) {
-    const uint32_t sA = base + (kb & 1) * STAGE, sW = sA + A_STAGE;
+  // Both operands are staged through registers: ld.global (next k-block in flight while the current one is multiplied)
+  // -> cvt.rna.tf32 (operands are ROUNDED, never truncated) -> swizzled st.shared.  SPLIT additionally stores the
+  // residual lo = rna(x - hi) of both operands: D += A_lo.W_hi + A_hi.W_lo + A_hi.W_hi ("3xTF32", ~fp32 accuracy).
+  constexpr int A_PER = TBM * 8 / TNT, W_PER = BN * 8 / TNT;
+  float4 ra[A_PER], rw[W_PER];
+  auto fetch = [&](int kb) {
     const int k0 = kb * TBK;
 #pragma unroll
-    for (int i = 0; i < TBM * 8 / TNT; ++i) {
+    for (int i = 0; i < A_PER; ++i) {
       int q = tid + i * TNT;
       int r = q >> 3, c = q & 7;
       int m = m0 + r;
       m = m < g.M ? m : g.M - 1;  // clamp: rows past M are never stored
-      cp_async16(sA + sw128_off(r, c), A + (int64_t)m * g.lda + k0 + c * 4);
+      ra[i] = *reinterpret_cast<const float4*>(A + (int64_t)m * g.lda + k0 + c * 4);
     }
 #pragma unroll
-    for (int i = 0; i < BN * 8 / TNT; ++i) {
+    for (int i = 0; i < W_PER; ++i) {
       int q = tid + i * TNT;
       int r = q >> 3, c = q & 7;
-      cp_async16(sW + sw128_off(r, c), W + (int64_t)(n0 + r) * g.ldw + k0 + c * 4);
+      rw[i] = *reinterpret_cast<const float4*>(W + (int64_t)(n0 + r) * g.ldw + k0 + c * 4);
     }
-    cp_async_commit();
+  };
+  auto sub4 = [](float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); };
+  auto store = [&](int kb) {
+    const uint32_t sA = base + (kb & 1) * STAGE, sW = sA + A_STAGE;
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int q = tid + i * TNT;
+      uint32_t off = sw128_off(q >> 3, q & 7);
+      float4 hi = rna_tf32(ra[i]);
+      st_shared_v4(sA + off, hi);
+      if (SPLIT) st_shared_v4(sA + (A_STAGE + W_STAGE) + off, rna_tf32(sub4(ra[i], hi)));
+    }
+#pragma unroll
+    for (int i = 0; i < W_PER; ++i) {
+      int q = tid + i * TNT;
+      uint32_t off = sw128_off(q >> 3, q & 7);
+      float4 hi = rna_tf32(rw[i]);
+      st_shared_v4(sW + off, hi);
+      if (SPLIT) st_shared_v4(sW + (A_STAGE + W_STAGE) + off, rna_tf32(sub4(rw[i], hi)));
+    }
   };
 
   constexpr uint32_t idesc = umma_idesc_tf32(TBM, BN);
-  load_stage(0);
+  fetch(0);
   for (int kb = 0; kb < nkb; ++kb) {
-    if (kb + 1 < nkb) {
-      // the stage we are about to refill was read by the MMAs of iteration kb-1: wait for their commit
-      if (kb >= 1) mbar_wait(((kb + 1) & 1) ? bar_mma1 : bar_mma0, (uint32_t)(((kb - 1) >> 1) & 1));
-      load_stage(kb + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    // stage kb&1 was last read by the MMAs of iteration kb-2: wait for their commit before overwriting it
+    if (kb >= 2) mbar_wait((kb & 1) ? bar_mma1 : bar_mma0, (uint32_t)(((kb - 2) >> 1) & 1));
+    store(kb);
+    if (kb + 1 < nkb) fetch(kb + 1);
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
@@ -95,8 +114,17 @@ __global__ void __launch_bounds__(TNT) gemm_tc_kernel(GemmArgs g) {
       const uint32_t sA = base + (kb & 1) * STAGE, sW = sA + A_STAGE;
       const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sW);
 #pragma unroll
-      for (int kk = 0; kk < TBK / 8; ++kk)
-        umma_tf32_ss(tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+      for (int kk = 0; kk < TBK / 8; ++kk) {
+        const uint64_t o = (uint64_t)(kk * 2);
+        if (SPLIT) {
+          const uint64_t dal = umma_desc_sw128(sA + A_STAGE + W_STAGE), dbl = umma_desc_sw128(sW + A_STAGE + W_STAGE);
+          umma_tf32_ss(tmem, dal + o, db + o, idesc, (kb | kk) != 0 ? 1u : 0u);
+          umma_tf32_ss(tmem, da + o, dbl + o, idesc, 1u);
+          umma_tf32_ss(tmem, da + o, db + o, idesc, 1u);
+        } else {
+          umma_tf32_ss(tmem, da + o, db + o, idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+      }
       umma_commit((kb & 1) ? bar_mma1 : bar_mma0);
       if (kb == nkb - 1) umma_commit(bar_acc);
     }
@@ -150,18 +178,22 @@ __global__ void __launch_bounds__(TNT) gemm_tc_kernel(GemmArgs g) {
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int BN>
-int launch_bn(const GemmArgs& g, cudaStream_t st) {
-  constexpr int smem = 2 * (A_STAGE + BN * 128) + 1024;
+template <int BN, bool SPLIT>
+int launch_bn2(const GemmArgs& g, cudaStream_t st) {
+  constexpr int smem = 2 * (A_STAGE + BN * 128) * (SPLIT ? 2 : 1) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
     attr_done = true;
   }
   int batch = g.batch > 0 ? g.batch : 1;
   dim3 grid((g.M + TBM - 1) / TBM, g.N / BN, batch);
-  gemm_tc_kernel<BN><<<grid, TNT, smem, st>>>(g);
+  gemm_tc_kernel<BN, SPLIT><<<grid, TNT, smem, st>>>(g);
   return 1;
+}
+template <int BN>
+int launch_bn(const GemmArgs& g, cudaStream_t st) {
+  return g.precision >= 2 ? launch_bn2<BN, true>(g, st) : launch_bn2<BN, false>(g, st);
 }
 
 }  // namespace

@@ -30,6 +30,13 @@ int launch_fold_bn(const float* W, const float* b, const float* gamma, const flo
                    const float* var, int N, int K, float eps, float* Wf, float* bf, cudaStream_t st);
 int launch_copy_cols(const float* src, int ld_src, int col0, int ncols, int rows, float* dst, cudaStream_t st);
 
+// ---- sa_fused.cu ----------------------------------------------------------------------------
+// Fused set-abstraction block on the tensor cores (gather + 2 dense layers + max-pool), levels 0..2.
+// Returns -1 when the (level, variant) combination is not built.
+int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, const float* new_xyz, const int* grp,
+                    const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
+                    const float* b3, int n_clouds, int N, int S, float* out, cudaStream_t st);
+
 // ---- cond.cu --------------------------------------------------------------------------------
 struct CondWeights {
   const float *et0_w, *et0_b, *et2_w, *et2_b, *et4_w, *et4_b;  // embed_text 512->256->256->128

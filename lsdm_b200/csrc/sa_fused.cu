@@ -1,0 +1,271 @@
+// Fused PointNet++ set-abstraction block (reference pointnet2_utils.py:107-135,174-199) on the tensor cores:
+//   gather (P[j] + Wx.(xyz_j - c_s), ReLU)  ->  1x1 conv + BN + ReLU  ->  1x1 conv + BN + ReLU  ->  max over the 32 samples
+// for 128 grouped rows (4 centroids x 32 samples) per tile, with NOTHING but the pooled [centroid, C3] features
+// leaving the SM.  Persistent CTAs of 128 threads (thread == grouped row == TMEM lane):
+//   * layer weights live in shared memory for the whole kernel (K-major SWIZZLE_128B, rounded to TF32 once);
+//   * the gathered first-layer activations are written straight into the A-operand position of the second layer,
+//     either in tensor memory (tcgen05.st, A-from-TMEM MMA) or in shared memory (swizzled st.shared, SS MMA);
+//   * each layer is one batch of tcgen05.mma (M=128, N=C, K=8) committed to an mbarrier; its epilogue reads the
+//     accumulator with tcgen05.ld (thread = row), applies bias + ReLU (+ TF32 rounding) and feeds the next layer;
+//   * the last epilogue max-pools the 32 rows of each warp with redux.sync on the non-negative float bit patterns.
+// Several CTAs are co-resident per SM (TMEM columns are split between them), which overlaps one tile's gather /
+// epilogues with another tile's MMAs.
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace lsdm {
+
+namespace {
+
+using namespace tc;
+
+struct SaArgs {
+  const float* P;        // [C*N, C1] first-layer feature half incl. bias (nullptr for sa1)
+  const float* xyz;      // [C, N, 3] source points
+  const float* new_xyz;  // [C, S, 3] centroids
+  const int* grp;        // [C, S, 32]
+  const float* Wx;       // [C1, 3]
+  const float* Wf3;      // [C1, 3]  (sa1: feature half acts on the coordinates)
+  const float* b1;       // [C1]     (sa1)
+  const float* W2;       // [C2, C1]
+  const float* b2;
+  const float* W3;       // [C3, C2]
+  const float* b3;
+  float* out;            // [C*S, C3]
+  int n_tiles, N, S;
+};
+
+template <int C1, int C2, int C3, bool FIRST, bool A_TMEM>
+__global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
+  constexpr int KB2 = C1 / 32, KB3 = C2 / 32;         // k-blocks of layer 2 / layer 3
+  constexpr int W2_BYTES = C2 * C1 * 4, W3_BYTES = C3 * C2 * 4;
+  constexpr int H_BYTES = A_TMEM ? 0 : 128 * C1 * 4;  // h1 tile in smem (SS path)
+  constexpr int H2_BYTES = A_TMEM ? 0 : 128 * C2 * 4;
+  constexpr uint32_t COL_H1 = 0, COL_D2 = A_TMEM ? C1 : 0, COL_D3 = COL_D2 + C2;
+  constexpr uint32_t NEED = COL_D3 + C3;
+  constexpr uint32_t TCOLS = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : (NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512)));
+  static_assert(NEED <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_wx[C1 * 3], s_wf[FIRST ? C1 * 3 : 1], s_b1[FIRST ? C1 : 1], s_b2[C2], s_b3[C3];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW2 = base, sW3 = sW2 + W2_BYTES, sH1 = sW3 + W3_BYTES, sH2 = sH1 + H_BYTES;
+  const uint32_t bar = smem_u32(&s_bar);
+
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), TCOLS);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  // weights -> smem, K-major SW128 k-blocks [rows x 32 floats], rounded to TF32 (RNA) once
+  for (int q = tid; q < C2 * C1 / 4; q += 128) {
+    int n = q / (C1 / 4), k4 = q % (C1 / 4);
+    float4 v = *reinterpret_cast<const float4*>(a.W2 + (int64_t)n * C1 + k4 * 4);
+    st_shared_v4(sW2 + (k4 >> 3) * (C2 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  for (int q = tid; q < C3 * C2 / 4; q += 128) {
+    int n = q / (C2 / 4), k4 = q % (C2 / 4);
+    float4 v = *reinterpret_cast<const float4*>(a.W3 + (int64_t)n * C2 + k4 * 4);
+    st_shared_v4(sW3 + (k4 >> 3) * (C3 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  for (int i = tid; i < C1 * 3; i += 128) {
+    s_wx[i] = a.Wx[i];
+    if (FIRST) s_wf[i] = a.Wf3[i];
+  }
+  if (FIRST)
+    for (int i = tid; i < C1; i += 128) s_b1[i] = a.b1[i];
+  for (int i = tid; i < C2; i += 128) s_b2[i] = a.b2[i];
+  for (int i = tid; i < C3; i += 128) s_b3[i] = a.b3[i];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's lane quarter
+  constexpr uint32_t idesc2 = umma_idesc_tf32(128, C2), idesc3 = umma_idesc_tf32(128, C3);
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    // ---------------- gather + first layer (CUDA cores, exact fp32 geometry) ----------------
+    const int64_t row = (int64_t)tile * 128 + tid;
+    const int64_t cs = row >> 5;
+    const int64_t c = cs / a.S;
+    const int j = a.grp[row];
+    const float* pj = a.xyz + (c * a.N + j) * 3;
+    const float* pc = a.new_xyz + cs * 3;
+    const float jx = pj[0], jy = pj[1], jz = pj[2];
+    const float rx = jx - pc[0], ry = jy - pc[1], rz = jz - pc[2];
+    const float* prow = FIRST ? nullptr : a.P + (c * a.N + j) * C1;
+#pragma unroll 1
+    for (int kb = 0; kb < KB2; ++kb) {
+      uint32_t v[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 p4;
+        if (FIRST) {
+          p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          p4 = *reinterpret_cast<const float4*>(prow + kb * 32 + q * 4);
+        }
+        float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ch = kb * 32 + q * 4 + e;
+          float x = FIRST ? s_b1[ch] : pv[e];
+          x = fmaf(s_wx[ch * 3 + 0], rx, x);
+          x = fmaf(s_wx[ch * 3 + 1], ry, x);
+          x = fmaf(s_wx[ch * 3 + 2], rz, x);
+          if (FIRST) {
+            x = fmaf(s_wf[ch * 3 + 0], jx, x);
+            x = fmaf(s_wf[ch * 3 + 1], jy, x);
+            x = fmaf(s_wf[ch * 3 + 2], jz, x);
+          }
+          v[q * 4 + e] = __float_as_uint(rna_tf32(fmaxf(x, 0.0f)));
+        }
+      }
+      if (A_TMEM) {
+        tmem_st32(tlane + COL_H1 + kb * 32, v);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(sH1 + kb * (128 * 128) + sw128_off(tid, q),
+                       make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                   __uint_as_float(v[q * 4 + 3])));
+      }
+    }
+    if (A_TMEM) tmem_st_wait(); else fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---------------- layer 2 on the tensor core ----------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB2; ++kb) {
+        const uint64_t db = umma_desc_sw128(sW2 + kb * (C2 * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (A_TMEM) {
+            umma_tf32_ts(tmem + COL_D2, tmem + COL_H1 + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc2, (kb | kk) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = umma_desc_sw128(sH1 + kb * (128 * 128));
+            umma_tf32_ss(tmem + COL_D2, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc2, (kb | kk) != 0 ? 1u : 0u);
+          }
+        }
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---------------- epilogue 2: bias + ReLU + TF32 rounding -> A operand of layer 3 ----------------
+#pragma unroll 1
+    for (int kb = 0; kb < KB3; ++kb) {
+      uint32_t v[32];
+      tmem_ld32(tlane + COL_D2 + kb * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        v[e] = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(v[e]) + s_b2[kb * 32 + e], 0.0f)));
+      if (A_TMEM) {
+        tmem_st32(tlane + COL_D2 + kb * 32, v);  // in place: the accumulator columns become the next A operand
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(sH2 + kb * (128 * 128) + sw128_off(tid, q),
+                       make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                   __uint_as_float(v[q * 4 + 3])));
+      }
+    }
+    if (A_TMEM) tmem_st_wait(); else fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---------------- layer 3 ----------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB3; ++kb) {
+        const uint64_t db = umma_desc_sw128(sW3 + kb * (C3 * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (A_TMEM) {
+            umma_tf32_ts(tmem + COL_D3, tmem + COL_D2 + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc3, (kb | kk) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = umma_desc_sw128(sH2 + kb * (128 * 128));
+            umma_tf32_ss(tmem + COL_D3, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc3, (kb | kk) != 0 ? 1u : 0u);
+          }
+        }
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---------------- epilogue 3: bias + ReLU + max over the warp's 32 samples ----------------
+    float* orow = a.out + ((int64_t)tile * 4 + warp) * C3;
+#pragma unroll 1
+    for (int c0 = 0; c0 < C3; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tlane + COL_D3 + c0, v);
+      tmem_ld_wait();
+      uint32_t res = 0;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float x = fmaxf(__uint_as_float(v[e]) + s_b3[c0 + e], 0.0f);  // >= 0: uint order == float order
+        uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(x));
+        if (lane == e) res = mx;
+      }
+      orow[c0 + lane] = __uint_as_float(res);
+    }
+    tc_fence_before();  // the next tile's MMAs overwrite D2/D3 only after every thread's loads above
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+template <int C1, int C2, int C3, bool FIRST, bool A_TMEM>
+int launch_t(const SaArgs& a, cudaStream_t st) {
+  constexpr int need = C2 * C1 * 4 + C3 * C2 * 4 + (A_TMEM ? 0 : 128 * (C1 + C2) * 4) + 1024;
+  constexpr uint32_t cols_need = (A_TMEM ? C1 : 0) + C2 + C3;
+  constexpr int tcols = cols_need <= 32 ? 32 : (cols_need <= 64 ? 64 : (cols_need <= 128 ? 128 : (cols_need <= 256 ? 256 : 512)));
+  constexpr int by_tmem = 512 / tcols;
+  // co-residency is bounded by TMEM columns; pad the shared-memory request so the SM never takes more CTAs than that
+  // (an extra persistent CTA would spin in tcgen05.alloc until the others exit)
+  constexpr int by_smem = (227 * 1024) / (need + 1024);
+  constexpr int per_sm = by_tmem < by_smem ? by_tmem : by_smem;
+  static_assert(per_sm >= 1, "does not fit");
+  constexpr int floor_smem = (227 * 1024) / (per_sm + 1) + 1;  // > 1/(per_sm+1) of the SM => at most per_sm CTAs
+  constexpr int smem = need > floor_smem ? need : floor_smem;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return -1;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * per_sm;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM><<<grid, 128, smem, st>>>(a);
+  return 1;
+}
+
+}  // namespace
+
+// level: 0 (sa1: 6->32->32->64) or 1 (sa2: 67->64->64->128).  a_tmem selects the A-from-TMEM variant.
+int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, const float* new_xyz, const int* grp,
+                    const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
+                    const float* b3, int n_clouds, int N, int S, float* out, cudaStream_t st) {
+  SaArgs a{P, xyz, new_xyz, grp, Wx, Wf3, b1, W2, b2, W3, b3, out, n_clouds * S / 4, N, S};
+  if (level == 0) return a_tmem ? launch_t<32, 32, 64, true, true>(a, st) : launch_t<32, 32, 64, true, false>(a, st);
+  if (level == 1) return a_tmem ? launch_t<64, 64, 128, false, true>(a, st) : launch_t<64, 64, 128, false, false>(a, st);
+  if (level == 2) return a_tmem ? launch_t<128, 128, 256, false, true>(a, st) : -1;
+  return -1;
+}
+
+}  // namespace lsdm

@@ -57,6 +57,17 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// round-to-nearest (ties away) fp32 -> tf32, result kept in an fp32 container (low 13 mantissa bits zero)
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 rna_tf32(float4 v) { return make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w)); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------
 // one full warp; writes the TMEM base address (lane 0, column base) to *dst_smem
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {

@@ -45,8 +45,10 @@ class Engine:
         self._keep = []
         self.T = 0
         self._alloc_workspace()
-        self.precision = os.environ.get("LSDM_PRECISION", "fp32")
-        self.set_precision(self.precision == "tf32")
+        # default: tensor cores (TF32 condition encoder with the fused SA kernels, 3xTF32 x0 network); LSDM_PRECISION=fp32
+        # selects the CUDA-core fp32 build of every dense layer
+        self.set_precision(os.environ.get("LSDM_PRECISION", "tf32"))
+        self.set_option("sa_fused", int(os.environ.get("LSDM_SA_FUSED", "2")))
 
     # ------------------------------------------------------------------ lifecycle
     def _alloc_workspace(self):
@@ -248,14 +250,24 @@ class Engine:
         _lib.check(self.lib.lsdm_profile_end(self.h, ms, cnt, n, C.byref(fl)))
         return dict(zip(self.KCLASSES, ms)), dict(zip(self.KCLASSES, cnt)), fl.value
 
-    def set_precision(self, tf32: bool):
-        _lib.check(self.lib.lsdm_set_precision(self.h, 1 if tf32 else 0))
+    PRECISIONS = {"fp32": (0, 0), "tf32": (1, 2), "tf32-all": (1, 1), "3xtf32": (2, 2)}
 
-    def debug_gemm(self, A, W, bias=None, act=0, group_max=False, tf32=False, bias_mode=1):
+    def set_precision(self, mode):
+        """'fp32': CUDA-core fp32 everywhere.  'tf32' (tensor cores): TF32 for the condition encoder, 3xTF32 for the
+        per-step x0 network.  'tf32-all': TF32 everywhere.  '3xtf32': split-TF32 everywhere (~fp32 accuracy)."""
+        enc, step = self.PRECISIONS[mode]
+        _lib.check(self.lib.lsdm_set_precision(self.h, enc, step))
+        self.precision = mode
+
+    def set_option(self, name, value):
+        _lib.check(self.lib.lsdm_set_option(self.h, name.encode(), int(value)))
+
+    def debug_gemm(self, A, W, bias=None, act=0, group_max=False, tf32=False, bias_mode=1, precision=None):
         """One linear layer through the library's GEMM (test hook)."""
         M, K = A.shape
         N = W.shape[0]
         out = torch.empty(M // 32 if group_max else M, N, device=self.device)
         _lib.check(self.lib.lsdm_debug_gemm(self.h, _ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(out), out.stride(0), _ptr(bias),
-                                            bias_mode, M, N, K, act, 1 if group_max else 0, 1 if tf32 else 0, _stream(self.device)))
+                                            bias_mode, M, N, K, act, 1 if group_max else 0,
+                                            (1 if tf32 else 0) if precision is None else precision, _stream(self.device)))
         return out

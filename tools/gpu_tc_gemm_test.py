@@ -12,7 +12,7 @@ def tf32_round(x):
     return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
-def run(eng, M, N, K, act, group_max, bias_mode=1, exact=True, lda_pad=0):
+def run(eng, M, N, K, act, group_max, bias_mode=1, exact=True, lda_pad=0, precision=1):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     A = torch.randn(M, K + lda_pad, device="cuda", generator=g)[:, :K]
     W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
@@ -29,11 +29,11 @@ def run(eng, M, N, K, act, group_max, bias_mode=1, exact=True, lda_pad=0):
         ref = ref.sigmoid()
     if group_max:
         ref = ref.view(M // 32, 32, N).max(1)[0]
-    got = eng.debug_gemm(A, W, b, act=act, group_max=group_max, tf32=True, bias_mode=bias_mode)
+    got = eng.debug_gemm(A, W, b, act=act, group_max=group_max, bias_mode=bias_mode, precision=precision)
     torch.cuda.synchronize()
     err = (got.double() - ref).abs()
     rel = float((got.double() - ref).norm() / ref.norm())
-    tag = f"M={M} N={N} K={K} act={act} gmax={int(group_max)} bm={bias_mode} exact={int(exact)} pad={lda_pad}"
+    tag = f"M={M} N={N} K={K} act={act} gmax={int(group_max)} bm={bias_mode} exact={int(exact)} pad={lda_pad} prec={precision}"
     print(f"{tag:70s} rel_l2 {rel:.3e} max_abs {float(err.max()):.3e} nan {int(torch.isnan(got).sum())}")
     if rel > 1e-2 and not group_max:
         # structure of the error: which rows / cols are wrong
@@ -70,22 +70,25 @@ def main():
     run(eng, 4096, 128, 64, 3, False, lda_pad=192)
     run(eng, 4096, 128, 128, 2, False, exact=False)
     run(eng, 4096, 256, 256, 0, False, exact=False)
+    for (M, N, K) in [(4096, 128, 128), (4096, 256, 256), (1000, 64, 32), (2048, 192, 256), (1024, 1024, 512), (4096, 32, 32)]:
+        run(eng, M, N, K, 2, False, exact=False, precision=2)
+    run(eng, 8192, 128, 64, 1, True, exact=False, precision=2)
     # timing: big memory-bound and compute-bound cases
     for (M, N, K, gm) in [(18874368 // 4, 32, 32, False), (18874368 // 4, 64, 32, True), (1 << 20, 128, 128, False), (1 << 19, 256, 256, False),
                           (65536, 1024, 512, False)]:
         A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda"); b = torch.randn(N, device="cuda")
-        for tf32 in (False, True):
-            eng.debug_gemm(A, W, b, act=1, group_max=gm, tf32=tf32)
+        for tf32 in (0, 1, 2):
+            eng.debug_gemm(A, W, b, act=1, group_max=gm, precision=tf32)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5):
-                eng.debug_gemm(A, W, b, act=1, group_max=gm, tf32=tf32)
+                eng.debug_gemm(A, W, b, act=1, group_max=gm, precision=tf32)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             flops = 2.0 * M * N * K
             byts = 4.0 * (M * K + N * K + (M // 32 if gm else M) * N)
-            print(f"time M={M} N={N} K={K} gmax={int(gm)} tf32={int(tf32)}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s")
+            print(f"time M={M} N={N} K={K} gmax={int(gm)} prec={int(tf32)}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s")
 
 
 if __name__ == "__main__":
