@@ -213,7 +213,7 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   w->tr = a.take<float>(C * TRANS);
   w->qq = a.take<float>(C * TRANS);
   w->hm = a.take<float>(B * NPTS * 3);
-  w->human_scratch = a.take<float>(B * 2 * NPTS * 64);
+  w->human_scratch = a.take<float>(B * 2 * NPTS * 64 + B * 128);
   w->fps_start = a.take<int64_t>(4 * C);
   w->t_dev = a.take<int64_t>(B);
   const size_t np[5] = {1024, 1024, 256, 64, 16};

@@ -136,122 +136,157 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// POSA decoder: one CTA (256 threads) per sample.  Pre-norm activations go through a global scratch
-// (L2-resident, 256 KB per sample); GroupNorm(8 groups of 8 channels) statistics over all points of the
-// sample are accumulated in double and applied while the next layer reads the scratch.
+// POSA decoder.  GroupNorm(8 groups of 8 channels) normalises over ALL points of a sample, so each layer is one
+// launch over (sample, 64-point slab) CTAs: the CTA normalises its slab of the previous layer's pre-norm output
+// (statistics from the previous launch), applies ReLU and the 64->64 (or 3->64 / 64->3) linear layer out of shared
+// memory, writes the pre-norm result and adds its partial (sum, sum of squares) per group in double precision.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gn_stats(const float* __restrict__ y, int npts, float* s_mean, float* s_rstd,
-                                         double* s_acc) {
-  // y[npts][64]; thread owns channel tid%64 over points tid/64 + 4k  (256 threads)
-  const int tid = threadIdx.x, ch = tid & 63, p0 = tid >> 6;
-  double s = 0.0, ss = 0.0;
-  for (int p = p0; p < npts; p += 4) {
-    double v = (double)y[p * 64 + ch];
-    s += v;
-    ss += v * v;
-  }
-  // reduce the 8 channels of a group (adjacent lanes) then across the 4 point-slices
-  for (int o = 4; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  }
-  if ((ch & 7) == 0) {
-    s_acc[(p0 * 8 + (ch >> 3)) * 2 + 0] = s;
-    s_acc[(p0 * 8 + (ch >> 3)) * 2 + 1] = ss;
-  }
-  __syncthreads();
-  if (tid < 8) {
-    double a = 0.0, q = 0.0;
-    for (int k = 0; k < 4; ++k) {
-      a += s_acc[(k * 8 + tid) * 2];
-      q += s_acc[(k * 8 + tid) * 2 + 1];
+constexpr int HS = 64;  // points per CTA
+
+// stats[b][layer][group][2] (double): sum, sumsq
+__device__ __forceinline__ void group_stats_accumulate(const float (&acc)[16], int p_valid, int chq, double* stats_out,
+                                                        double* s_red) {
+  // thread holds 16 consecutive channels (2 groups) of one point
+  double s0 = 0, q0 = 0, s1 = 0, q1 = 0;
+  if (p_valid) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s0 += acc[e];
+      q0 += (double)acc[e] * acc[e];
+      s1 += acc[8 + e];
+      q1 += (double)acc[8 + e] * acc[8 + e];
     }
-    double n = (double)npts * 8.0;
-    double mean = a / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[tid] = (float)mean;
-    s_rstd[tid] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  // reduce over the points of the CTA: threads with equal chq (tid % 4)
+  const int tid = threadIdx.x;
+  for (int o = 4; o < 32; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+  }
+  if ((tid & 31) < 4) {
+    double* r = s_red + ((tid >> 5) * 4 + chq) * 4;
+    r[0] = s0; r[1] = q0; r[2] = s1; r[3] = q1;
   }
   __syncthreads();
+  if (tid < 16) {  // 4 chq x 4 values
+    int q = tid >> 2, v = tid & 3;
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += s_red[(w * 4 + q) * 4 + v];
+    int group = q * 2 + (v >> 1);
+    atomicAdd(&stats_out[group * 2 + (v & 1)], t);
+  }
 }
 
-__global__ void __launch_bounds__(256) human_kernel(HumanWeights w, const float* __restrict__ objs,
-                                                    float* __restrict__ scratch, float* __restrict__ hm) {
-  __shared__ __align__(16) float s_w[64 * 64];
-  __shared__ float s_b[64], s_g[64], s_be[64], s_mean[8], s_rstd[8];
-  __shared__ double s_acc[64];
-  __shared__ float s_w3[3 * 64 + 3];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const float* pts = objs + (int64_t)b * NOBJ * NPTS * 3;  // slot 0 = human
-  float* y0 = scratch + (int64_t)b * 2 * NPTS * 64;
-  float* y1 = y0 + NPTS * 64;
-
-  // layer 0: 3 -> 64 (pre-norm) -> y0
-  for (int i = tid; i < 64 * 3; i += 256) s_w[i] = w.w0[i];
+// layer 0: y0 = W0 pts + b0 (3 -> 64), stats
+__global__ void __launch_bounds__(256) human_l0_kernel(HumanWeights w, const float* __restrict__ objs, float* __restrict__ y0,
+                                                       double* __restrict__ stats) {
+  __shared__ float s_w[64 * 3], s_b[64];
+  __shared__ double s_red[8 * 4 * 4];
+  const int b = blockIdx.y, p0 = blockIdx.x * HS, tid = threadIdx.x;
+  if (tid < 192) s_w[tid] = w.w0[tid];
   if (tid < 64) s_b[tid] = w.b0[tid];
   __syncthreads();
-  for (int i = tid; i < NPTS * 64; i += 256) {
-    int p = i >> 6, ch = i & 63;
-    float v = s_b[ch];
-    v = fmaf(s_w[ch * 3 + 0], pts[p * 3 + 0], v);
-    v = fmaf(s_w[ch * 3 + 1], pts[p * 3 + 1], v);
-    v = fmaf(s_w[ch * 3 + 2], pts[p * 3 + 2], v);
-    y0[i] = v;
+  const int p = p0 + (tid >> 2), chq = tid & 3;
+  const float* pt = objs + ((int64_t)b * NOBJ * NPTS + p) * 3;
+  const float x = pt[0], y = pt[1], z = pt[2];
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    int ch = chq * 16 + e;
+    acc[e] = fmaf(s_w[ch * 3 + 2], z, fmaf(s_w[ch * 3 + 1], y, fmaf(s_w[ch * 3], x, s_b[ch])));
+  }
+  float* o = y0 + ((int64_t)b * NPTS + p) * 64 + chq * 16;
+#pragma unroll
+  for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+  group_stats_accumulate(acc, 1, chq, stats + ((int64_t)b * 3 + 0) * 16, s_red);
+}
+
+// layers 1, 2: y = W relu(gn(prev)) + b over npts points (64 -> 64), stats
+__global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict__ Wl, const float* __restrict__ bl,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const float* __restrict__ prev, float* __restrict__ out,
+                                                        double* stats, int slot_in, int slot_out, int npts_in, int npts) {
+  __shared__ __align__(16) float s_w[64 * 68];  // [ch][k], row stride 68 floats (16B aligned, conflict-free float4 reads)
+  __shared__ __align__(16) float s_a[HS * 64];  // normalised + ReLU input slab [p][k]
+  __shared__ float s_b[64], s_scale[64], s_shift[64];
+  __shared__ double s_red[8 * 4 * 4];
+  const int b = blockIdx.y, p0 = blockIdx.x * HS, tid = threadIdx.x;
+  for (int i = tid; i < 64 * 64; i += 256) s_w[(i >> 6) * 68 + (i & 63)] = Wl[i];
+  if (tid < 64) {
+    const double* st = stats + ((int64_t)b * 3 + slot_in) * 16;
+    int g = tid >> 3;
+    double n = (double)npts_in * 8.0;
+    double mean = st[g * 2] / n;
+    double var = st[g * 2 + 1] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    float sc = rstd * gamma[tid];
+    s_scale[tid] = sc;
+    s_shift[tid] = beta[tid] - (float)mean * sc;
+    s_b[tid] = bl[tid];
   }
   __syncthreads();
-  gn_stats(y0, NPTS, s_mean, s_rstd, s_acc);
-
-  // layers 1 and 2: relu(gn(prev)) -> 64 -> 64 (pre-norm)
-  for (int layer = 1; layer <= 2; ++layer) {
-    const float* wl = layer == 1 ? w.w1 : w.w2;
-    const float* bl = layer == 1 ? w.b1 : w.b2;
-    const float* gp = layer == 1 ? w.g0 : w.g1;
-    const float* bp = layer == 1 ? w.be0 : w.be1;
-    const float* src = layer == 1 ? y0 : y1;
-    float* dst = layer == 1 ? y1 : y0;
-    const int npts = layer == 1 ? NPTS : 655;
-    for (int i = tid; i < 64 * 64; i += 256) s_w[i] = wl[i];
-    if (tid < 64) {
-      s_b[tid] = bl[tid];
-      s_g[tid] = gp[tid];
-      s_be[tid] = bp[tid];
-    }
-    __syncthreads();
-    // thread = (point slice tid/64, out channel tid%64): warp reads one input row (broadcast) and 32 weight rows
-    const int ch = tid & 63;
-    for (int p = tid >> 6; p < npts; p += 4) {
-      const float* xr = src + p * 64;
-      float acc = s_b[ch];
-#pragma unroll 8
-      for (int k = 0; k < 64; ++k) {
-        float a = fmaxf((xr[k] - s_mean[k >> 3]) * s_rstd[k >> 3] * s_g[k] + s_be[k], 0.0f);
-        acc = fmaf(s_w[ch * 64 + k], a, acc);
-      }
-      dst[p * 64 + ch] = acc;
-    }
-    __syncthreads();
-    gn_stats(dst, npts, s_mean, s_rstd, s_acc);
+  for (int i = tid; i < HS * 64; i += 256) {
+    int p = p0 + (i >> 6), k = i & 63;
+    float v = p < npts ? prev[((int64_t)b * NPTS + p) * 64 + k] : 0.f;
+    s_a[i] = fmaxf(fmaf(v, s_scale[k], s_shift[k]), 0.0f);
   }
-  // final: relu(gn2(y0[:655])) -> 3, nearest x2 upsample, keep 1024: hm[p] = out[p/2]
-  for (int i = tid; i < 3 * 64; i += 256) s_w3[i] = w.w3[i];
+  __syncthreads();
+  const int pl = tid >> 2, chq = tid & 3, p = p0 + pl;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = s_b[chq * 16 + e];
+#pragma unroll 4
+  for (int k = 0; k < 64; k += 4) {
+    float4 a4 = *reinterpret_cast<const float4*>(&s_a[pl * 64 + k]);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float4 w4 = *reinterpret_cast<const float4*>(&s_w[(chq * 16 + e) * 68 + k]);
+      acc[e] = fmaf(w4.w, a4.w, fmaf(w4.z, a4.z, fmaf(w4.y, a4.y, fmaf(w4.x, a4.x, acc[e]))));
+    }
+  }
+  if (p < npts) {
+    float* o = out + ((int64_t)b * NPTS + p) * 64 + chq * 16;
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+  }
+  group_stats_accumulate(acc, p < npts, chq, stats + ((int64_t)b * 3 + slot_out) * 16, s_red);
+}
+
+// final: hm[2p], hm[2p+1] = W3 relu(gn(y2[p])) + b3 for p < 512 (64 -> 3, nearest x2 upsample, first 1024 kept)
+__global__ void __launch_bounds__(256) human_out_kernel(HumanWeights w, const float* __restrict__ y2,
+                                                        const double* __restrict__ stats, float* __restrict__ hm) {
+  __shared__ float s_w3[3 * 64 + 3], s_scale[64], s_shift[64];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  if (tid < 192) s_w3[tid] = w.w3[tid];
   if (tid < 3) s_w3[192 + tid] = w.b3[tid];
   if (tid < 64) {
-    s_g[tid] = w.g2[tid];
-    s_be[tid] = w.be2[tid];
+    const double* st = stats + ((int64_t)b * 3 + 2) * 16;
+    int g = tid >> 3;
+    double n = 655.0 * 8.0;
+    double mean = st[g * 2] / n;
+    double var = st[g * 2 + 1] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float sc = (float)(1.0 / sqrt(var + 1e-5)) * w.g2[tid];
+    s_scale[tid] = sc;
+    s_shift[tid] = w.be2[tid] - (float)mean * sc;
   }
   __syncthreads();
-  for (int i = tid; i < 512 * 3; i += 256) {
-    int p = i / 3, d = i % 3;
-    const float* xr = y0 + p * 64;
-    float acc = s_w3[192 + d];
-    for (int k = 0; k < 64; ++k) {
-      float a = fmaxf((xr[k] - s_mean[k >> 3]) * s_rstd[k >> 3] * s_g[k] + s_be[k], 0.0f);
-      acc = fmaf(s_w3[d * 64 + k], a, acc);
-    }
-    float* o = hm + ((int64_t)b * NPTS + 2 * p) * 3;
-    o[d] = acc;
-    o[3 + d] = acc;
+  // one warp per point: lanes hold 2 channels each
+  const int lane = tid & 31, p = blockIdx.x * 8 + (tid >> 5);
+  if (p >= 512) return;
+  float2 v = *reinterpret_cast<const float2*>(y2 + ((int64_t)b * NPTS + p) * 64 + lane * 2);
+  float a0 = fmaxf(fmaf(v.x, s_scale[lane * 2], s_shift[lane * 2]), 0.f);
+  float a1 = fmaxf(fmaf(v.y, s_scale[lane * 2 + 1], s_shift[lane * 2 + 1]), 0.f);
+  float r0 = warp_sum(a0 * s_w3[lane * 2] + a1 * s_w3[lane * 2 + 1]);
+  float r1 = warp_sum(a0 * s_w3[64 + lane * 2] + a1 * s_w3[64 + lane * 2 + 1]);
+  float r2 = warp_sum(a0 * s_w3[128 + lane * 2] + a1 * s_w3[128 + lane * 2 + 1]);
+  if (lane < 6) {
+    int d = lane % 3;
+    float r = (d == 0 ? r0 : (d == 1 ? r1 : r2)) + s_w3[192 + d];
+    hm[((int64_t)b * NPTS + 2 * p + lane / 3) * 3 + d] = r;
   }
 }
 
@@ -271,8 +306,17 @@ int launch_time_embed(const float* pe, const float* w1, const float* b1, const f
 }
 
 int launch_human(const HumanWeights& w, const float* objs, int B, float* scratch, float* hm, cudaStream_t st) {
-  human_kernel<<<B, 256, 0, st>>>(w, objs, scratch, hm);
-  return 1;
+  // scratch: y0[B,1024,64] | y1[B,1024,64] | stats[B,3,8,2] doubles
+  float* y0 = scratch;
+  float* y1 = scratch + (size_t)B * NPTS * 64;
+  double* stats = reinterpret_cast<double*>(scratch + (size_t)2 * B * NPTS * 64);
+  cudaMemsetAsync(stats, 0, sizeof(double) * B * 3 * 16, st);
+  human_l0_kernel<<<dim3(NPTS / HS, B), 256, 0, st>>>(w, objs, y0, stats);
+  // layer 1 over 1024 points (stats slot 0 -> 1); layer 2 over the first 655 points (stats slot 1 -> 2)
+  human_mid_kernel<<<dim3(NPTS / HS, B), 256, 0, st>>>(w.w1, w.b1, w.g0, w.be0, y0, y1, stats, 0, 1, NPTS, NPTS);
+  human_mid_kernel<<<dim3((655 + HS - 1) / HS, B), 256, 0, st>>>(w.w2, w.b2, w.g1, w.be1, y1, y0, stats, 1, 2, NPTS, 655);
+  human_out_kernel<<<dim3(512 / 8, B), 256, 0, st>>>(w, y0, stats, hm);
+  return 4;
 }
 
 }  // namespace lsdm

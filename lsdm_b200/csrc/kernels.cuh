@@ -59,7 +59,7 @@ struct HumanWeights {
   const float *w2, *b2, *g2, *be2;  // 64->64 on the first 655 points
   const float *w3, *b3;             // 64->3
 };
-// POSA decoder, one CTA per sample; scratch[B,2,1024,64]; hm[B,1024,3]
+// POSA decoder (4 launches); scratch: y0[B,1024,64] | y1[B,1024,64] | GroupNorm stats [B,3,8,2] doubles; hm[B,1024,3]
 int launch_human(const HumanWeights& w, const float* objs /*[B,9,1024,3], slot 0 used*/, int B, float* scratch,
                  float* hm, cudaStream_t st);
 

@@ -88,16 +88,36 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
   constexpr uint32_t idesc2 = umma_idesc_tf32(128, C2), idesc3 = umma_idesc_tf32(128, C3);
   uint32_t phase = 0;
 
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  // contiguous tile range per CTA (consecutive tiles share a cloud: xyz / P rows stay hot in L1/L2); the group index of
+  // tile+2 and the coordinates of tile+1 are fetched one iteration early so the two dependent global latencies
+  // (grp -> xyz) are off the per-tile critical path
+  const int per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = (t0 + per < a.n_tiles) ? t0 + per : a.n_tiles;
+  struct Pre { int j; float jx, jy, jz, cx, cy, cz; };
+  auto load_idx = [&](int tile) -> int { return tile < t1 ? a.grp[(int64_t)tile * 128 + tid] : 0; };
+  auto load_pts = [&](int tile, int j) -> Pre {
+    Pre p{j, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (tile < t1) {
+      const int64_t cs = ((int64_t)tile * 128 + tid) >> 5;
+      const float* pj = a.xyz + ((cs / a.S) * a.N + j) * 3;
+      const float* pc = a.new_xyz + cs * 3;
+      p.jx = pj[0]; p.jy = pj[1]; p.jz = pj[2];
+      p.cx = pc[0]; p.cy = pc[1]; p.cz = pc[2];
+    }
+    return p;
+  };
+  Pre cur = load_pts(t0, load_idx(t0));
+  int j1 = load_idx(t0 + 1);
+  for (int tile = t0; tile < t1; ++tile) {
     // ---------------- gather + first layer (CUDA cores, exact fp32 geometry) ----------------
+    const Pre nxt = load_pts(tile + 1, j1);
+    j1 = load_idx(tile + 2);
     const int64_t row = (int64_t)tile * 128 + tid;
     const int64_t cs = row >> 5;
     const int64_t c = cs / a.S;
-    const int j = a.grp[row];
-    const float* pj = a.xyz + (c * a.N + j) * 3;
-    const float* pc = a.new_xyz + cs * 3;
-    const float jx = pj[0], jy = pj[1], jz = pj[2];
-    const float rx = jx - pc[0], ry = jy - pc[1], rz = jz - pc[2];
+    const int j = cur.j;
+    const float jx = cur.jx, jy = cur.jy, jz = cur.jz;
+    const float rx = jx - cur.cx, ry = jy - cur.cy, rz = jz - cur.cz;
     const float* prow = FIRST ? nullptr : a.P + (c * a.N + j) * C1;
 #pragma unroll 1
     for (int kb = 0; kb < KB2; ++kb) {
@@ -220,6 +240,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
       orow[c0 + lane] = __uint_as_float(res);
     }
     tc_fence_before();  // the next tile's MMAs overwrite D2/D3 only after every thread's loads above
+    cur = nxt;
   }
   tc_fence_before();
   __syncthreads();
