@@ -183,7 +183,7 @@ def run_ours(args):
     hoisted = args.mode == "hoisted"
     T = 1000
 
-    model = SceneDiffusionModel(**get_default_model_proxd())
+    model = SceneDiffusionModel(**{**get_default_model_proxd(), "device": local_rank})
     model.load_state_dict(syn.make_state_dict(0, "wellcond"))
     model.eval()
     diff = create_gaussian_diffusion(get_default_diffusion())

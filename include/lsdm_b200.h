@@ -149,7 +149,8 @@ LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h);
 LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32_t precision_step);
 
 /* Tuning knobs.  "sa_fused": 0 = set-abstraction blocks as gather + GEMM launches, 1 = fused tensor-core SA kernel with the
- * activations staged in shared memory, 2 = fused with the activations kept in tensor memory (A-from-TMEM MMA). */
+ * activations staged in shared memory, 2 = fused with the activations kept in tensor memory (A-from-TMEM MMA), 3 = levels 1-2
+ * with the transposed-last-layer variant (in-register max-pool, constant-bank weights), level 3 as in 2. */
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value);
 
 /* Test hook: one linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) through the fp32 (precision 0) or tcgen05 TF32 / 3xTF32

@@ -59,10 +59,18 @@ struct Bump {
 
 struct Workspace {
   // conditions
-  float *enc, *out_cat, *attn_w, *tr, *qq, *hm, *human_scratch;
-  int64_t *fps_start, *t_dev;
-  int *idx[4], *grp[4], *nn_idx[4];
-  float *xyz[5], *feat[5], *nn_w[4];
+  float* human_scratch;
+  int64_t* t_dev;
+  // selection results (depend only on the clouds and the FPS start draws); two sets so that lsdm_sample_loop can run the
+  // selection chain of step k+1 on a side stream while the dense layers of step k run on the caller's stream
+  struct Sel {
+    float *enc, *out_cat, *attn_w, *tr, *qq, *hm;  // step-invariant condition-MLP / human-decoder outputs
+    int64_t* fps_start;
+    int *idx[4], *grp[4], *nn_idx[4];
+    float *xyz[5], *nn_w[4];
+  } sel[2];
+  int cur;  // set used by the last encode (debug taps)
+  float* feat[5];
   float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out;
   // step
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
@@ -83,16 +91,20 @@ struct lsdm_handle {
   float *sa_w[4][3], *sa_b[4][3], *sa_wx[4], *sa_wf[4];
   float *fp_w[4][3], *fp_b[4][3], *fp_wa[4], *fp_wb[4];
   float *head_w, *head_b;
+  std::vector<float> host_wx[2], host_wf[2], host_b1[2], host_b2[2];  // host copies for the v2 fused SA kernels (kernel params)
   // schedule
   float* sched = nullptr;  // 5 x T
   int T = 0;
   Workspace ws{};
   bool have_ws = false;
   int64_t launches = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_sel[2] = {nullptr, nullptr}, ev_dense[2] = {nullptr, nullptr};
   // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
   int precision = 0;       // dense layers of the condition encoder (PointNet++): 0 fp32, 1 tf32, 2 3xtf32
   int precision_step = 0;
-  int sa_fused = 0;  // 0: gather + GEMMs; 1: fused SA kernel, A operands in smem; 2: fused, A operands in TMEM  // dense layers of the per-step x0 network + upsampler
+  int sa_fused = 0;  // 0: gather + GEMMs; 1: fused SA kernel, A operands in smem; 2: fused, A operands in TMEM;
+                     // 3: levels 0-1 with the transposed-last-layer kernel (v2), level 2 as in 2  // dense layers of the per-step x0 network + upsampler
   bool profiling = false;
   struct ProfRec { int cls; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
@@ -207,29 +219,33 @@ void build_registry(lsdm_handle* h) {
 size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   const size_t B = (size_t)h->cfg.batch_local, C = B * NOBJ, nc = (size_t)h->cfg.n_cats;
   Bump a(base);
-  w->enc = a.take<float>(B * LAT);
-  w->out_cat = a.take<float>(B * nc);
-  w->attn_w = a.take<float>(B * NOBJ);
-  w->tr = a.take<float>(C * TRANS);
-  w->qq = a.take<float>(C * TRANS);
-  w->hm = a.take<float>(B * NPTS * 3);
   w->human_scratch = a.take<float>(B * 2 * NPTS * 64 + B * 128);
-  w->fps_start = a.take<int64_t>(4 * C);
   w->t_dev = a.take<int64_t>(B);
   const size_t np[5] = {1024, 1024, 256, 64, 16};
   const size_t fc[5] = {3, 64, 128, 256, 512};
-  w->xyz[0] = nullptr;
   w->feat[0] = nullptr;
-  for (int l = 1; l <= 4; ++l) {
-    w->idx[l - 1] = a.take<int>(C * np[l]);
-    w->grp[l - 1] = a.take<int>(C * np[l] * 32);
-    w->xyz[l] = a.take<float>(C * np[l] * 3);
-    w->feat[l] = a.take<float>(C * np[l] * fc[l]);
-  }
+  w->cur = 0;
   const size_t fn[4] = {64, 256, 1024, 1024};  // fine-point count of fp4, fp3, fp2, fp1
-  for (int l = 0; l < 4; ++l) {
-    w->nn_idx[l] = a.take<int>(C * fn[l] * 3);
-    w->nn_w[l] = a.take<float>(C * fn[l] * 3);
+  for (int l = 1; l <= 4; ++l) w->feat[l] = a.take<float>(C * np[l] * fc[l]);
+  for (int k = 0; k < 2; ++k) {
+    Workspace::Sel& s = w->sel[k];
+    s.enc = a.take<float>(B * LAT);
+    s.out_cat = a.take<float>(B * nc);
+    s.attn_w = a.take<float>(B * NOBJ);
+    s.tr = a.take<float>(C * TRANS);
+    s.qq = a.take<float>(C * TRANS);
+    s.hm = a.take<float>(B * NPTS * 3);
+    s.fps_start = a.take<int64_t>(4 * C);
+    s.xyz[0] = nullptr;
+    for (int l = 1; l <= 4; ++l) {
+      s.idx[l - 1] = a.take<int>(C * np[l]);
+      s.grp[l - 1] = a.take<int>(C * np[l] * 32);
+      s.xyz[l] = a.take<float>(C * np[l] * 3);
+    }
+    for (int l = 0; l < 4; ++l) {
+      s.nn_idx[l] = a.take<int>(C * fn[l] * 3);
+      s.nn_w[l] = a.take<float>(C * fn[l] * 3);
+    }
   }
   w->tA = a.take<float>(C * 1048576);
   w->tB = a.take<float>(C * 1048576);
@@ -309,33 +325,75 @@ int check_ready(lsdm_handle* h, bool need_cond) {
   return LSDM_OK;
 }
 
-int pointnet2(lsdm_handle* h, const float* clouds, cudaStream_t st) {
+// FPS (4 levels), ball queries (4 levels), 3-NN weights (4 levels): everything that depends only on coordinates.
+// Also the small per-sample condition MLPs and the POSA human decoder, which are equally independent of x / t.
+int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const float* clouds, const float* cats,
+                 const float* mask_global, const int64_t* fps_start, cudaStream_t st) {
+  const int B = h->cfg.batch_local, C = B * NOBJ;
+  Workspace& w = h->ws;
+  {
+    const float* objs = clouds;
+    CondWeights cw{h->W("embed_text.0.weight"), h->W("embed_text.0.bias"), h->W("embed_text.2.weight"), h->W("embed_text.2.bias"),
+                   h->W("embed_text.4.weight"), h->W("embed_text.4.bias"), h->W("predict_cat.0.weight"), h->W("predict_cat.0.bias"),
+                   h->W("predict_cat.2.weight"), h->W("predict_cat.2.bias"), h->W("predict_cat.4.weight"), h->W("predict_cat.4.bias"),
+                   h->W("embed_cat.0.weight"), h->W("embed_cat.0.bias"), h->W("attn_layer.q_proj_weight"),
+                   h->W("attn_layer.k_proj_weight"), h->W("attn_layer.in_proj_bias"), h->W("translation_layer.0.weight"),
+                   h->W("translation_layer.0.bias"), h->W("translation_layer.2.weight"), h->W("translation_layer.2.bias"),
+                   h->W("pcd_attention.q_proj_weight"), h->W("pcd_attention.in_proj_bias")};
+    prof_launch(h, st, K_COND, [&] { return launch_cond(cw, text, cats, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset,
+                                                        h->cfg.n_cats, q.enc, q.out_cat, q.attn_w, q.tr, q.qq, st); });
+    HumanWeights hw{};
+    hw.w0 = h->W("human_backbone.de_spiral.0.conv.layer.weight"); hw.b0 = h->W("human_backbone.de_spiral.0.conv.layer.bias");
+    hw.g0 = h->W("human_backbone.de_spiral.0.norm.weight"); hw.be0 = h->W("human_backbone.de_spiral.0.norm.bias");
+    hw.w1 = h->W("human_backbone.de_spiral.1.conv.layer.weight"); hw.b1 = h->W("human_backbone.de_spiral.1.conv.layer.bias");
+    hw.g1 = h->W("human_backbone.de_spiral.1.norm.weight"); hw.be1 = h->W("human_backbone.de_spiral.1.norm.bias");
+    hw.w2 = h->W("human_backbone.de_spiral.2.conv.layer.weight"); hw.b2 = h->W("human_backbone.de_spiral.2.conv.layer.bias");
+    hw.g2 = h->W("human_backbone.de_spiral.2.norm.weight"); hw.be2 = h->W("human_backbone.de_spiral.2.norm.bias");
+    hw.w3 = h->W("human_backbone.de_spiral.3.layer.weight"); hw.b3 = h->W("human_backbone.de_spiral.3.layer.bias");
+    prof_launch(h, st, K_COND, [&] { return launch_human(hw, objs, B, w.human_scratch, q.hm, st); });
+  }
+  if (fps_start != q.fps_start) CK(cudaMemcpyAsync(q.fps_start, fps_start, sizeof(int64_t) * 4 * C, cudaMemcpyDefault, st));
+  prof_launch(h, st, K_FPS, [&] { return launch_fps4(clouds, q.fps_start, C, q.idx[0], q.idx[1], q.idx[2], q.idx[3], q.xyz[1], q.xyz[2],
+                                                     q.xyz[3], q.xyz[4], st); });
+  const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
+  for (int l = 0; l < 4; ++l)
+    prof_launch(h, st, K_BALL, [&] { return launch_ball_query(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st); });
+  const int fine[4] = {3, 2, 1, 0}, coarse[4] = {4, 3, 2, 1};
+  const int fineN[4] = {64, 256, 1024, 1024}, coarseN[4] = {16, 64, 256, 1024};
+  for (int l = 0; l < 4; ++l)
+    prof_launch(h, st, K_3NN, [&] { return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st); });
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+// Dense layers of PointNet++ given the selection results.
+int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cudaStream_t st) {
   Workspace& w = h->ws;
   const int C = h->cfg.batch_local * NOBJ;
-  prof_launch(h, st, K_FPS, [&] { return launch_fps4(clouds, w.fps_start, C, w.idx[0], w.idx[1], w.idx[2], w.idx[3], w.xyz[1], w.xyz[2], w.xyz[3],
-                             w.xyz[4], st); });
-  const float* xyz[5] = {clouds, w.xyz[1], w.xyz[2], w.xyz[3], w.xyz[4]};
+  const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   const float* feat[5] = {clouds, w.feat[1], w.feat[2], w.feat[3], w.feat[4]};
   for (int l = 0; l < 4; ++l) {
     const SASpec& s = kSA[l];
     const int N = s.N, S = s.npoint, C1 = s.mlp[0], C2 = s.mlp[1], C3 = s.mlp[2];
-    prof_launch(h, st, K_BALL, [&] { return launch_ball_query(xyz[l], xyz[l + 1], C, N, S, s.radius, w.grp[l], st); });
     const float* P = nullptr;
     if (l > 0) {  // first conv, feature half, once per source point
       GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE));
       P = w.tP;
     }
-    const int fused_max_level = h->sa_fused == 2 ? 2 : 1;
+    const int fused_max_level = h->sa_fused >= 2 ? 2 : 1;
     if (h->precision >= 1 && h->sa_fused > 0 && l <= fused_max_level) {
       int r = prof_launch(h, st, K_GEMM, [&] {
-        return launch_sa_fused(l, h->sa_fused == 2, P, xyz[l], xyz[l + 1], w.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
+        if (h->sa_fused == 3 && l <= 1)
+          return launch_sa_fused_v2(l, P, xyz[l], xyz[l + 1], q.grp[l], h->host_wx[l].data(), h->host_wf[l].data(), h->host_b1[l].data(),
+                                    h->host_b2[l].data(), h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], st);
+        return launch_sa_fused(l, h->sa_fused >= 2, P, xyz[l], xyz[l + 1], q.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
                                h->sa_w[l][1], h->sa_b[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], st);
       });
       if (r < 0) return fail(LSDM_EINVAL, "fused SA kernel unavailable for this level");
       if (h->profiling) h->gemm_flops += 2.0 * C * S * 32 * ((double)C1 * C2 + (double)C2 * C3);
       continue;
     }
-    prof_launch(h, st, K_GATHER, [&] { return launch_sa_gather(P, h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0], xyz[l], xyz[l + 1], w.grp[l], C, N, S, C1,
+    prof_launch(h, st, K_GATHER, [&] { return launch_sa_gather(P, h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0], xyz[l], xyz[l + 1], q.grp[l], C, N, S, C1,
                                     w.tA, st); });
     const int rows = C * S * 32;
     GE(gemm(h, st, w.tA, C1, h->sa_w[l][1], C1, w.tB, C2, h->sa_b[l][1], rows, C2, C1, ACT_RELU));
@@ -349,14 +407,13 @@ int pointnet2(lsdm_handle* h, const float* clouds, cudaStream_t st) {
   for (int l = 0; l < 4; ++l) {
     const FPSpec& s = kFP[l];
     const int N = fineN[l], S = coarseN[l], C1 = s.mlp[0];
-    prof_launch(h, st, K_3NN, [&] { return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, N, S, w.nn_idx[l], w.nn_w[l], st); });
     const float* Pa = nullptr;
     if (s.Ca > 0) {
       GE(gemm(h, st, feat[fine[l]], s.Ca, h->fp_wa[l], s.Ca, w.tA, C1, h->fp_b[l][0], C * N, C1, s.Ca, ACT_NONE));
       Pa = w.tA;
     }
     GE(gemm(h, st, coarse_feat, s.Cb, h->fp_wb[l], s.Cb, w.tB, C1, nullptr, C * S, C1, s.Cb, ACT_NONE));
-    prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, h->fp_b[l][0], w.tB, w.nn_idx[l], w.nn_w[l], C, N, S, C1, w.tP, st); });
+    prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l], C, N, S, C1, w.tP, st); });
     if (l < 3) {
       GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU));
       coarse_feat = outs[l];
@@ -380,7 +437,7 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   if (t != w.t_dev) CK(cudaMemcpyAsync(w.t_dev, t, sizeof(int64_t) * B, cudaMemcpyDefault, st));
   prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
                                    h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
-                                   h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.enc, h->W("upsampling_layer.0.weight"),
+                                   h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.sel[w.cur].enc, h->W("upsampling_layer.0.weight"),
                                    h->W("upsampling_layer.0.bias"), B, w.s256, w.H1, st); });
   GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), B * 256, 512,
           128, ACT_GELU, 0, h->precision_step));
@@ -459,6 +516,12 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
     return fail(LSDM_ENOMEM, std::string("cudaMalloc weights: ") + cudaGetErrorString(e));
   }
   h->derived = h->arena + h->arena_floats;
+  cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&h->ev_sel[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_dense[i], cudaEventDisableTiming);
+  }
   *out = h;
   return LSDM_OK;
 }
@@ -468,6 +531,12 @@ LSDM_API void lsdm_destroy(lsdm_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->arena) cudaFree(h->arena);
   if (h->sched) cudaFree(h->sched);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_sel[i]) cudaEventDestroy(h->ev_sel[i]);
+    if (h->ev_dense[i]) cudaEventDestroy(h->ev_dense[i]);
+  }
   delete h;
 }
 
@@ -560,6 +629,19 @@ LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
   fold("pcd_backbone.conv1", "pcd_backbone.bn1", 128, 128, &h->head_w, &h->head_b);
   if (off > h->derived_floats) return fail(LSDM_ENOMEM, "derived weight arena too small");
   CK(cudaPeekAtLastError());
+  // host copies of the small per-channel vectors of sa1 / sa2 (kernel parameters of the v2 fused kernels)
+  for (int l = 0; l < 2; ++l) {
+    const int C1 = kSA[l].mlp[0], C2 = kSA[l].mlp[1];
+    h->host_wx[l].resize(C1 * 3);
+    h->host_wf[l].assign(C1 * 3, 0.f);
+    h->host_b1[l].resize(C1);
+    h->host_b2[l].resize(C2);
+    CK(cudaMemcpyAsync(h->host_wx[l].data(), h->sa_wx[l], sizeof(float) * C1 * 3, cudaMemcpyDeviceToHost, st));
+    if (l == 0) CK(cudaMemcpyAsync(h->host_wf[l].data(), h->sa_wf[l], sizeof(float) * C1 * 3, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->host_b1[l].data(), h->sa_b[l][0], sizeof(float) * C1, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->host_b2[l].data(), h->sa_b[l][1], sizeof(float) * C2, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));  // one-off, load time only
   h->finalized = true;
   return LSDM_OK;
 }
@@ -599,41 +681,30 @@ LSDM_API int lsdm_set_workspace(lsdm_handle* h, void* workspace, size_t bytes) {
   return LSDM_OK;
 }
 
+// Everything of the condition encoder except the selection chain (which the caller has already enqueued for set `si`).
+static int encode_dense(lsdm_handle* h, const float* text, const float* objs, const float* cats, const float* mask_global, int si,
+                        cudaStream_t st) {
+  Workspace& w = h->ws;
+  const int B = h->cfg.batch_local;
+  GE(dense_phase(h, w.sel[si], objs, st));
+  SceneWeights sw{h->W("pcd_attention.k_proj_weight"), h->W("pcd_attention.v_proj_weight"), h->W("pcd_attention.in_proj_bias"),
+                  h->W("pcd_attention.out_proj.weight"), h->W("pcd_attention.out_proj.bias"),
+                  h->W("point_wise_trans_layer.0.weight"), h->W("point_wise_trans_layer.0.bias")};
+  prof_launch(h, st, K_SCENE, [&] { return launch_point_attention(sw, w.backbone, w.sel[si].attn_w, w.sel[si].qq, B, w.pa, w.pw, st); });
+  prof_launch(h, st, K_SCENE, [&] { return launch_scene_mix(w.pw, w.sel[si].hm, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, w.pcd_out, st); });
+  CK(cudaPeekAtLastError());
+  w.cur = si;
+  h->have_cond = true;
+  return LSDM_OK;
+}
+
 LSDM_API int lsdm_encode_conditions(lsdm_handle* h, const float* text, const float* objs, const float* cats, const float* mask_global,
                            const int64_t* fps_start, void* stream) {
   GE(check_ready(h, false));
   if (!text || !objs || !cats || !mask_global || !fps_start) return fail(LSDM_EINVAL, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  Workspace& w = h->ws;
-  const int B = h->cfg.batch_local, C = B * NOBJ;
-  CK(cudaMemcpyAsync(w.fps_start, fps_start, sizeof(int64_t) * 4 * C, cudaMemcpyDefault, st));
-  CondWeights cw{h->W("embed_text.0.weight"), h->W("embed_text.0.bias"), h->W("embed_text.2.weight"), h->W("embed_text.2.bias"),
-                 h->W("embed_text.4.weight"), h->W("embed_text.4.bias"), h->W("predict_cat.0.weight"), h->W("predict_cat.0.bias"),
-                 h->W("predict_cat.2.weight"), h->W("predict_cat.2.bias"), h->W("predict_cat.4.weight"), h->W("predict_cat.4.bias"),
-                 h->W("embed_cat.0.weight"), h->W("embed_cat.0.bias"), h->W("attn_layer.q_proj_weight"),
-                 h->W("attn_layer.k_proj_weight"), h->W("attn_layer.in_proj_bias"), h->W("translation_layer.0.weight"),
-                 h->W("translation_layer.0.bias"), h->W("translation_layer.2.weight"), h->W("translation_layer.2.bias"),
-                 h->W("pcd_attention.q_proj_weight"), h->W("pcd_attention.in_proj_bias")};
-  prof_launch(h, st, K_COND, [&] { return launch_cond(cw, text, cats, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, h->cfg.n_cats, w.enc,
-                             w.out_cat, w.attn_w, w.tr, w.qq, st); });
-  HumanWeights hw{};
-  hw.w0 = h->W("human_backbone.de_spiral.0.conv.layer.weight"); hw.b0 = h->W("human_backbone.de_spiral.0.conv.layer.bias");
-  hw.g0 = h->W("human_backbone.de_spiral.0.norm.weight"); hw.be0 = h->W("human_backbone.de_spiral.0.norm.bias");
-  hw.w1 = h->W("human_backbone.de_spiral.1.conv.layer.weight"); hw.b1 = h->W("human_backbone.de_spiral.1.conv.layer.bias");
-  hw.g1 = h->W("human_backbone.de_spiral.1.norm.weight"); hw.be1 = h->W("human_backbone.de_spiral.1.norm.bias");
-  hw.w2 = h->W("human_backbone.de_spiral.2.conv.layer.weight"); hw.b2 = h->W("human_backbone.de_spiral.2.conv.layer.bias");
-  hw.g2 = h->W("human_backbone.de_spiral.2.norm.weight"); hw.be2 = h->W("human_backbone.de_spiral.2.norm.bias");
-  hw.w3 = h->W("human_backbone.de_spiral.3.layer.weight"); hw.b3 = h->W("human_backbone.de_spiral.3.layer.bias");
-  prof_launch(h, st, K_COND, [&] { return launch_human(hw, objs, B, w.human_scratch, w.hm, st); });
-  GE(pointnet2(h, objs, st));
-  SceneWeights sw{h->W("pcd_attention.k_proj_weight"), h->W("pcd_attention.v_proj_weight"), h->W("pcd_attention.in_proj_bias"),
-                  h->W("pcd_attention.out_proj.weight"), h->W("pcd_attention.out_proj.bias"),
-                  h->W("point_wise_trans_layer.0.weight"), h->W("point_wise_trans_layer.0.bias")};
-  prof_launch(h, st, K_SCENE, [&] { return launch_point_attention(sw, w.backbone, w.attn_w, w.qq, B, w.pa, w.pw, st); });
-  prof_launch(h, st, K_SCENE, [&] { return launch_scene_mix(w.pw, w.hm, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, w.pcd_out, st); });
-  CK(cudaPeekAtLastError());
-  h->have_cond = true;
-  return LSDM_OK;
+  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start, st));
+  return encode_dense(h, text, objs, cats, mask_global, 0, st);
 }
 
 LSDM_API int lsdm_denoise_step(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,
@@ -650,7 +721,7 @@ LSDM_API int lsdm_forward(lsdm_handle* h, float* x, const int64_t* t, float* out
   cudaStream_t st = (cudaStream_t)stream;
   GE(step_core(h, x, t, nullptr, nullptr, x0, guiding, true, 0, st));
   if (out_cat)
-    CK(cudaMemcpyAsync(out_cat, h->ws.out_cat, sizeof(float) * h->cfg.batch_local * h->cfg.n_cats, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(out_cat, h->ws.sel[h->ws.cur].out_cat, sizeof(float) * h->cfg.batch_local * h->cfg.n_cats, cudaMemcpyDeviceToDevice, st));
   return LSDM_OK;
 }
 
@@ -666,9 +737,34 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
   const size_t per = (size_t)B * NPTS * 3;
   // device-side timestep vector (the reference builds th.tensor([i]*B) on the host every step, gaussian_diffusion.py:737)
   int64_t* tvec = h->ws.t_dev;
+  if (!text || !objs || !cats || !mask_global) return fail(LSDM_EINVAL, "null argument");
+  // STRICT: the selection chain (FPS -> ball queries -> 3-NN) of step k+1 depends only on the clouds and on that step's
+  // FPS start draws, never on x, so it runs on the handle's side stream while the dense layers of step k occupy the
+  // caller's stream (two selection buffer sets; events order producer / consumer / reuse).
+  const bool pipelined = !hoisted && n_steps > 1 && !h->profiling;
+  cudaStream_t side = pipelined ? h->side : st;
+  if (pipelined) {
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(side, h->ev_fork, 0));
+  }
+  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side));
+  if (pipelined) CK(cudaEventRecord(h->ev_sel[0], side));
   for (int k = 0; k < n_steps; ++k) {
-    if (!hoisted || k == 0)
-      GE(lsdm_encode_conditions(h, text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, stream));
+    const int si = hoisted ? 0 : (k & 1);
+    if (!hoisted && k + 1 < n_steps) {
+      const int sn = (k + 1) & 1;
+      if (pipelined && k >= 1) CK(cudaStreamWaitEvent(side, h->ev_dense[sn], 0));  // set sn was last read by dense(k-1)
+      if (pipelined) {
+        GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side));
+        CK(cudaEventRecord(h->ev_sel[sn], side));
+      }
+    }
+    if (pipelined) CK(cudaStreamWaitEvent(st, h->ev_sel[si], 0));
+    if (!pipelined && !hoisted && k >= 1) GE(select_phase(h, h->ws.sel[si], text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, st));
+    if (!hoisted || k == 0) {
+      GE(encode_dense(h, text, objs, cats, mask_global, si, st));
+      if (pipelined) CK(cudaEventRecord(h->ev_dense[si], st));
+    }
     prof_launch(h, st, K_OTHER, [&] {
       fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(tvec, B, (int64_t)(t_first - k));
       return 1;
@@ -684,7 +780,7 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
 
 LSDM_API int lsdm_get_out_cat(lsdm_handle* h, float* out_cat, void* stream) {
   GE(check_ready(h, true));
-  CK(cudaMemcpyAsync(out_cat, h->ws.out_cat, sizeof(float) * h->cfg.batch_local * h->cfg.n_cats, cudaMemcpyDeviceToDevice,
+  CK(cudaMemcpyAsync(out_cat, h->ws.sel[h->ws.cur].out_cat, sizeof(float) * h->cfg.batch_local * h->cfg.n_cats, cudaMemcpyDeviceToDevice,
                      (cudaStream_t)stream));
   return LSDM_OK;
 }
@@ -724,18 +820,19 @@ LSDM_API int lsdm_cat_loss(lsdm_handle* h, const float* probs, const float* targ
 LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, size_t dst_bytes, void* stream) {
   if (!h || !name || !h->have_ws) return fail(LSDM_EINVAL, "bad argument");
   const Workspace& w = h->ws;
+  const Workspace::Sel& q = w.sel[w.cur];
   const int64_t B = h->cfg.batch_local, C = B * NOBJ;
   struct Tap { const char* n; const void* p; int64_t count; size_t esz; };
   const Tap taps[] = {
-      {"backbone", w.backbone, C * NPTS * 3, 4}, {"hm", w.hm, B * NPTS * 3, 4}, {"attn_w", w.attn_w, B * NOBJ, 4},
-      {"tr", w.tr, C * TRANS, 4}, {"enc", w.enc, B * LAT, 4}, {"pa", w.pa, C * TRANS, 4}, {"pw", w.pw, C * NPTS * 3, 4},
-      {"emb_cat", w.cat, B * NPTS * 256, 4}, {"pcd_out", w.pcd_out, B * NPTS * 3, 4}, {"out_cat", w.out_cat, B * h->cfg.n_cats, 4},
-      {"fps_idx0", w.idx[0], C * 1024, 4}, {"fps_idx1", w.idx[1], C * 256, 4}, {"fps_idx2", w.idx[2], C * 64, 4},
-      {"fps_idx3", w.idx[3], C * 16, 4}, {"ball_idx0", w.grp[0], C * 1024 * 32, 4}, {"ball_idx1", w.grp[1], C * 256 * 32, 4},
-      {"ball_idx2", w.grp[2], C * 64 * 32, 4}, {"ball_idx3", w.grp[3], C * 16 * 32, 4}, {"l1_feat", w.feat[1], C * 1024 * 64, 4},
+      {"backbone", w.backbone, C * NPTS * 3, 4}, {"hm", q.hm, B * NPTS * 3, 4}, {"attn_w", q.attn_w, B * NOBJ, 4},
+      {"tr", q.tr, C * TRANS, 4}, {"enc", q.enc, B * LAT, 4}, {"pa", w.pa, C * TRANS, 4}, {"pw", w.pw, C * NPTS * 3, 4},
+      {"emb_cat", w.cat, B * NPTS * 256, 4}, {"pcd_out", w.pcd_out, B * NPTS * 3, 4}, {"out_cat", q.out_cat, B * h->cfg.n_cats, 4},
+      {"fps_idx0", q.idx[0], C * 1024, 4}, {"fps_idx1", q.idx[1], C * 256, 4}, {"fps_idx2", q.idx[2], C * 64, 4},
+      {"fps_idx3", q.idx[3], C * 16, 4}, {"ball_idx0", q.grp[0], C * 1024 * 32, 4}, {"ball_idx1", q.grp[1], C * 256 * 32, 4},
+      {"ball_idx2", q.grp[2], C * 64 * 32, 4}, {"ball_idx3", q.grp[3], C * 16 * 32, 4}, {"l1_feat", w.feat[1], C * 1024 * 64, 4},
       {"l2_feat", w.feat[2], C * 256 * 128, 4}, {"l3_feat", w.feat[3], C * 64 * 256, 4}, {"l4_feat", w.feat[4], C * 16 * 512, 4},
       {"fp4_feat", w.g3, C * 64 * 256, 4}, {"fp3_feat", w.g2, C * 256 * 256, 4}, {"fp2_feat", w.g1, C * 1024 * 128, 4},
-      {"nn_idx3", w.nn_idx[3], C * 1024 * 3, 4}, {"nn_w3", w.nn_w[3], C * 1024 * 3, 4}, {"nn_idx0", w.nn_idx[0], C * 64 * 3, 4},
+      {"nn_idx3", q.nn_idx[3], C * 1024 * 3, 4}, {"nn_w3", q.nn_w[3], C * 1024 * 3, 4}, {"nn_idx0", q.nn_idx[0], C * 64 * 3, 4},
       {"x0", w.x0, B * NPTS * 3, 4}, {"guiding", w.guiding, B * NPTS * 3, 4}, {"s256", w.s256, B * 256, 4},
   };
   for (const Tap& t : taps) {
@@ -756,7 +853,7 @@ LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h) { return h ? h->launche
 
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   if (!h || !name) return fail(LSDM_EINVAL, "null argument");
-  if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 2) {
+  if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 3) {
     h->sa_fused = value;
     return LSDM_OK;
   }

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict_
                                                         const float* __restrict__ prev, float* __restrict__ out,
                                                         double* stats, int slot_in, int slot_out, int npts_in, int npts) {
   __shared__ __align__(16) float s_w[64 * 68];  // [ch][k], row stride 68 floats (16B aligned, conflict-free float4 reads)
-  __shared__ __align__(16) float s_a[HS * 64];  // normalised + ReLU input slab [p][k]
+  __shared__ __align__(16) float s_a[HS * 68];  // normalised + ReLU input slab [p][k], row stride 68 (conflict-free float4 reads)
   __shared__ float s_b[64], s_scale[64], s_shift[64];
   __shared__ double s_red[8 * 4 * 4];
   const int b = blockIdx.y, p0 = blockIdx.x * HS, tid = threadIdx.x;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict_
   for (int i = tid; i < HS * 64; i += 256) {
     int p = p0 + (i >> 6), k = i & 63;
     float v = p < npts ? prev[((int64_t)b * NPTS + p) * 64 + k] : 0.f;
-    s_a[i] = fmaxf(fmaf(v, s_scale[k], s_shift[k]), 0.0f);
+    s_a[(i >> 6) * 68 + k] = fmaxf(fmaf(v, s_scale[k], s_shift[k]), 0.0f);
   }
   __syncthreads();
   const int pl = tid >> 2, chq = tid & 3, p = p0 + pl;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict_
   for (int e = 0; e < 16; ++e) acc[e] = s_b[chq * 16 + e];
 #pragma unroll 4
   for (int k = 0; k < 64; k += 4) {
-    float4 a4 = *reinterpret_cast<const float4*>(&s_a[pl * 64 + k]);
+    float4 a4 = *reinterpret_cast<const float4*>(&s_a[pl * 68 + k]);
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       float4 w4 = *reinterpret_cast<const float4*>(&s_w[(chq * 16 + e) * 68 + k]);

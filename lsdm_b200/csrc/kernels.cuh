@@ -37,6 +37,10 @@ int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, co
                     const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
                     const float* b3, int n_clouds, int N, int S, float* out, cudaStream_t st);
 
+int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp, const float* h_wx,
+                       const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
+                       int n_clouds, int N, int S, float* out, cudaStream_t st);
+
 // ---- cond.cu --------------------------------------------------------------------------------
 struct CondWeights {
   const float *et0_w, *et0_b, *et2_w, *et2_b, *et4_w, *et4_b;  // embed_text 512->256->256->128

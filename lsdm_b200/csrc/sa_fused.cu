@@ -276,6 +276,222 @@ int launch_t(const SaArgs& a, cudaStream_t st) {
   return 1;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v2 (levels 0 and 1): the last layer is computed TRANSPOSED, D3^T[channel, point] = W3 . h2^T, so that a thread owns one
+// output channel and the 32-sample max-pool is an in-register max over 32 accumulator columns (no cross-lane traffic);
+// the small per-channel vectors (Wx, Wf, biases) travel as kernel parameters so they are constant-bank FFMA operands.
+//   gather (thread = row) -> h1 in TMEM -> MMA2 (A from TMEM) -> D2 -> bias/ReLU/RNA -> h2 in smem (K-major SW128)
+//   -> MMA3^T (A = W3 rows = channels, B = h2 rows = points) -> D3^T (aliases h1/D2 columns) -> max over 4 x 32 columns.
+// TMEM: 128 columns per CTA.
+// ------------------------------------------------------------------------------------------------------------------
+template <int C1, int C2, int C3, bool FIRST>
+struct SaConst {
+  float wx[C1 * 3];
+  float wf[FIRST ? C1 * 3 : 1];
+  float b1[FIRST ? C1 : 1];
+  float b2[C2];
+};
+
+template <int C1, int C2, int C3, bool FIRST>
+__global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(SaArgs a, const __grid_constant__ SaConst<C1, C2, C3, FIRST> k) {
+  static_assert(C3 <= 128 && C1 + C2 <= 128, "v2 covers sa1 / sa2");
+  constexpr int KB2 = C1 / 32, KB3 = C2 / 32;
+  constexpr int W2_BYTES = C2 * C1 * 4, W3_BYTES = 128 * C2 * 4, H2_BYTES = 128 * C2 * 4;
+  constexpr uint32_t COL_H1 = 0, COL_D2 = C1, COL_D3T = 0, TCOLS = 128;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_b3[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW2 = base, sW3 = sW2 + W2_BYTES, sH2 = sW3 + W3_BYTES;
+  const uint32_t bar = smem_u32(&s_bar);
+
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), TCOLS);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (int q = tid; q < C2 * C1 / 4; q += 128) {
+    int n = q / (C1 / 4), k4 = q % (C1 / 4);
+    float4 v = *reinterpret_cast<const float4*>(a.W2 + (int64_t)n * C1 + k4 * 4);
+    st_shared_v4(sW2 + (k4 >> 3) * (C2 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  for (int q = tid; q < 128 * C2 / 4; q += 128) {  // W3 rows >= C3 are zero padding up to the UMMA M of 128
+    int n = q / (C2 / 4), k4 = q % (C2 / 4);
+    float4 v = n < C3 ? *reinterpret_cast<const float4*>(a.W3 + (int64_t)n * C2 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    st_shared_v4(sW3 + (k4 >> 3) * (128 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  s_b3[tid] = tid < C3 ? a.b3[tid] : 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t idesc2 = umma_idesc_tf32(128, C2), idesc3 = umma_idesc_tf32(128, 128);
+  const float bias3 = s_b3[tid];
+  uint32_t phase = 0;
+
+  const int per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = (t0 + per < a.n_tiles) ? t0 + per : a.n_tiles;
+  struct Pre { int j; float jx, jy, jz, cx, cy, cz; };
+  auto load_idx = [&](int tile) -> int { return tile < t1 ? a.grp[(int64_t)tile * 128 + tid] : 0; };
+  auto load_pts = [&](int tile, int j) -> Pre {
+    Pre p{j, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (tile < t1) {
+      const int64_t cs = ((int64_t)tile * 128 + tid) >> 5;
+      const float* pj = a.xyz + ((cs / a.S) * a.N + j) * 3;
+      const float* pc = a.new_xyz + cs * 3;
+      p.jx = pj[0]; p.jy = pj[1]; p.jz = pj[2];
+      p.cx = pc[0]; p.cy = pc[1]; p.cz = pc[2];
+    }
+    return p;
+  };
+  Pre cur = load_pts(t0, load_idx(t0));
+  int j1 = load_idx(t0 + 1);
+  for (int tile = t0; tile < t1; ++tile) {
+    const Pre nxt = load_pts(tile + 1, j1);
+    j1 = load_idx(tile + 2);
+    const int64_t cs = ((int64_t)tile * 128 + tid) >> 5;
+    const int64_t c = cs / a.S;
+    const float jx = cur.jx, jy = cur.jy, jz = cur.jz;
+    const float rx = jx - cur.cx, ry = jy - cur.cy, rz = jz - cur.cz;
+    const float* prow = FIRST ? nullptr : a.P + (c * a.N + cur.j) * C1;
+    // ---- gather + first layer: thread = grouped row, constant-bank weights ----
+#pragma unroll
+    for (int kb = 0; kb < KB2; ++kb) {
+      uint32_t v[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float pv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!FIRST) {
+          float4 p4 = *reinterpret_cast<const float4*>(prow + kb * 32 + q * 4);
+          pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ch = kb * 32 + q * 4 + e;
+          float x = FIRST ? k.b1[FIRST ? ch : 0] : pv[e];
+          x = fmaf(k.wx[ch * 3 + 0], rx, x);
+          x = fmaf(k.wx[ch * 3 + 1], ry, x);
+          x = fmaf(k.wx[ch * 3 + 2], rz, x);
+          if (FIRST) {
+            x = fmaf(k.wf[FIRST ? ch * 3 + 0 : 0], jx, x);
+            x = fmaf(k.wf[FIRST ? ch * 3 + 1 : 0], jy, x);
+            x = fmaf(k.wf[FIRST ? ch * 3 + 2 : 0], jz, x);
+          }
+          v[q * 4 + e] = __float_as_uint(rna_tf32(fmaxf(x, 0.0f)));
+        }
+      }
+      tmem_st32(tlane + COL_H1 + kb * 32, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2: D2[point, ch] = h1 . W2^T (A from TMEM) ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB2; ++kb) {
+        const uint64_t db = umma_desc_sw128(sW2 + kb * (C2 * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_tf32_ts(tmem + COL_D2, tmem + COL_H1 + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc2, (kb | kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 2: bias + ReLU + RNA -> h2 tile in smem (B operand of the transposed last layer) ----
+#pragma unroll
+    for (int kb = 0; kb < KB3; ++kb) {
+      uint32_t v[32];
+      tmem_ld32(tlane + COL_D2 + kb * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 o;
+        o.x = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 0]) + k.b2[kb * 32 + q * 4 + 0], 0.0f));
+        o.y = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 1]) + k.b2[kb * 32 + q * 4 + 1], 0.0f));
+        o.z = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 2]) + k.b2[kb * 32 + q * 4 + 2], 0.0f));
+        o.w = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 3]) + k.b2[kb * 32 + q * 4 + 3], 0.0f));
+        st_shared_v4(sH2 + kb * (128 * 128) + sw128_off(tid, q), o);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 3, transposed: D3T[ch, point] = W3 . h2^T ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB3; ++kb) {
+        const uint64_t da = umma_desc_sw128(sW3 + kb * (128 * 128)), db = umma_desc_sw128(sH2 + kb * (128 * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_tf32_ss(tmem + COL_D3T, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc3, (kb | kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 3: thread = channel; max over each centroid's 32 columns, then bias + ReLU (monotone, so after the max) ----
+    if (tid < C3) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        tmem_ld32(tlane + COL_D3T + g * 32, v);
+        tmem_ld_wait();
+        float m = __uint_as_float(v[0]);
+#pragma unroll
+        for (int e = 1; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
+        a.out[((int64_t)tile * 4 + g) * C3 + tid] = fmaxf(m + bias3, 0.0f);
+      }
+    }
+    tc_fence_before();
+    cur = nxt;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+template <int C1, int C2, int C3, bool FIRST>
+int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float* h_b1, const float* h_b2, cudaStream_t st) {
+  SaConst<C1, C2, C3, FIRST> k;
+  for (int i = 0; i < C1 * 3; ++i) k.wx[i] = h_wx[i];
+  if (FIRST) {
+    for (int i = 0; i < C1 * 3; ++i) k.wf[i] = h_wf[i];
+    for (int i = 0; i < C1; ++i) k.b1[i] = h_b1[i];
+  } else {
+    k.wf[0] = 0.f;
+    k.b1[0] = 0.f;
+  }
+  for (int i = 0; i < C2; ++i) k.b2[i] = h_b2[i];
+  constexpr int need = C2 * C1 * 4 + 2 * 128 * C2 * 4 + 1024;
+  constexpr int by_smem = (227 * 1024) / (need + 1024);
+  constexpr int per_sm = by_smem < 4 ? by_smem : 4;  // 4 x 128 TMEM columns
+  constexpr int floor_smem = (227 * 1024) / (per_sm + 1) + 1;
+  constexpr int smem = need > floor_smem ? need : floor_smem;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(sa_fused_v2_kernel<C1, C2, C3, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return -1;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * per_sm;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  sa_fused_v2_kernel<C1, C2, C3, FIRST><<<grid, 128, smem, st>>>(a, k);
+  return 1;
+}
+
 }  // namespace
 
 // level: 0 (sa1: 6->32->32->64) or 1 (sa2: 67->64->64->128).  a_tmem selects the A-from-TMEM variant.
@@ -286,6 +502,16 @@ int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, co
   if (level == 0) return a_tmem ? launch_t<32, 32, 64, true, true>(a, st) : launch_t<32, 32, 64, true, false>(a, st);
   if (level == 1) return a_tmem ? launch_t<64, 64, 128, false, true>(a, st) : launch_t<64, 64, 128, false, false>(a, st);
   if (level == 2) return a_tmem ? launch_t<128, 128, 256, false, true>(a, st) : -1;
+  return -1;
+}
+
+// v2 (transposed last layer, constant-bank vectors) for levels 0 and 1; h_* are HOST copies of the small per-channel vectors.
+int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp, const float* h_wx,
+                       const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
+                       int n_clouds, int N, int S, float* out, cudaStream_t st) {
+  SaArgs a{P, xyz, new_xyz, grp, nullptr, nullptr, nullptr, W2, nullptr, W3, b3, out, n_clouds * S / 4, N, S};
+  if (level == 0) return launch_v2<32, 32, 64, true>(a, h_wx, h_wf, h_b1, h_b2, st);
+  if (level == 1) return launch_v2<64, 64, 128, false>(a, h_wx, h_wf, h_b1, h_b2, st);
   return -1;
 }
 

@@ -171,7 +171,7 @@ class GaussianDiffusion:
         self._check_x(x)
         net = self._unwrap(model)
         eng = self._engine(model, x.shape[0], x.device)
-        net.encode(mask, given_objs, given_cats, y, fps_start)
+        net.encode(mask, given_objs, given_cats, y, fps_start, device=x.device)
         sample, x0, guiding = eng.denoise_step(x, t, noise, clip_denoised=clip_denoised)
         net.saved_cat = eng.out_cat().unsqueeze(1)
         net.saved_guiding_points = guiding
@@ -268,7 +268,7 @@ class GaussianDiffusion:
             fps0 = net.draw_fps_starts(B)
             nz0 = th.randn_like(img)
             t0 = th.full((B,), n_total - 1, device=img.device, dtype=th.long)
-            net.encode(mask, given_objs, given_cats, text, fps0)
+            net.encode(mask, given_objs, given_cats, text, fps0, device=img.device)
             cur, x0, gd = eng.denoise_step(img, t0, nz0, clip_denoised=clip_denoised)
             done = 1
             while done < n_total:

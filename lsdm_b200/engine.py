@@ -48,7 +48,7 @@ class Engine:
         # default: tensor cores (TF32 condition encoder with the fused SA kernels, 3xTF32 x0 network); LSDM_PRECISION=fp32
         # selects the CUDA-core fp32 build of every dense layer
         self.set_precision(os.environ.get("LSDM_PRECISION", "tf32"))
-        self.set_option("sa_fused", int(os.environ.get("LSDM_SA_FUSED", "2")))
+        self.set_option("sa_fused", int(os.environ.get("LSDM_SA_FUSED", "3")))
 
     # ------------------------------------------------------------------ lifecycle
     def _alloc_workspace(self):

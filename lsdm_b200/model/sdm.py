@@ -237,12 +237,14 @@ class SceneDiffusionModel(nn.Module):
         draws = [torch.randint(0, n, (bg * N_OBJ,), dtype=torch.long) for n in FPS_LEVEL_N]
         return torch.stack([d.view(bg, N_OBJ)[off:off + batch_local].reshape(-1) for d in draws])
 
-    def encode(self, mask, given_objs, given_cats, y, fps_start=None):
+    def encode(self, mask, given_objs, given_cats, y, fps_start=None, device=None):
         """Step-invariant part of forward (reference sdm.py:147-203).  Returns the engine."""
         if self.training:
             raise NotImplementedError("train-mode BatchNorm statistics / dropout are not on the accelerated path yet; call .eval()")
         B = given_objs.shape[0]
-        eng = self.engine(B, given_objs.device if given_objs.is_cuda else torch.device(self.device))
+        if device is None:
+            device = given_objs.device if given_objs.is_cuda else next(self.parameters()).device
+        eng = self.engine(B, device)
         if fps_start is None:
             fps_start = self.draw_fps_starts(B)
         eng.encode_conditions(self._encode_text(y), given_objs, given_cats, mask, fps_start)
@@ -257,7 +259,7 @@ class SceneDiffusionModel(nn.Module):
         """
         if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
             raise ValueError("x must be a contiguous float32 CUDA tensor (it is updated in place)")
-        eng = self.encode(mask, given_objs, given_cats, y)
+        eng = self.encode(mask, given_objs, given_cats, y, device=x.device)
         out_cat, x0, guiding = eng.forward(x, timesteps)
         self.saved_cat = out_cat.unsqueeze(1)
         self.saved_guiding_points = guiding

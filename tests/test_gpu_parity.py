@@ -26,7 +26,7 @@ MODES = ["tf32", "fp32"]
 @pytest.fixture(params=MODES)
 def mode(request, monkeypatch):
     monkeypatch.setenv("LSDM_PRECISION", request.param)
-    monkeypatch.setenv("LSDM_SA_FUSED", "2" if request.param == "tf32" else "0")
+    monkeypatch.setenv("LSDM_SA_FUSED", "3" if request.param == "tf32" else "0")
     return request.param
 
 
