@@ -285,6 +285,27 @@ def run_ours(args):
                        "call, FPS starts drawn on the CPU generator and uploaded per chunk, noise drawn on the device generator "
                        "(as the reference does), final samples read back"}
 
+    # ---- hoisted variant (conditions encoded once per loop; an algorithmic optimisation, reported separately) ----
+    hoisted_info = None
+    if not hoisted:
+        xh = g["x_T"].clone()
+        eng.sample_loop(xh, g["text_emb"], g["given_objs"], g["given_cats"], g["mask"], fps_dev[:1], noise_dev[:W], T - 1, True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        eng.sample_loop(xh, g["text_emb"], g["given_objs"], g["given_cats"], g["mask"], fps_dev[:1], noise_dev[W:W + K], T - 1 - W, True)
+        h1.record()
+        torch.cuda.synchronize()
+        hms = h0.elapsed_time(h1)
+        if world > 1:
+            thm = torch.tensor([hms], device=dev)
+            dist.all_reduce(thm, op=dist.ReduceOp.MAX)
+            hms = float(thm.item())
+        hoisted_info = {"value": Bg * K / (hms * 1e-3), "unit": UNIT, "ms_per_step": hms / K,
+                        "note": "conditions (incl. PointNet++) encoded once per K-step call instead of every step: NOT the reference's per-step work"}
+
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -298,7 +319,7 @@ def run_ours(args):
                        "l2": "per-step working set (GBs of intermediates over 9*B clouds) is far larger than the 126 MB L2; no flush needed",
                        "weights": "seeded well-conditioned random init (lsdm_b200.synthetic)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernel_time_shares": shares,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "hoisted": hoisted_info,
         }
         print(json.dumps(line))
     if world > 1:

@@ -150,7 +150,9 @@ LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32
 
 /* Tuning knobs.  "sa_fused": 0 = set-abstraction blocks as gather + GEMM launches, 1 = fused tensor-core SA kernel with the
  * activations staged in shared memory, 2 = fused with the activations kept in tensor memory (A-from-TMEM MMA), 3 = levels 1-2
- * with the transposed-last-layer variant (in-register max-pool, constant-bank weights), level 3 as in 2. */
+ * with the transposed-last-layer variant (in-register max-pool, constant-bank weights), level 3 as in 2.
+ * "fp_tail": 1 = the last two fp1 layers + conv1/bn1/conv2 head as one fused tensor-core kernel.
+ * "gemm_ws" (process-wide): 1 = persistent warp-specialised tcgen05 GEMM (default), 0 = one-CTA-per-tile tcgen05 GEMM. */
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value);
 
 /* Test hook: one linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) through the fp32 (precision 0) or tcgen05 TF32 / 3xTF32

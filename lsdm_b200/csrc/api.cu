@@ -91,6 +91,8 @@ struct lsdm_handle {
   float *sa_w[4][3], *sa_b[4][3], *sa_wx[4], *sa_wf[4];
   float *fp_w[4][3], *fp_b[4][3], *fp_wa[4], *fp_wb[4];
   float *head_w, *head_b;
+  std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
+  int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
   std::vector<float> host_wx[2], host_wf[2], host_b1[2], host_b2[2];  // host copies for the v2 fused SA kernels (kernel params)
   // schedule
   float* sched = nullptr;  // 5 x T
@@ -418,6 +420,14 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU));
       coarse_feat = outs[l];
     } else {
+      if (h->precision >= 1 && h->fp_tail) {
+        int r = prof_launch(h, st, K_GEMM, [&] {
+          return launch_fp1_tail(w.tP, h->fp_w[l][1], h->fp_w[l][2], h->head_w, h->host_tail.data(), (int64_t)C * N, w.backbone, st);
+        });
+        if (r < 0) return fail(LSDM_EINVAL, "fused fp1 tail unavailable");
+        if (h->profiling) h->gemm_flops += 2.0 * C * N * 3.0 * 128 * 128;
+        continue;
+      }
       GE(gemm(h, st, w.tP, 128, h->fp_w[l][1], 128, w.tA, 128, h->fp_b[l][1], C * N, 128, 128, ACT_RELU));
       GE(gemm(h, st, w.tA, 128, h->fp_w[l][2], 128, w.tP, 128, h->fp_b[l][2], C * N, 128, 128, ACT_RELU));
       GE(gemm(h, st, w.tP, 128, h->head_w, 128, w.tA, 128, h->head_b, C * N, 128, 128, ACT_RELU));
@@ -641,6 +651,12 @@ LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
     CK(cudaMemcpyAsync(h->host_b1[l].data(), h->sa_b[l][0], sizeof(float) * C1, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->host_b2[l].data(), h->sa_b[l][1], sizeof(float) * C2, cudaMemcpyDeviceToHost, st));
   }
+  h->host_tail.resize(771);
+  CK(cudaMemcpyAsync(h->host_tail.data(), h->fp_b[3][1], sizeof(float) * 128, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->host_tail.data() + 128, h->fp_b[3][2], sizeof(float) * 128, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->host_tail.data() + 256, h->head_b, sizeof(float) * 128, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->host_tail.data() + 384, h->W("pcd_backbone.conv2.weight"), sizeof(float) * 384, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->host_tail.data() + 768, h->W("pcd_backbone.conv2.bias"), sizeof(float) * 3, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));  // one-off, load time only
   h->finalized = true;
   return LSDM_OK;
@@ -857,6 +873,14 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
     h->sa_fused = value;
     return LSDM_OK;
   }
+  if (strcmp(name, "fp_tail") == 0 && (value == 0 || value == 1)) {
+    h->fp_tail = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "gemm_ws") == 0 && (value == 0 || value == 1)) {
+    g_gemm_ws = value;  // process-wide
+    return LSDM_OK;
+  }
   return fail(LSDM_EINVAL, std::string("unknown option or bad value: ") + name);
 }
 
@@ -876,7 +900,8 @@ LSDM_API int lsdm_debug_gemm(lsdm_handle* h, const float* A, int64_t lda, const 
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc;
   g.bias = bias; g.bias_mode = bias ? bias_mode : 0;
   g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = act; g.group_max = group_max; g.precision = precision;
-  int r = precision >= 1 ? launch_gemm_tc(g, (cudaStream_t)stream) : launch_gemm_simt(g, (cudaStream_t)stream);
+  int r = precision >= 1 ? (g_gemm_ws ? launch_gemm_ws(g, (cudaStream_t)stream) : launch_gemm_tc(g, (cudaStream_t)stream))
+                         : launch_gemm_simt(g, (cudaStream_t)stream);
   if (r < 0) return fail(LSDM_EINVAL, "gemm shape not supported by the requested implementation");
   h->launches += r;
   CK(cudaPeekAtLastError());

@@ -26,7 +26,9 @@ struct GemmArgs {
 // Launches the GEMM on `stream`; returns the number of kernels launched (1) or a negative value on bad arguments.
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
-int launch_gemm_tc(const GemmArgs& g, cudaStream_t stream);
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t stream);   // one CTA per tile (simple pipeline)
+int launch_gemm_ws(const GemmArgs& g, cudaStream_t stream);   // persistent, warp-specialised (default tensor path)
+extern int g_gemm_ws;                                          // 1: launch_gemm uses the warp-specialised kernel
 bool gemm_tc_eligible(const GemmArgs& g);
 
 }  // namespace lsdm

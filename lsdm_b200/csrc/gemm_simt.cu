@@ -167,8 +167,10 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
 }
 
 // Dispatcher of the generic interface (gemm.cuh).
+int g_gemm_ws = 1;
+
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
-  if (g.precision >= 1 && gemm_tc_eligible(g)) return launch_gemm_tc(g, stream);
+  if (g.precision >= 1 && gemm_tc_eligible(g)) return g_gemm_ws ? launch_gemm_ws(g, stream) : launch_gemm_tc(g, stream);
   return launch_gemm_simt(g, stream);
 }
 

@@ -1,0 +1,263 @@
+// Persistent, warp-specialised tcgen05 implementation of the generic linear-layer GEMM (gemm.cuh):
+//   C[M,N] = act(A[M,K] . W[N,K]^T + bias),  TF32 (operands rounded to nearest) or 3xTF32, fp32 accumulate in TMEM.
+// One CTA per SM loops over 128 x BN output tiles.  Nine warps, three roles:
+//   warps 0-3  producers : ld.global (next k-block prefetched in registers) -> cvt.rna.tf32 [-> hi/lo split] ->
+//                          swizzled st.shared into an NSTAGE ring (K-major SWIZZLE_128B k-blocks) -> mbarrier "full"
+//   warp  8    MMA issuer: one thread; waits "full", issues tcgen05.mma (M=128, N=BN, K=8), tcgen05.commit -> "empty";
+//                          after the last k-block commits the tile's accumulator -> "acc_full"
+//   warps 4-7  epilogue  : tcgen05.ld of the finished accumulator (two TMEM buffers alternate, so the epilogue of tile i
+//                          overlaps the loads + MMAs of tile i+1), bias / activation, then either a shared-memory
+//                          transpose for coalesced 128-bit stores or the 32-row group max (redux.sync) -> "acc_empty"
+#include "gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace lsdm {
+
+namespace {
+
+using namespace tc;
+
+constexpr int WBM = 128, WBK = 32;
+constexpr int W_A_STAGE = WBM * 128;  // bytes of one A k-block
+constexpr int WS_THREADS = 288;
+constexpr int WSTG = 36;              // epilogue transpose row stride (floats)
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int tiles_m, int tiles_n, int total_tiles) {
+  constexpr int NSTAGE = SPLIT ? 2 : 3;
+  constexpr int W_STAGE = BN * 128;
+  constexpr int HALF = W_A_STAGE + W_STAGE;          // [A | W]; SPLIT appends [A_lo | W_lo]
+  constexpr int STAGE = HALF * (SPLIT ? 2 : 1);
+  constexpr uint32_t TCOLS_PER = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr int A_PER = WBM * 8 / 128, W_PER = BN * 8 / 128;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_full[NSTAGE], s_empty[NSTAGE], s_accf[2], s_acce[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[1024];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int nkb = g.K / WBK;
+
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 2 * TCOLS_PER);
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 128);
+      mbar_init(smem_u32(&s_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_accf[i]), 1);
+      mbar_init(smem_u32(&s_acce[i]), 128);
+    }
+    fence_mbar_init();
+  }
+  if (g.bias_mode == 1)
+    for (int i = tid; i < g.N; i += WS_THREADS) s_bias[i] = g.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  auto decode = [&](int t, int& m0, int& n0, int& z) {
+    int per_z = tiles_m * tiles_n;
+    z = t / per_z;
+    int r = t - z * per_z;
+    m0 = (r / tiles_n) * WBM;
+    n0 = (r % tiles_n) * BN;
+  };
+
+  if (warp < 4) {
+    // =============================== producers ===============================
+    float4 ra[A_PER], rw[W_PER];
+    auto fetch = [&](int t, int kb) {
+      int m0, n0, z;
+      decode(t, m0, n0, z);
+      const float* __restrict__ A = g.A + (int64_t)z * g.strideA;
+      const float* __restrict__ W = g.W + (int64_t)z * g.strideW;
+      const int k0 = kb * WBK;
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        int q = tid + i * 128;
+        int r = q >> 3, c = q & 7;
+        int m = m0 + r;
+        m = m < g.M ? m : g.M - 1;
+        ra[i] = *reinterpret_cast<const float4*>(A + (int64_t)m * g.lda + k0 + c * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < W_PER; ++i) {
+        int q = tid + i * 128;
+        int r = q >> 3, c = q & 7;
+        rw[i] = *reinterpret_cast<const float4*>(W + (int64_t)(n0 + r) * g.ldw + k0 + c * 4);
+      }
+    };
+    auto sub4 = [](float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); };
+    int t = blockIdx.x, kb = 0;
+    if (t < total_tiles) fetch(t, 0);
+    uint32_t it = 0;
+    while (t < total_tiles) {
+      const uint32_t s = it % NSTAGE;
+      if (it >= (uint32_t)NSTAGE) mbar_wait(smem_u32(&s_empty[s]), ((it / NSTAGE) & 1u) ^ 1u);
+      const uint32_t sA = base + s * STAGE, sW = sA + W_A_STAGE;
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        int q = tid + i * 128;
+        uint32_t off = sw128_off(q >> 3, q & 7);
+        float4 hi = rna_tf32(ra[i]);
+        st_shared_v4(sA + off, hi);
+        if (SPLIT) st_shared_v4(sA + HALF + off, rna_tf32(sub4(ra[i], hi)));
+      }
+#pragma unroll
+      for (int i = 0; i < W_PER; ++i) {
+        int q = tid + i * 128;
+        uint32_t off = sw128_off(q >> 3, q & 7);
+        float4 hi = rna_tf32(rw[i]);
+        st_shared_v4(sW + off, hi);
+        if (SPLIT) st_shared_v4(sW + HALF + off, rna_tf32(sub4(rw[i], hi)));
+      }
+      // advance and prefetch the next k-block (possibly of the next tile) before publishing this one
+      if (++kb == nkb) {
+        kb = 0;
+        t += gridDim.x;
+      }
+      if (t < total_tiles) fetch(t, kb);
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&s_full[s]));
+      ++it;
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(WBM, BN);
+      uint32_t it = 0, ti = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const uint32_t b = ti & 1u;
+        if (ti >= 2) mbar_wait(smem_u32(&s_acce[b]), ((ti >> 1) - 1u) & 1u);
+        tc_fence_after();
+        const uint32_t d = tmem + b * TCOLS_PER;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % NSTAGE;
+          mbar_wait(smem_u32(&s_full[s]), (it / NSTAGE) & 1u);
+          tc_fence_after();
+          const uint32_t sA = base + s * STAGE, sW = sA + W_A_STAGE;
+          const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sW);
+#pragma unroll
+          for (int kk = 0; kk < WBK / 8; ++kk) {
+            const uint64_t o = (uint64_t)(kk * 2);
+            if (SPLIT) {
+              const uint64_t dal = umma_desc_sw128(sA + HALF), dbl = umma_desc_sw128(sW + HALF);
+              umma_tf32_ss(d, dal + o, db + o, idesc, (kb | kk) != 0 ? 1u : 0u);
+              umma_tf32_ss(d, da + o, dbl + o, idesc, 1u);
+              umma_tf32_ss(d, da + o, db + o, idesc, 1u);
+            } else {
+              umma_tf32_ss(d, da + o, db + o, idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&s_empty[s]));
+        }
+        umma_commit(smem_u32(&s_accf[b]));
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q4 = warp - 4;  // TMEM lane quarter == warp % 4
+    float* stg = reinterpret_cast<float*>(base_ptr + NSTAGE * STAGE) + q4 * 32 * WSTG;
+    uint32_t ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      int m0, n0, z;
+      decode(t, m0, n0, z);
+      float* __restrict__ C = g.C + (int64_t)z * g.strideC;
+      const uint32_t b = ti & 1u;
+      mbar_wait(smem_u32(&s_accf[b]), (ti >> 1) & 1u);
+      tc_fence_after();
+      const int row = m0 + q4 * 32 + lane;
+      const float rbias = (g.bias_mode == 2 && row < g.M) ? g.bias[row] : 0.0f;
+      const uint32_t tl = tmem + b * TCOLS_PER + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tl + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) + rbias;
+          if (g.bias_mode == 1) x += s_bias[n0 + c0 + j];
+          f[j] = apply_act_rt(x, g.act);
+        }
+        if (g.group_max) {
+          uint32_t res = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(f[j]));
+            if (lane == j) res = mx;
+          }
+          const int gm = (m0 >> 5) + q4;
+          if (gm < (g.M >> 5)) C[(int64_t)gm * g.ldc + n0 + c0 + lane] = __uint_as_float(res);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + lane * WSTG + q * 4) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int r = 4 * j + (lane >> 3), q = lane & 7;
+            float4 val = *reinterpret_cast<const float4*>(stg + r * WSTG + q * 4);
+            int m = m0 + q4 * 32 + r;
+            if (m < g.M) *reinterpret_cast<float4*>(C + (int64_t)m * g.ldc + n0 + c0 + q * 4) = val;
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&s_acce[b]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 2 * TCOLS_PER);
+}
+
+template <int BN, bool SPLIT>
+int launch_ws2(const GemmArgs& g, cudaStream_t st) {
+  constexpr int nstage = SPLIT ? 2 : 3;
+  constexpr int smem = nstage * (W_A_STAGE + BN * 128) * (SPLIT ? 2 : 1) + 4 * 32 * WSTG * 4 + 1024;
+  static_assert(smem <= 227 * 1024 - 8 * 1024, "shared memory budget");
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    attr_done = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int batch = g.batch > 0 ? g.batch : 1;
+  const int tiles_m = (g.M + WBM - 1) / WBM, tiles_n = g.N / BN;
+  const int64_t total = (int64_t)tiles_m * tiles_n * batch;
+  if (total > 0x7fffffff) return -1;
+  const int grid = total < sms ? (int)total : sms;
+  gemm_ws_kernel<BN, SPLIT><<<grid, WS_THREADS, smem, st>>>(g, tiles_m, tiles_n, (int)total);
+  return 1;
+}
+template <int BN>
+int launch_ws(const GemmArgs& g, cudaStream_t st) {
+  return g.precision >= 2 ? launch_ws2<BN, true>(g, st) : launch_ws2<BN, false>(g, st);
+}
+
+}  // namespace
+
+int launch_gemm_ws(const GemmArgs& g, cudaStream_t st) {
+  if (!gemm_tc_eligible(g) || g.N > 1024) return -1;
+  switch (g.N) {
+    case 32: return launch_ws<32>(g, st);
+    case 64: return launch_ws<64>(g, st);
+    case 128: return launch_ws<128>(g, st);
+    case 192: return launch_ws<192>(g, st);
+    default: return launch_ws<256>(g, st);
+  }
+}
+
+}  // namespace lsdm

@@ -41,6 +41,11 @@ int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float*
                        const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
                        int n_clouds, int N, int S, float* out, cudaStream_t st);
 
+// fused tail of the backbone: fp1 layers 2-3 + conv1/bn1 head + conv2, TF32 tensor cores; h_consts is a HOST array
+// [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]
+int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const float* Wh, const float* h_consts, int64_t rows,
+                    float* out, cudaStream_t st);
+
 // ---- cond.cu --------------------------------------------------------------------------------
 struct CondWeights {
   const float *et0_w, *et0_b, *et2_w, *et2_b, *et4_w, *et4_b;  // embed_text 512->256->256->128

@@ -49,6 +49,8 @@ class Engine:
         # selects the CUDA-core fp32 build of every dense layer
         self.set_precision(os.environ.get("LSDM_PRECISION", "tf32"))
         self.set_option("sa_fused", int(os.environ.get("LSDM_SA_FUSED", "3")))
+        self.set_option("gemm_ws", int(os.environ.get("LSDM_GEMM_WS", "0")))
+        self.set_option("fp_tail", int(os.environ.get("LSDM_FP_TAIL", "1")))
 
     # ------------------------------------------------------------------ lifecycle
     def _alloc_workspace(self):

@@ -225,3 +225,95 @@ def test_no_cpu_fallback():
     inp = syn.make_inputs(1, 1)
     with pytest.raises(ValueError):
         m(inp["x_T"].clone(), inp["mask"], torch.zeros(1, dtype=torch.long), inp["given_objs"], inp["given_cats"], inp["text_emb"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-size (BASELINE batch sizes) checks through size-independent properties: the oracle is too slow there.
+# ---------------------------------------------------------------------------------------------------------------------
+def _loop_inputs(B, steps, seed=21):
+    inp = _cuda(syn.make_inputs(seed, B))
+    fps, noise = syn.make_step_randoms(seed + 1, B, steps)
+    return inp, fps.cuda(), noise.cuda()
+
+
+def test_full_batch_sharding_and_determinism():
+    """B=64 (BASELINE config 2 batch), 3 strict steps from t=999: (i) two runs are bit-identical, (ii) two shards of 32 with the
+    global mask / offsets reproduce the unsharded rows, (iii) hoisted == strict when every step repeats the same FPS starts."""
+    B, K = 64, 3
+    m, diff = _model("wellcond")
+    inp, fps, noise = _loop_inputs(B, K)
+    eng = diff._engine(m, B, torch.device("cuda", torch.cuda.current_device()))
+
+    def run(engine, lo, hi, fps_all, hoisted=False):
+        x = inp["x_T"][lo:hi].clone()
+        f = fps_all.view(-1, 4, B, 9)[:, :, lo:hi].reshape(fps_all.shape[0], 4, (hi - lo) * 9).contiguous()
+        engine.sample_loop(x, inp["text_emb"][lo:hi], inp["given_objs"][lo:hi].contiguous(), inp["given_cats"][lo:hi].contiguous(),
+                           inp["mask"], f, noise[:, lo:hi].contiguous(), 999, hoisted)
+        torch.cuda.synchronize()
+        return x
+
+    full = run(eng, 0, B, fps)
+    assert torch.equal(full, run(eng, 0, B, fps))                      # (i) deterministic
+    assert torch.isfinite(full).all()
+    m.set_shard(B, 0)
+    e0 = diff._engine(m, 32, torch.device("cuda", torch.cuda.current_device()))
+    lo_half = run(e0, 0, 32, fps)
+    m.set_shard(B, 32)
+    e1 = diff._engine(m, 32, torch.device("cuda", torch.cuda.current_device()))
+    hi_half = run(e1, 32, 64, fps)
+    m.set_shard(None)
+    assert rel_l2(torch.cat([lo_half, hi_half]).cpu(), full.cpu()) < 1e-6  # (ii) sharded == global (same kernels, same rows)
+    eng = diff._engine(m, B, torch.device("cuda", torch.cuda.current_device()))
+    same = fps[:1].repeat(K, 1, 1)
+    strict_same = run(eng, 0, B, same)
+    hoisted = run(eng, 0, B, same, hoisted=True)
+    assert rel_l2(hoisted.cpu(), strict_same.cpu()) < 1e-6            # (iii)
+
+
+def test_config3_ddim100_respaced_vs_oracle():
+    """BASELINE config 3 schedule ('ddim100' respacing, ancestral sampler -- the only respaced sampler alive in the reference),
+    last 3 of the 100 steps, batch 2, against the oracle."""
+    from lsdm_b200.util.model_util import create_gaussian_diffusion, get_default_diffusion
+
+    m, _ = _model("wellcond")
+    diff = create_gaussian_diffusion(get_default_diffusion(), timestep_respacing="ddim100")
+    assert diff.num_timesteps == 100
+    B, K = 2, 3
+    inp = syn.make_inputs(31, B)
+    fps, noise = syn.make_step_randoms(32, B, K)
+    keep = O.space_timesteps(1000, "ddim100")
+    tables = O.diffusion_tables(O.respaced_betas(O.cosine_betas(1000), keep))
+    sd = syn.make_state_dict(0, "wellcond")
+    g = _cuda(inp)
+    with injected_rng(fps_starts=[v for s in fps for v in s], noises=list(noise)):
+        sample = diff.p_sample_loop(m, (B, 1024, 3), g["mask"], g["given_objs"], g["given_cats"], g["text_emb"], noise=g["x_T"].clone(),
+                                    clip_denoised=False, skip_timesteps=100 - K, init_image=None)
+    # skip_timesteps makes the reference q_sample(zeros, t, noise) first: x_start = sqrt(1-abar_t) * noise
+    x = inp["x_T"].clone() * float(tables["sqrt_one_minus_alphas_cumprod"][K - 1])
+    x = x.float()
+    for k in range(K):
+        t = torch.full((B,), K - 1 - k, dtype=torch.long)
+        out = O.p_sample(sd, tables, x, inp["mask"], t, inp["given_objs"], inp["given_cats"], inp["text_emb"], list(fps[k]), noise[k])
+        x = out["sample"]
+    assert rel_l2(sample.cpu(), x) < TOL_E2E
+
+
+def test_training_losses_batch64_properties():
+    """BASELINE config 4 per-GPU batch (64): finite scalars, loss = mse + cat_loss, chamfer(x, x) == 0, and the batch-mean chamfer
+    equals the mean of the two half-batches."""
+    m, diff = _model("wellcond")
+    B = 64
+    inp = _cuda(syn.make_inputs(41, B, training=True))
+    terms = diff.training_losses(m, inp["x_start"].clone(), inp["mask"], inp["t"], inp["given_objs"], inp["given_cats"], inp["target_cat"],
+                                 y=inp["text_emb"])
+    vals = {k: float(v) for k, v in terms.items()}
+    assert all(np.isfinite(v) for v in vals.values())
+    assert abs(vals["loss"] - (vals["mse"] + vals["cat_loss"])) < 1e-5 * abs(vals["loss"])
+    eng = m._engine
+    a, b = inp["x_start"], inp["x_T"]
+    assert float(eng.chamfer(a, a)) == 0.0
+    whole = float(eng.chamfer(a, b))
+    halves = 0.5 * (float(eng.chamfer(a[:32], b[:32])) + float(eng.chamfer(a[32:], b[32:])))
+    assert abs(whole - halves) < 1e-5 * whole
+    ref = O.chamfer_distance(a[:4].cpu(), b[:4].cpu())
+    assert abs(float(eng.chamfer(a[:4], b[:4])) - float(ref)) < 1e-4 * float(ref)
