@@ -85,6 +85,7 @@ struct lsdm_handle {
   std::unordered_map<std::string, int> index;
   float* arena = nullptr;    // raw state-dict tensors
   float* derived = nullptr;  // folded / split tensors
+  int64_t round_delta = 0;   // float offset from a weight in (arena|derived) to its TF32-rounded copy (tensor path)
   int64_t arena_floats = 0, derived_floats = 0;
   bool finalized = false, have_sched = false, have_cond = false;
   // folded weights
@@ -298,8 +299,10 @@ int prof_launch(lsdm_handle* h, cudaStream_t st, int cls, F&& f) {
   return r;
 }
 
+enum GemmFlags { GF_A_ROUNDED = 1, GF_ROUND_OUT = 2 };
+
 int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const float* W, int64_t ldw, float* C,
-         int64_t ldc, const float* bias, int M, int N, int K, int act, int group_max = 0, int prec = -1) {
+         int64_t ldc, const float* bias, int M, int N, int K, int act, int group_max = 0, int prec = -1, int flags = 0) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.strideA = 0;
   g.W = W; g.ldw = ldw; g.strideW = 0;
@@ -307,6 +310,14 @@ int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const flo
   g.bias = bias; g.bias_mode = bias ? 1 : 0;
   g.M = M; g.N = N; g.K = K; g.batch = 1;
   g.act = act; g.group_max = group_max; g.precision = prec >= 0 ? prec : h->precision;
+  if (g.precision == 1) {  // plain TF32: activations are rounded by their producers, weights have a rounded copy
+    g.a_rounded = (flags & GF_A_ROUNDED) ? 1 : 0;
+    g.round_out = (flags & GF_ROUND_OUT) ? 1 : 0;
+    if (g.a_rounded) {
+      g.W = W + h->round_delta;
+      g.w_rounded = 1;
+    }
+  }
   int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
   if (r < 0) return fail(LSDM_EINVAL, "gemm: unsupported shape M=" + std::to_string(M) + " N=" + std::to_string(N) +
                                           " K=" + std::to_string(K));
@@ -379,7 +390,7 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     const int N = s.N, S = s.npoint, C1 = s.mlp[0], C2 = s.mlp[1], C3 = s.mlp[2];
     const float* P = nullptr;
     if (l > 0) {  // first conv, feature half, once per source point
-      GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE));
+      GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE, 0, -1, GF_A_ROUNDED));
       P = w.tP;
     }
     const int fused_max_level = h->sa_fused >= 2 ? 2 : 1;
@@ -387,19 +398,19 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       int r = prof_launch(h, st, K_GEMM, [&] {
         if (h->sa_fused == 3 && l <= 1)
           return launch_sa_fused_v2(l, P, xyz[l], xyz[l + 1], q.grp[l], h->host_wx[l].data(), h->host_wf[l].data(), h->host_b1[l].data(),
-                                    h->host_b2[l].data(), h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], st);
+                                    h->host_b2[l].data(), h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], h->precision == 1, st);
         return launch_sa_fused(l, h->sa_fused >= 2, P, xyz[l], xyz[l + 1], q.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
-                               h->sa_w[l][1], h->sa_b[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], st);
+                               h->sa_w[l][1], h->sa_b[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], h->precision == 1, st);
       });
       if (r < 0) return fail(LSDM_EINVAL, "fused SA kernel unavailable for this level");
       if (h->profiling) h->gemm_flops += 2.0 * C * S * 32 * ((double)C1 * C2 + (double)C2 * C3);
       continue;
     }
     prof_launch(h, st, K_GATHER, [&] { return launch_sa_gather(P, h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0], xyz[l], xyz[l + 1], q.grp[l], C, N, S, C1,
-                                    w.tA, st); });
+                                    w.tA, h->precision == 1, st); });
     const int rows = C * S * 32;
-    GE(gemm(h, st, w.tA, C1, h->sa_w[l][1], C1, w.tB, C2, h->sa_b[l][1], rows, C2, C1, ACT_RELU));
-    GE(gemm(h, st, w.tB, C2, h->sa_w[l][2], C2, w.feat[l + 1], C3, h->sa_b[l][2], rows, C3, C2, ACT_RELU, 1));
+    GE(gemm(h, st, w.tA, C1, h->sa_w[l][1], C1, w.tB, C2, h->sa_b[l][1], rows, C2, C1, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
+    GE(gemm(h, st, w.tB, C2, h->sa_w[l][2], C2, w.feat[l + 1], C3, h->sa_b[l][2], rows, C3, C2, ACT_RELU, 1, -1, GF_A_ROUNDED | GF_ROUND_OUT));
   }
   // feature propagation: fine level <- coarse level
   const int fine[4] = {3, 2, 1, 0}, coarse[4] = {4, 3, 2, 1};
@@ -411,13 +422,13 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     const int N = fineN[l], S = coarseN[l], C1 = s.mlp[0];
     const float* Pa = nullptr;
     if (s.Ca > 0) {
-      GE(gemm(h, st, feat[fine[l]], s.Ca, h->fp_wa[l], s.Ca, w.tA, C1, h->fp_b[l][0], C * N, C1, s.Ca, ACT_NONE));
+      GE(gemm(h, st, feat[fine[l]], s.Ca, h->fp_wa[l], s.Ca, w.tA, C1, h->fp_b[l][0], C * N, C1, s.Ca, ACT_NONE, 0, -1, GF_A_ROUNDED));
       Pa = w.tA;
     }
-    GE(gemm(h, st, coarse_feat, s.Cb, h->fp_wb[l], s.Cb, w.tB, C1, nullptr, C * S, C1, s.Cb, ACT_NONE));
-    prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l], C, N, S, C1, w.tP, st); });
+    GE(gemm(h, st, coarse_feat, s.Cb, h->fp_wb[l], s.Cb, w.tB, C1, nullptr, C * S, C1, s.Cb, ACT_NONE, 0, -1, GF_A_ROUNDED));
+    prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l], C, N, S, C1, w.tP, h->precision == 1, st); });
     if (l < 3) {
-      GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU));
+      GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
       coarse_feat = outs[l];
     } else {
       if (h->precision >= 1 && h->fp_tail) {
@@ -428,9 +439,9 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
         if (h->profiling) h->gemm_flops += 2.0 * C * N * 3.0 * 128 * 128;
         continue;
       }
-      GE(gemm(h, st, w.tP, 128, h->fp_w[l][1], 128, w.tA, 128, h->fp_b[l][1], C * N, 128, 128, ACT_RELU));
-      GE(gemm(h, st, w.tA, 128, h->fp_w[l][2], 128, w.tP, 128, h->fp_b[l][2], C * N, 128, 128, ACT_RELU));
-      GE(gemm(h, st, w.tP, 128, h->head_w, 128, w.tA, 128, h->head_b, C * N, 128, 128, ACT_RELU));
+      GE(gemm(h, st, w.tP, 128, h->fp_w[l][1], 128, w.tA, 128, h->fp_b[l][1], C * N, 128, 128, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
+      GE(gemm(h, st, w.tA, 128, h->fp_w[l][2], 128, w.tP, 128, h->fp_b[l][2], C * N, 128, 128, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
+      GE(gemm(h, st, w.tP, 128, h->head_w, 128, w.tA, 128, h->head_b, C * N, 128, 128, ACT_RELU, 0, -1, GF_A_ROUNDED));
       prof_launch(h, st, K_HEAD, [&] { return launch_head3(w.tA, h->W("pcd_backbone.conv2.weight"), h->W("pcd_backbone.conv2.bias"),
                                   (int64_t)C * N, w.backbone, st); });
     }
@@ -496,6 +507,15 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   return LSDM_OK;
 }
 
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
+    dst[i] = __uint_as_float(r);
+  }
+}
+
 __global__ void fill_t_kernel(int64_t* t, int n, int64_t v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = v;
@@ -520,7 +540,8 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
   build_registry(h);
   // derived (folded) weights: generous upper bound = all backbone conv weights + biases again
   h->derived_floats = 2000000;
-  cudaError_t e = cudaMalloc(&h->arena, sizeof(float) * (h->arena_floats + h->derived_floats));
+  cudaError_t e = cudaMalloc(&h->arena, sizeof(float) * 2 * (h->arena_floats + h->derived_floats));
+  h->round_delta = h->arena_floats + h->derived_floats;
   if (e != cudaSuccess) {
     delete h;
     return fail(LSDM_ENOMEM, std::string("cudaMalloc weights: ") + cudaGetErrorString(e));
@@ -639,6 +660,12 @@ LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
   fold("pcd_backbone.conv1", "pcd_backbone.bn1", 128, 128, &h->head_w, &h->head_b);
   if (off > h->derived_floats) return fail(LSDM_ENOMEM, "derived weight arena too small");
   CK(cudaPeekAtLastError());
+  // TF32-rounded (round-to-nearest) copy of every weight: the cp.async-fed tensor GEMM reads operands without touching them
+  prof_launch(h, st, K_OTHER, [&] {
+    int64_t n = h->round_delta;
+    round_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->arena, h->arena + h->round_delta, n);
+    return 1;
+  });
   // host copies of the small per-channel vectors of sa1 / sa2 (kernel parameters of the v2 fused kernels)
   for (int l = 0; l < 2; ++l) {
     const int C1 = kSA[l].mlp[0], C2 = kSA[l].mlp[1];
@@ -875,6 +902,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   }
   if (strcmp(name, "fp_tail") == 0 && (value == 0 || value == 1)) {
     h->fp_tail = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "gemm_async") == 0 && (value == 0 || value == 1)) {
+    g_gemm_async = value;  // process-wide
     return LSDM_OK;
   }
   if (strcmp(name, "gemm_ws") == 0 && (value == 0 || value == 1)) {

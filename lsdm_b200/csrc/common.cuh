@@ -38,6 +38,39 @@ __device__ __forceinline__ float apply_act_rt(float x, int act) {
   }
 }
 
+// Epilogue transform of one 32-column accumulator chunk: f = [round_tf32](act(v + row_bias + col_bias)).
+// The activation / rounding selectors are resolved ONCE per chunk (switch outside the unrolled element loop).
+template <int ACT, bool ROUND>
+__device__ __forceinline__ void epi_chunk_t(float (&f)[32], const uint32_t (&v)[32], float rbias, const float* cbias) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = __uint_as_float(v[j]) + rbias;
+    if (cbias) x += cbias[j];
+    x = apply_act<ACT>(x);
+    if (ROUND) {
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+      x = __uint_as_float(r);
+    }
+    f[j] = x;
+  }
+}
+__device__ __forceinline__ void epi_chunk(float (&f)[32], const uint32_t (&v)[32], float rbias, const float* cbias, int act,
+                                          int round_out) {
+  switch (act * 2 + (round_out ? 1 : 0)) {
+    case ACT_NONE * 2: epi_chunk_t<ACT_NONE, false>(f, v, rbias, cbias); break;
+    case ACT_NONE * 2 + 1: epi_chunk_t<ACT_NONE, true>(f, v, rbias, cbias); break;
+    case ACT_RELU * 2: epi_chunk_t<ACT_RELU, false>(f, v, rbias, cbias); break;
+    case ACT_RELU * 2 + 1: epi_chunk_t<ACT_RELU, true>(f, v, rbias, cbias); break;
+    case ACT_GELU * 2: epi_chunk_t<ACT_GELU, false>(f, v, rbias, cbias); break;
+    case ACT_GELU * 2 + 1: epi_chunk_t<ACT_GELU, true>(f, v, rbias, cbias); break;
+    case ACT_SIGMOID * 2: epi_chunk_t<ACT_SIGMOID, false>(f, v, rbias, cbias); break;
+    case ACT_SIGMOID * 2 + 1: epi_chunk_t<ACT_SIGMOID, true>(f, v, rbias, cbias); break;
+    case ACT_SILU * 2: epi_chunk_t<ACT_SILU, false>(f, v, rbias, cbias); break;
+    default: epi_chunk_t<ACT_SILU, true>(f, v, rbias, cbias); break;
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

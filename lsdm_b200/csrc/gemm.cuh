@@ -21,6 +21,9 @@ struct GemmArgs {
   int group_max;  // 1: C has M/32 rows, row g = max over rows [32g, 32g+32) of the activated tile
   int precision;  // 0: fp32 CUDA cores (bit-faithful); 1: TF32 tensor cores (tcgen05, operands rounded-to-nearest);
                   // 2: 3xTF32 (hi/lo split of both operands, ~fp32 accuracy on the tensor cores)
+  int a_rounded;  // A already holds TF32-representable values (its producer rounded them)  } both set: operands can be
+  int w_rounded;  // W points at the TF32-rounded weight copy made at finalize                } staged by cp.async, no registers
+  int round_out;  // epilogue rounds C to TF32 (round-to-nearest) because C feeds another tensor-core GEMM
 };
 
 // Launches the GEMM on `stream`; returns the number of kernels launched (1) or a negative value on bad arguments.
@@ -28,6 +31,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t stream);   // one CTA per tile (simple pipeline)
 int launch_gemm_ws(const GemmArgs& g, cudaStream_t stream);   // persistent, warp-specialised (default tensor path)
+extern int g_gemm_async;                                       // 1: pre-rounded operands take the cp.async-fed persistent kernel
 extern int g_gemm_ws;                                          // 1: launch_gemm uses the warp-specialised kernel
 bool gemm_tc_eligible(const GemmArgs& g);
 

@@ -167,10 +167,14 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
 }
 
 // Dispatcher of the generic interface (gemm.cuh).
-int g_gemm_ws = 1;
+int g_gemm_ws = 0;
+int g_gemm_async = 1;
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
-  if (g.precision >= 1 && gemm_tc_eligible(g)) return g_gemm_ws ? launch_gemm_ws(g, stream) : launch_gemm_tc(g, stream);
+  if (g.precision >= 1 && gemm_tc_eligible(g)) {
+    const bool async_ok = g.precision == 1 && g.a_rounded && g.w_rounded && g_gemm_async && g.N <= 1024;
+    return (g_gemm_ws || async_ok) ? launch_gemm_ws(g, stream) : launch_gemm_tc(g, stream);
+  }
   return launch_gemm_simt(g, stream);
 }
 

@@ -142,12 +142,7 @@ __global__ void __launch_bounds__(TNT) gemm_tc_kernel(GemmArgs g) {
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
     tmem_ld_wait();
     float f[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(v[j]) + rbias;
-      if (g.bias_mode == 1) x += s_bias[c0 + j];
-      f[j] = apply_act_rt(x, g.act);
-    }
+    epi_chunk(f, v, rbias, g.bias_mode == 1 ? &s_bias[c0] : nullptr, g.act, g.round_out);
     if (g.group_max) {
       // rows of this warp = one 32-sample group; values are post-ReLU (>= 0), so uint order == float order
       uint32_t res = 0;

@@ -22,9 +22,9 @@ constexpr int W_A_STAGE = WBM * 128;  // bytes of one A k-block
 constexpr int WS_THREADS = 288;
 constexpr int WSTG = 36;              // epilogue transpose row stride (floats)
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool ASYNC>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int tiles_m, int tiles_n, int total_tiles) {
-  constexpr int NSTAGE = SPLIT ? 2 : 3;
+  constexpr int NSTAGE = SPLIT ? 2 : (ASYNC ? 4 : 3);
   constexpr int W_STAGE = BN * 128;
   constexpr int HALF = W_A_STAGE + W_STAGE;          // [A | W]; SPLIT appends [A_lo | W_lo]
   constexpr int STAGE = HALF * (SPLIT ? 2 : 1);
@@ -67,7 +67,42 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
     n0 = (r % tiles_n) * BN;
   };
 
-  if (warp < 4) {
+  if (warp < 4 && ASYNC) {
+    // ============ producers, pre-rounded operands: cp.async straight into the swizzled ring, NSTAGE k-blocks in flight ============
+    int t = blockIdx.x, kb = 0;
+    uint32_t it = 0;
+    while (t < total_tiles) {
+      const uint32_t s = it % NSTAGE;
+      if (it >= (uint32_t)NSTAGE) mbar_wait(smem_u32(&s_empty[s]), ((it / NSTAGE) & 1u) ^ 1u);
+      int m0, n0, z;
+      decode(t, m0, n0, z);
+      const float* __restrict__ A = g.A + (int64_t)z * g.strideA;
+      const float* __restrict__ W = g.W + (int64_t)z * g.strideW;
+      const uint32_t sA = base + s * STAGE, sW = sA + W_A_STAGE;
+      const int k0 = kb * WBK;
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        int q = tid + i * 128;
+        int r = q >> 3, c = q & 7;
+        int m = m0 + r;
+        m = m < g.M ? m : g.M - 1;
+        cp_async16(sA + sw128_off(r, c), A + (int64_t)m * g.lda + k0 + c * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < W_PER; ++i) {
+        int q = tid + i * 128;
+        int r = q >> 3, c = q & 7;
+        cp_async16(sW + sw128_off(r, c), W + (int64_t)(n0 + r) * g.ldw + k0 + c * 4);
+      }
+      cp_async_mbar_arrive(smem_u32(&s_full[s]));
+      if (++kb == nkb) {
+        kb = 0;
+        t += gridDim.x;
+      }
+      ++it;
+    }
+    cp_async_wait<0>();
+  } else if (warp < 4) {
     // =============================== producers ===============================
     float4 ra[A_PER], rw[W_PER];
     auto fetch = [&](int t, int kb) {
@@ -138,6 +173,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const uint32_t s = it % NSTAGE;
           mbar_wait(smem_u32(&s_full[s]), (it / NSTAGE) & 1u);
+          if (ASYNC) fence_proxy_async();  // cp.async (generic proxy) writes -> tensor core (async proxy)
           tc_fence_after();
           const uint32_t sA = base + s * STAGE, sW = sA + W_A_STAGE;
           const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sW);
@@ -179,12 +215,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
         tmem_ld32(tl + (uint32_t)c0, v);
         tmem_ld_wait();
         float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + rbias;
-          if (g.bias_mode == 1) x += s_bias[n0 + c0 + j];
-          f[j] = apply_act_rt(x, g.act);
-        }
+        epi_chunk(f, v, rbias, g.bias_mode == 1 ? &s_bias[n0 + c0] : nullptr, g.act, g.round_out);
         if (g.group_max) {
           uint32_t res = 0;
 #pragma unroll
@@ -218,14 +249,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
   if (warp == 0) tmem_dealloc(tmem, 2 * TCOLS_PER);
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool ASYNC>
 int launch_ws2(const GemmArgs& g, cudaStream_t st) {
-  constexpr int nstage = SPLIT ? 2 : 3;
+  constexpr int nstage = SPLIT ? 2 : (ASYNC ? 4 : 3);
   constexpr int smem = nstage * (W_A_STAGE + BN * 128) * (SPLIT ? 2 : 1) + 4 * 32 * WSTG * 4 + 1024;
   static_assert(smem <= 227 * 1024 - 8 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, SPLIT, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
     attr_done = true;
   }
   static int sms = 0;
@@ -239,12 +270,14 @@ int launch_ws2(const GemmArgs& g, cudaStream_t st) {
   const int64_t total = (int64_t)tiles_m * tiles_n * batch;
   if (total > 0x7fffffff) return -1;
   const int grid = total < sms ? (int)total : sms;
-  gemm_ws_kernel<BN, SPLIT><<<grid, WS_THREADS, smem, st>>>(g, tiles_m, tiles_n, (int)total);
+  gemm_ws_kernel<BN, SPLIT, ASYNC><<<grid, WS_THREADS, smem, st>>>(g, tiles_m, tiles_n, (int)total);
   return 1;
 }
 template <int BN>
 int launch_ws(const GemmArgs& g, cudaStream_t st) {
-  return g.precision >= 2 ? launch_ws2<BN, true>(g, st) : launch_ws2<BN, false>(g, st);
+  if (g.precision >= 2) return launch_ws2<BN, true, false>(g, st);
+  if (g.a_rounded && g.w_rounded && g_gemm_async) return launch_ws2<BN, false, true>(g, st);
+  return launch_ws2<BN, false, false>(g, st);
 }
 
 }  // namespace

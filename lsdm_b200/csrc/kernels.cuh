@@ -19,10 +19,10 @@ int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, i
 // P == nullptr (sa1): P is replaced by bias[ch] + Wf[ch,0:3] . xyz[c,j]   (features are the coordinates)
 int launch_sa_gather(const float* P, const float* Wx, const float* Wf3, const float* bias, const float* xyz,
                      const float* new_xyz, const int* group, int n_clouds, int N, int S, int C1, float* h1,
-                     cudaStream_t st);
+                     int round_out, cudaStream_t st);
 // h[(c,n), ch] = relu(Pa[(c,n), ch] + sum_k w[c,n,k] * Pb[c*S + idx[c,n,k], ch]);  Pa == nullptr -> bias[ch]
 int launch_fp_combine(const float* Pa, const float* bias, const float* Pb, const int* nn_idx, const float* nn_w,
-                      int n_clouds, int N, int S, int C1, float* h, cudaStream_t st);
+                      int n_clouds, int N, int S, int C1, float* h, int round_out, cudaStream_t st);
 // out[row, 0:3] = h[row, 0:128] . W[3,128]^T + b
 int launch_head3(const float* h, const float* W, const float* b, int64_t rows, float* out, cudaStream_t st);
 // eval-mode BatchNorm folded into the preceding 1x1 conv: Wf = W * s, bf = (b - mean) * s + beta, s = gamma / sqrt(var + eps)
@@ -35,11 +35,11 @@ int launch_copy_cols(const float* src, int ld_src, int col0, int ncols, int rows
 // Returns -1 when the (level, variant) combination is not built.
 int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, const float* new_xyz, const int* grp,
                     const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
-                    const float* b3, int n_clouds, int N, int S, float* out, cudaStream_t st);
+                    const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
 
 int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp, const float* h_wx,
                        const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
-                       int n_clouds, int N, int S, float* out, cudaStream_t st);
+                       int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
 
 // fused tail of the backbone: fp1 layers 2-3 + conv1/bn1 head + conv2, TF32 tensor cores; h_consts is a HOST array
 // [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]

@@ -5,6 +5,7 @@
 //   SA (pointnet2_utils.py:120-131,192-195): conv1([xyz_j - c_s || f_j]) = Wx.(xyz_j - c_s) + (Wf.f_j + b)
 //   FP (pointnet2_utils.py:297-311):         conv1([f1_n || sum_k w_k f2_k]) = (Wa.f1_n + b) + sum_k w_k (Wb.f2_k)
 #include "kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace lsdm {
 
@@ -15,7 +16,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
                                                         const float* __restrict__ Wf3, const float* __restrict__ bias,
                                                         const float* __restrict__ xyz, const float* __restrict__ new_xyz,
                                                         const int* __restrict__ group, int64_t rows, int N, int S, int C1,
-                                                        float* __restrict__ h1) {
+                                                        float* __restrict__ h1, int round_out) {
   extern __shared__ float sw[];  // Wx[C1][3] (+ Wf3[C1][3] + bias[C1] when P == nullptr)
   for (int i = threadIdx.x; i < C1 * 3; i += blockDim.x) sw[i] = Wx[i];
   if (P == nullptr) {
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
         v = fmaf(sw[ch * 3 + 0], rx, v);
         v = fmaf(sw[ch * 3 + 1], ry, v);
         v = fmaf(sw[ch * 3 + 2], rz, v);
-        out[ch] = fmaxf(v, 0.0f);
+        v = fmaxf(v, 0.0f);
+        out[ch] = round_out ? tc::rna_tf32(v) : v;
       }
     } else {
       for (int ch = lane; ch < C1; ch += 32) {
@@ -53,7 +55,8 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
         v = fmaf(sw[C1 * 3 + ch * 3 + 0], jx, v);
         v = fmaf(sw[C1 * 3 + ch * 3 + 1], jy, v);
         v = fmaf(sw[C1 * 3 + ch * 3 + 2], jz, v);
-        out[ch] = fmaxf(v, 0.0f);
+        v = fmaxf(v, 0.0f);
+        out[ch] = round_out ? tc::rna_tf32(v) : v;
       }
     }
   }
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) fp_combine_kernel(const float* __restrict__ Pa, const float* __restrict__ bias,
                                                          const float* __restrict__ Pb, const int* __restrict__ nn_idx,
                                                          const float* __restrict__ nn_w, int64_t rows, int N, int S, int C1,
-                                                         float* __restrict__ h) {
+                                                         float* __restrict__ h, int round_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(256) fp_combine_kernel(const float* __restrict
       float it = b0[ch] * w0;
       it = fmaf(b1[ch], w1, it);
       it = fmaf(b2[ch], w2, it);
-      out[ch] = fmaxf(v + it, 0.0f);
+      float r = fmaxf(v + it, 0.0f);
+      out[ch] = round_out ? tc::rna_tf32(r) : r;
     }
   }
 }
@@ -146,17 +150,17 @@ inline int grid_for_warps(int64_t rows, int warps_per_cta) {
 
 int launch_sa_gather(const float* P, const float* Wx, const float* Wf3, const float* bias, const float* xyz,
                      const float* new_xyz, const int* group, int n_clouds, int N, int S, int C1, float* h1,
-                     cudaStream_t st) {
+                     int round_out, cudaStream_t st) {
   int64_t rows = (int64_t)n_clouds * S * 32;
   size_t smem = (size_t)C1 * 7 * sizeof(float);
-  sa_gather_kernel<<<grid_for_warps(rows, 8), 256, smem, st>>>(P, Wx, Wf3, bias, xyz, new_xyz, group, rows, N, S, C1, h1);
+  sa_gather_kernel<<<grid_for_warps(rows, 8), 256, smem, st>>>(P, Wx, Wf3, bias, xyz, new_xyz, group, rows, N, S, C1, h1, round_out);
   return 1;
 }
 
 int launch_fp_combine(const float* Pa, const float* bias, const float* Pb, const int* nn_idx, const float* nn_w,
-                      int n_clouds, int N, int S, int C1, float* h, cudaStream_t st) {
+                      int n_clouds, int N, int S, int C1, float* h, int round_out, cudaStream_t st) {
   int64_t rows = (int64_t)n_clouds * N;
-  fp_combine_kernel<<<grid_for_warps(rows, 8), 256, 0, st>>>(Pa, bias, Pb, nn_idx, nn_w, rows, N, S, C1, h);
+  fp_combine_kernel<<<grid_for_warps(rows, 8), 256, 0, st>>>(Pa, bias, Pb, nn_idx, nn_w, rows, N, S, C1, h, round_out);
   return 1;
 }
 

@@ -33,6 +33,7 @@ struct SaArgs {
   const float* b3;
   float* out;            // [C*S, C3]
   int n_tiles, N, S;
+  int round_out;  // pooled features feed a tensor-core GEMM next: store them rounded to TF32
 };
 
 template <int C1, int C2, int C3, bool FIRST, bool A_TMEM>
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
         uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(x));
         if (lane == e) res = mx;
       }
-      orow[c0 + lane] = __uint_as_float(res);
+      orow[c0 + lane] = a.round_out ? rna_tf32(__uint_as_float(res)) : __uint_as_float(res);
     }
     tc_fence_before();  // the next tile's MMAs overwrite D2/D3 only after every thread's loads above
     cur = nxt;
@@ -449,7 +450,8 @@ __global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(Sa
         float m = __uint_as_float(v[0]);
 #pragma unroll
         for (int e = 1; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
-        a.out[((int64_t)tile * 4 + g) * C3 + tid] = fmaxf(m + bias3, 0.0f);
+        const float r = fmaxf(m + bias3, 0.0f);
+        a.out[((int64_t)tile * 4 + g) * C3 + tid] = a.round_out ? rna_tf32(r) : r;
       }
     }
     tc_fence_before();
@@ -497,8 +499,8 @@ int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float
 // level: 0 (sa1: 6->32->32->64) or 1 (sa2: 67->64->64->128).  a_tmem selects the A-from-TMEM variant.
 int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, const float* new_xyz, const int* grp,
                     const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
-                    const float* b3, int n_clouds, int N, int S, float* out, cudaStream_t st) {
-  SaArgs a{P, xyz, new_xyz, grp, Wx, Wf3, b1, W2, b2, W3, b3, out, n_clouds * S / 4, N, S};
+                    const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st) {
+  SaArgs a{P, xyz, new_xyz, grp, Wx, Wf3, b1, W2, b2, W3, b3, out, n_clouds * S / 4, N, S, round_out};
   if (level == 0) return a_tmem ? launch_t<32, 32, 64, true, true>(a, st) : launch_t<32, 32, 64, true, false>(a, st);
   if (level == 1) return a_tmem ? launch_t<64, 64, 128, false, true>(a, st) : launch_t<64, 64, 128, false, false>(a, st);
   if (level == 2) return a_tmem ? launch_t<128, 128, 256, false, true>(a, st) : -1;
@@ -508,8 +510,8 @@ int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, co
 // v2 (transposed last layer, constant-bank vectors) for levels 0 and 1; h_* are HOST copies of the small per-channel vectors.
 int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp, const float* h_wx,
                        const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
-                       int n_clouds, int N, int S, float* out, cudaStream_t st) {
-  SaArgs a{P, xyz, new_xyz, grp, nullptr, nullptr, nullptr, W2, nullptr, W3, b3, out, n_clouds * S / 4, N, S};
+                       int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st) {
+  SaArgs a{P, xyz, new_xyz, grp, nullptr, nullptr, nullptr, W2, nullptr, W3, b3, out, n_clouds * S / 4, N, S, round_out};
   if (level == 0) return launch_v2<32, 32, 64, true>(a, h_wx, h_wf, h_b1, h_b2, st);
   if (level == 1) return launch_v2<64, 64, 128, false>(a, h_wx, h_wf, h_b1, h_b2, st);
   return -1;
