@@ -172,6 +172,9 @@ LSDM_API int lsdm_profile_begin(lsdm_handle* h);
 LSDM_API int lsdm_profile_end(lsdm_handle* h, double* ms_by_class, int64_t* launches_by_class, int32_t n_class,
                               double* gemm_flops);
 
+/* Per-kernel detail of the last profiled pass for the tensor-core class: lines "tag\tlaunches\tms\tflops\n". */
+LSDM_API const char* lsdm_profile_report(const lsdm_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

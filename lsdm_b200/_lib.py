@@ -57,6 +57,7 @@ PROTOTYPES = {
     "lsdm_debug_gemm": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, _P]),
     "lsdm_profile_begin": (C.c_int, [_P]),
+    "lsdm_profile_report": (C.c_char_p, [_P]),
     "lsdm_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_double)]),
 }
 

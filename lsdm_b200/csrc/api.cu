@@ -71,7 +71,7 @@ struct Workspace {
   } sel[2];
   int cur;  // set used by the last encode (debug taps)
   float* feat[5];
-  float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out;
+  float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out[2];  // pcd_out: one per selection set (the step of k reads it while dense(k+1) writes the other)
   // step
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
   size_t bytes;
@@ -101,15 +101,16 @@ struct lsdm_handle {
   Workspace ws{};
   bool have_ws = false;
   int64_t launches = 0;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_sel[2] = {nullptr, nullptr}, ev_dense[2] = {nullptr, nullptr};
+  cudaStream_t side = nullptr, dense_st = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_sel[2] = {nullptr, nullptr}, ev_dense[2] = {nullptr, nullptr}, ev_step[2] = {nullptr, nullptr};
   // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
   int precision = 0;       // dense layers of the condition encoder (PointNet++): 0 fp32, 1 tf32, 2 3xtf32
   int precision_step = 0;
   int sa_fused = 0;  // 0: gather + GEMMs; 1: fused SA kernel, A operands in smem; 2: fused, A operands in TMEM;
                      // 3: levels 0-1 with the transposed-last-layer kernel (v2), level 2 as in 2  // dense layers of the per-step x0 network + upsampler
   bool profiling = false;
-  struct ProfRec { int cls; cudaEvent_t a, b; };
+  struct ProfRec { int cls; cudaEvent_t a, b; std::string tag; double flops; };
+  std::string prof_report;
   std::vector<ProfRec> prof;
   double gemm_flops = 0.0;
 
@@ -259,7 +260,8 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   w->backbone = a.take<float>(C * NPTS * 3);
   w->pa = a.take<float>(C * TRANS);
   w->pw = a.take<float>(C * NPTS * 3);
-  w->pcd_out = a.take<float>(B * NPTS * 3);
+  w->pcd_out[0] = a.take<float>(B * NPTS * 3);
+  w->pcd_out[1] = a.take<float>(B * NPTS * 3);
   const size_t rows = B * NPTS;
   w->s256 = a.take<float>(B * 256);
   w->H1 = a.take<float>(B * 256 * 128);
@@ -281,7 +283,7 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
 enum KClass { K_GEMM = 0, K_FPS, K_BALL, K_GATHER, K_3NN, K_FPCOMB, K_HEAD, K_COND, K_SCENE, K_DENOISE, K_OTHER, K_NCLASS };
 
 template <typename F>
-int prof_launch(lsdm_handle* h, cudaStream_t st, int cls, F&& f) {
+int prof_launch(lsdm_handle* h, cudaStream_t st, int cls, F&& f, const char* tag = nullptr, double flops = 0.0) {
   if (!h->profiling) {
     int r = f();
     if (r > 0) h->launches += r;
@@ -289,6 +291,8 @@ int prof_launch(lsdm_handle* h, cudaStream_t st, int cls, F&& f) {
   }
   lsdm_handle::ProfRec rec;
   rec.cls = cls;
+  rec.tag = tag ? tag : "";
+  rec.flops = flops;
   cudaEventCreate(&rec.a);
   cudaEventCreate(&rec.b);
   cudaEventRecord(rec.a, st);
@@ -318,7 +322,9 @@ int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const flo
       g.w_rounded = 1;
     }
   }
-  int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
+  char tag[64];
+  snprintf(tag, sizeof(tag), "gemm p%d N%d K%d%s", g.precision, N, K, group_max ? " gmax" : "");
+  int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); }, tag, 2.0 * M * (double)N * K);
   if (r < 0) return fail(LSDM_EINVAL, "gemm: unsupported shape M=" + std::to_string(M) + " N=" + std::to_string(N) +
                                           " K=" + std::to_string(K));
   if (h->profiling) h->gemm_flops += 2.0 * M * (double)N * K;
@@ -401,7 +407,7 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
                                     h->host_b2[l].data(), h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], h->precision == 1, st);
         return launch_sa_fused(l, h->sa_fused >= 2, P, xyz[l], xyz[l + 1], q.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
                                h->sa_w[l][1], h->sa_b[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], h->precision == 1, st);
-      });
+      }, l == 0 ? "sa_fused sa1" : (l == 1 ? "sa_fused sa2" : "sa_fused sa3"), 2.0 * C * S * 32 * ((double)C1 * C2 + (double)C2 * C3));
       if (r < 0) return fail(LSDM_EINVAL, "fused SA kernel unavailable for this level");
       if (h->profiling) h->gemm_flops += 2.0 * C * S * 32 * ((double)C1 * C2 + (double)C2 * C3);
       continue;
@@ -434,7 +440,7 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       if (h->precision >= 1 && h->fp_tail) {
         int r = prof_launch(h, st, K_GEMM, [&] {
           return launch_fp1_tail(w.tP, h->fp_w[l][1], h->fp_w[l][2], h->head_w, h->host_tail.data(), (int64_t)C * N, w.backbone, st);
-        });
+        }, "fp1_tail", 2.0 * C * N * 3.0 * 128 * 128);
         if (r < 0) return fail(LSDM_EINVAL, "fused fp1 tail unavailable");
         if (h->profiling) h->gemm_flops += 2.0 * C * N * 3.0 * 128 * 128;
         continue;
@@ -451,14 +457,15 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
 
 // x/t-dependent part: timestep embedding, upsampler, x += pcd_out, Input/OutputProcess, optional posterior.
 int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,
-              float* guiding_out, bool want_guiding, int clip, cudaStream_t st) {
+              float* guiding_out, bool want_guiding, int clip, cudaStream_t st, int si = -1) {
   Workspace& w = h->ws;
+  if (si < 0) si = w.cur;
   const int B = h->cfg.batch_local;
   const int rows = B * NPTS;
   if (t != w.t_dev) CK(cudaMemcpyAsync(w.t_dev, t, sizeof(int64_t) * B, cudaMemcpyDefault, st));
   prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
                                    h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
-                                   h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.sel[w.cur].enc, h->W("upsampling_layer.0.weight"),
+                                   h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.sel[si].enc, h->W("upsampling_layer.0.weight"),
                                    h->W("upsampling_layer.0.bias"), B, w.s256, w.H1, st); });
   GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), B * 256, 512,
           128, ACT_GELU, 0, h->precision_step));
@@ -470,7 +477,8 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
     g.C = w.embpre; g.ldc = 256; g.strideC = (int64_t)NPTS * 256;
     g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
     g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0; g.precision = h->precision_step;
-    int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); });
+    int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); }, "gemm p2 upsampler N256 K512 batched",
+                        2.0 * g.M * (double)g.N * g.K * g.batch);
     if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
     if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
   }
@@ -480,10 +488,10 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   if (want_guiding)
     CK(cudaMemcpy2DAsync(w.cat + (size_t)rows * 256 + 128, 256 * sizeof(float), w.cat + 128, 256 * sizeof(float),
                          128 * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
-  prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(x, w.pcd_out, h->W("input_process.pose_embedding.0.weight"),
+  prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(x, w.pcd_out[si], h->W("input_process.pose_embedding.0.weight"),
                                     h->W("input_process.pose_embedding.0.bias"), rows, w.h1, st); });
   if (want_guiding)
-    prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(w.pcd_out, nullptr, h->W("input_process.pose_embedding.0.weight"),
+    prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(w.pcd_out[si], nullptr, h->W("input_process.pose_embedding.0.weight"),
                                       h->W("input_process.pose_embedding.0.bias"), rows, w.h1 + (size_t)rows * 64, st); });
   GE(gemm(h, st, w.h1, 64, h->W("input_process.pose_embedding.2.weight"), 64, w.cat, 256,
           h->W("input_process.pose_embedding.2.bias"), M, 128, 64, ACT_SIGMOID, 0, h->precision_step));
@@ -548,10 +556,12 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
   }
   h->derived = h->arena + h->arena_floats;
   cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->dense_st, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&h->ev_sel[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_dense[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
   }
   *out = h;
   return LSDM_OK;
@@ -563,10 +573,12 @@ LSDM_API void lsdm_destroy(lsdm_handle* h) {
   if (h->arena) cudaFree(h->arena);
   if (h->sched) cudaFree(h->sched);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->dense_st) cudaStreamDestroy(h->dense_st);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_sel[i]) cudaEventDestroy(h->ev_sel[i]);
     if (h->ev_dense[i]) cudaEventDestroy(h->ev_dense[i]);
+    if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
   }
   delete h;
 }
@@ -734,7 +746,7 @@ static int encode_dense(lsdm_handle* h, const float* text, const float* objs, co
                   h->W("pcd_attention.out_proj.weight"), h->W("pcd_attention.out_proj.bias"),
                   h->W("point_wise_trans_layer.0.weight"), h->W("point_wise_trans_layer.0.bias")};
   prof_launch(h, st, K_SCENE, [&] { return launch_point_attention(sw, w.backbone, w.sel[si].attn_w, w.sel[si].qq, B, w.pa, w.pw, st); });
-  prof_launch(h, st, K_SCENE, [&] { return launch_scene_mix(w.pw, w.sel[si].hm, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, w.pcd_out, st); });
+  prof_launch(h, st, K_SCENE, [&] { return launch_scene_mix(w.pw, w.sel[si].hm, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, w.pcd_out[si], st); });
   CK(cudaPeekAtLastError());
   w.cur = si;
   h->have_cond = true;
@@ -781,32 +793,43 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
   // device-side timestep vector (the reference builds th.tensor([i]*B) on the host every step, gaussian_diffusion.py:737)
   int64_t* tvec = h->ws.t_dev;
   if (!text || !objs || !cats || !mask_global) return fail(LSDM_EINVAL, "null argument");
-  // STRICT: the selection chain (FPS -> ball queries -> 3-NN) of step k+1 depends only on the clouds and on that step's
-  // FPS start draws, never on x, so it runs on the handle's side stream while the dense layers of step k occupy the
-  // caller's stream (two selection buffer sets; events order producer / consumer / reuse).
+  // STRICT, three-stage software pipeline over steps (nothing in the condition encoder depends on x):
+  //   side stream  : selection chain + condition MLPs + human decoder of step k+1   (FPS -> ball queries -> 3-NN)
+  //   dense stream : PointNet++ dense layers + scene branch of step k               -> pcd_out[k&1]
+  //   caller stream: x0 network + posterior of step k-... (the only part that is serial in x)
+  // Two buffer sets; events order producer -> consumer and consumer -> reuse.
   const bool pipelined = !hoisted && n_steps > 1 && !h->profiling;
   cudaStream_t side = pipelined ? h->side : st;
+  cudaStream_t dst = pipelined ? h->dense_st : st;
   if (pipelined) {
     CK(cudaEventRecord(h->ev_fork, st));
     CK(cudaStreamWaitEvent(side, h->ev_fork, 0));
+    CK(cudaStreamWaitEvent(dst, h->ev_fork, 0));
   }
   GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side));
   if (pipelined) CK(cudaEventRecord(h->ev_sel[0], side));
   for (int k = 0; k < n_steps; ++k) {
     const int si = hoisted ? 0 : (k & 1);
-    if (!hoisted && k + 1 < n_steps) {
+    if (pipelined && k + 1 < n_steps) {
       const int sn = (k + 1) & 1;
-      if (pipelined && k >= 1) CK(cudaStreamWaitEvent(side, h->ev_dense[sn], 0));  // set sn was last read by dense(k-1)
-      if (pipelined) {
-        GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side));
-        CK(cudaEventRecord(h->ev_sel[sn], side));
+      if (k >= 1) {  // set sn was last read by dense(k-1) and step(k-1)
+        CK(cudaStreamWaitEvent(side, h->ev_dense[sn], 0));
+        CK(cudaStreamWaitEvent(side, h->ev_step[sn], 0));
       }
+      GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side));
+      CK(cudaEventRecord(h->ev_sel[sn], side));
     }
-    if (pipelined) CK(cudaStreamWaitEvent(st, h->ev_sel[si], 0));
     if (!pipelined && !hoisted && k >= 1) GE(select_phase(h, h->ws.sel[si], text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, st));
     if (!hoisted || k == 0) {
-      GE(encode_dense(h, text, objs, cats, mask_global, si, st));
-      if (pipelined) CK(cudaEventRecord(h->ev_dense[si], st));
+      if (pipelined) {
+        CK(cudaStreamWaitEvent(dst, h->ev_sel[si], 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(dst, h->ev_step[si], 0));  // pcd_out[si] was last read by step(k-2)
+      }
+      GE(encode_dense(h, text, objs, cats, mask_global, si, dst));
+      if (pipelined) {
+        CK(cudaEventRecord(h->ev_dense[si], dst));
+        CK(cudaStreamWaitEvent(st, h->ev_dense[si], 0));
+      }
     }
     prof_launch(h, st, K_OTHER, [&] {
       fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(tvec, B, (int64_t)(t_first - k));
@@ -816,7 +839,8 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     // STRICT recomputes the guiding points every step like the reference; hoisted only needs them at the end
     const bool want_guiding = !hoisted || last;
     GE(step_core(h, x, tvec, noise_all + (size_t)k * per, x, last ? x0_out : nullptr, last ? guiding_out : nullptr,
-                 want_guiding, clip_denoised, st));
+                 want_guiding, clip_denoised, st, si));
+    if (pipelined) CK(cudaEventRecord(h->ev_step[si], st));
   }
   return LSDM_OK;
 }
@@ -829,7 +853,7 @@ LSDM_API int lsdm_get_out_cat(lsdm_handle* h, float* out_cat, void* stream) {
 }
 LSDM_API int lsdm_get_pcd_out(lsdm_handle* h, float* pcd_out, void* stream) {
   GE(check_ready(h, true));
-  CK(cudaMemcpyAsync(pcd_out, h->ws.pcd_out, sizeof(float) * h->cfg.batch_local * NPTS * 3, cudaMemcpyDeviceToDevice,
+  CK(cudaMemcpyAsync(pcd_out, h->ws.pcd_out[h->ws.cur], sizeof(float) * h->cfg.batch_local * NPTS * 3, cudaMemcpyDeviceToDevice,
                      (cudaStream_t)stream));
   return LSDM_OK;
 }
@@ -869,7 +893,7 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
   const Tap taps[] = {
       {"backbone", w.backbone, C * NPTS * 3, 4}, {"hm", q.hm, B * NPTS * 3, 4}, {"attn_w", q.attn_w, B * NOBJ, 4},
       {"tr", q.tr, C * TRANS, 4}, {"enc", q.enc, B * LAT, 4}, {"pa", w.pa, C * TRANS, 4}, {"pw", w.pw, C * NPTS * 3, 4},
-      {"emb_cat", w.cat, B * NPTS * 256, 4}, {"pcd_out", w.pcd_out, B * NPTS * 3, 4}, {"out_cat", q.out_cat, B * h->cfg.n_cats, 4},
+      {"emb_cat", w.cat, B * NPTS * 256, 4}, {"pcd_out", w.pcd_out[w.cur], B * NPTS * 3, 4}, {"out_cat", q.out_cat, B * h->cfg.n_cats, 4},
       {"fps_idx0", q.idx[0], C * 1024, 4}, {"fps_idx1", q.idx[1], C * 256, 4}, {"fps_idx2", q.idx[2], C * 64, 4},
       {"fps_idx3", q.idx[3], C * 16, 4}, {"ball_idx0", q.grp[0], C * 1024 * 32, 4}, {"ball_idx1", q.grp[1], C * 256 * 32, 4},
       {"ball_idx2", q.grp[2], C * 64 * 32, 4}, {"ball_idx3", q.grp[3], C * 16 * 32, 4}, {"l1_feat", w.feat[1], C * 1024 * 64, 4},
@@ -893,6 +917,8 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
 }
 
 LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h) { return h ? h->launches : 0; }
+
+LSDM_API const char* lsdm_profile_report(const lsdm_handle* h) { return h ? h->prof_report.c_str() : ""; }
 
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   if (!h || !name) return fail(LSDM_EINVAL, "null argument");
@@ -956,16 +982,36 @@ LSDM_API int lsdm_profile_end(lsdm_handle* h, double* ms_by_class, int64_t* laun
   if (!h || !ms_by_class || !launches_by_class || n_class < K_NCLASS) return fail(LSDM_EINVAL, "bad argument");
   h->profiling = false;
   for (int i = 0; i < n_class; ++i) ms_by_class[i] = 0.0, launches_by_class[i] = 0;
+  struct Agg { double ms = 0, flops = 0; int64_t n = 0; };
+  std::vector<std::pair<std::string, Agg>> aggs;
   for (auto& r : h->prof) {
     CK(cudaEventSynchronize(r.b));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, r.a, r.b));
     ms_by_class[r.cls] += ms;
     launches_by_class[r.cls] += 1;
+    if (!r.tag.empty()) {
+      Agg* a = nullptr;
+      for (auto& kv : aggs)
+        if (kv.first == r.tag) a = &kv.second;
+      if (!a) {
+        aggs.emplace_back(r.tag, Agg());
+        a = &aggs.back().second;
+      }
+      a->ms += ms;
+      a->flops += r.flops;
+      a->n += 1;
+    }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
   h->prof.clear();
+  h->prof_report.clear();
+  for (auto& kv : aggs) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%.6e\n", kv.first.c_str(), (long long)kv.second.n, kv.second.ms, kv.second.flops);
+    h->prof_report += line;
+  }
   if (gemm_flops) *gemm_flops = h->gemm_flops;
   return LSDM_OK;
 }

@@ -253,6 +253,14 @@ class Engine:
         _lib.check(self.lib.lsdm_profile_end(self.h, ms, cnt, n, C.byref(fl)))
         return dict(zip(self.KCLASSES, ms)), dict(zip(self.KCLASSES, cnt)), fl.value
 
+    def profile_report(self):
+        """Per-kernel rows of the tensor-core class from the last profiled pass: [{tag, launches, ms, flops}]."""
+        rows = []
+        for line in self.lib.lsdm_profile_report(self.h).decode().splitlines():
+            tag, n, ms, fl = line.split("\t")
+            rows.append({"tag": tag, "launches": int(n), "ms": float(ms), "flops": float(fl)})
+        return rows
+
     PRECISIONS = {"fp32": (0, 0), "tf32": (1, 2), "tf32-all": (1, 1), "3xtf32": (2, 2)}
 
     def set_precision(self, mode):
