@@ -249,8 +249,15 @@ def run_ours(args):
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     # fp32 CUDA-core GEMM today; the tensor roofline it is judged against is TF32 dense = half the measured bf16 rate
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
-    roofline = {"bound": "tensor", "kernel": "gemm (all dense layers)", "achieved": gemm_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": gemm_tflops / tf32_peak, "traffic": None,
+    traffic, traffic_src = None, None
+    try:  # dram bytes per launch of the same kernel class from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_kernel_metrics.json")) as f:
+            tc = json.load(f)["_tensor_class"]
+        traffic, traffic_src = tc["avg_dram_bytes_per_launch"], "profiles/r1_ncu_kernel_metrics.json (" + tc["source"] + ")"
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "tensor-core dense layers (sa_fused*, gemm_ws/gemm_tc, fp1_tail)", "achieved": gemm_tflops,
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": f"{peak_src} bf16_tflops_sustained/2 (TF32 dense runs at half the bf16 rate)",
                 "flops_per_launch_avg": gemm_flops / max(1, cls_n["gemm"]), "launches_per_step": cls_n["gemm"] / prof_steps,
                 "avg_launch_ms": gemm_ms / max(1, cls_n["gemm"]), "share_of_step": gemm_ms / tot_ms if tot_ms else None,
