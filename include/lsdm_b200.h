@@ -95,6 +95,17 @@ LSDM_API int lsdm_set_workspace(lsdm_handle* h, void* workspace, size_t bytes);
 LSDM_API int lsdm_encode_conditions(lsdm_handle* h, const float* text_emb, const float* given_objs, const float* given_cats,
                            const float* mask_global, const int64_t* fps_start, void* stream);
 
+/* model.train() variant of lsdm_encode_conditions (reference run/train_sdm.py:30-107 calls the model in train mode): the 22
+ * BatchNorm layers of the backbone use batch statistics over all 9*Bl clouds and update running_mean / running_var inside the
+ * handle (momentum 0.1, unbiased variance; read them back with lsdm_read_weight), and the backbone head applies
+ * drop_mask[9*Bl,128,1024] (0 or 2: Dropout(0.5), reference model/pcd_backbone/pointnet2.py:76, in the reference's layout). */
+LSDM_API int lsdm_encode_conditions_train(lsdm_handle* h, const float* text_emb, const float* given_objs, const float* given_cats,
+                                          const float* mask_global, const int64_t* fps_start, const float* drop_mask, void* stream);
+
+/* Current value of a state-dict entry held by the handle (e.g. BatchNorm running statistics after a train-mode forward);
+ * dst host or device, numel must match. */
+LSDM_API int lsdm_read_weight(lsdm_handle* h, const char* key, float* dst, int64_t numel, void* stream);
+
 /* Replaces one GaussianDiffusion.p_sample (diffusion/gaussian_diffusion.py:501-561) given encoded conditions:
  * timestep embedding, upsampler, x += pcd_out (IN PLACE, model/sdm.py:204), Input/OutputProcess, posterior
  * mean with the mutated x, ancestral noise.  t[Bl] int64 (host or device) indexes the schedule tables AND the

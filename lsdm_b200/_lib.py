@@ -42,6 +42,8 @@ PROTOTYPES = {
     "lsdm_workspace_bytes": (C.c_size_t, [_P]),
     "lsdm_set_workspace": (C.c_int, [_P, _P, C.c_size_t]),
     "lsdm_encode_conditions": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "lsdm_encode_conditions_train": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "lsdm_read_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, _P]),
     "lsdm_denoise_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "lsdm_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "lsdm_sample_loop": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),

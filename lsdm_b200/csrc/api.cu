@@ -60,6 +60,7 @@ struct Bump {
 struct Workspace {
   // conditions
   float* human_scratch;
+  double* bn_stats;
   int64_t* t_dev;
   // selection results (depend only on the clouds and the FPS start draws); two sets so that lsdm_sample_loop can run the
   // selection chain of step k+1 on a side stream while the dense layers of step k run on the caller's stream
@@ -91,6 +92,8 @@ struct lsdm_handle {
   // folded weights
   float *sa_w[4][3], *sa_b[4][3], *sa_wx[4], *sa_wf[4];
   float *fp_w[4][3], *fp_b[4][3], *fp_wa[4], *fp_wb[4];
+  float *sa_wx_raw[4], *sa_wf_raw[4], *fp_wa_raw[4], *fp_wb_raw[4];  // un-folded first-layer splits (train-mode BatchNorm)
+  bool fold_dirty = false;  // running statistics changed (train-mode forward): re-fold before the next eval-mode encode
   float *head_w, *head_b;
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
@@ -251,7 +254,8 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
       s.nn_w[l] = a.take<float>(C * fn[l] * 3);
     }
   }
-  w->tA = a.take<float>(C * 1048576);
+  w->tA = a.take<float>(C * 2097152);  // 2M floats/cloud: the train-mode path materialises sa1's [32768,64] pre-pool layer
+  w->bn_stats = a.take<double>(2 * 1024);
   w->tB = a.take<float>(C * 1048576);
   w->tP = a.take<float>(C * 262144);
   w->g3 = a.take<float>(C * 64 * 256);
@@ -302,6 +306,8 @@ int prof_launch(lsdm_handle* h, cudaStream_t st, int cls, F&& f, const char* tag
   if (r > 0) h->launches += r;
   return r;
 }
+
+extern "C" LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream);
 
 enum GemmFlags { GF_A_ROUNDED = 1, GF_ROUND_OUT = 2 };
 
@@ -547,7 +553,7 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
   h->cfg = *cfg;
   build_registry(h);
   // derived (folded) weights: generous upper bound = all backbone conv weights + biases again
-  h->derived_floats = 2000000;
+  h->derived_floats = 2700000;
   cudaError_t e = cudaMalloc(&h->arena, sizeof(float) * 2 * (h->arena_floats + h->derived_floats));
   h->round_delta = h->arena_floats + h->derived_floats;
   if (e != cudaSuccess) {
@@ -670,6 +676,23 @@ LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
     prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(h->fp_w[l][0], s.cin, s.Ca, s.Cb, s.mlp[0], h->fp_wb[l], st); });
   }
   fold("pcd_backbone.conv1", "pcd_backbone.bn1", 128, 128, &h->head_w, &h->head_b);
+  for (int l = 0; l < 4; ++l) {  // raw (un-folded) splits of the first SA / FP layers for the train-mode path
+    const SASpec& s = kSA[l];
+    const float* w0 = h->W(std::string("pcd_backbone.") + s.name + ".mlp_convs.0.weight");
+    h->sa_wx_raw[l] = take((int64_t)s.mlp[0] * 3);
+    h->sa_wf_raw[l] = take((int64_t)s.mlp[0] * (s.cin - 3));
+    prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(w0, s.cin, 0, 3, s.mlp[0], h->sa_wx_raw[l], st); });
+    prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(w0, s.cin, 3, s.cin - 3, s.mlp[0], h->sa_wf_raw[l], st); });
+    const FPSpec& f = kFP[l];
+    const float* f0 = h->W(std::string("pcd_backbone.") + f.name + ".mlp_convs.0.weight");
+    h->fp_wa_raw[l] = nullptr;
+    if (f.Ca > 0) {
+      h->fp_wa_raw[l] = take((int64_t)f.mlp[0] * f.Ca);
+      prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(f0, f.cin, 0, f.Ca, f.mlp[0], h->fp_wa_raw[l], st); });
+    }
+    h->fp_wb_raw[l] = take((int64_t)f.mlp[0] * f.Cb);
+    prof_launch(h, st, K_OTHER, [&] { return launch_copy_cols(f0, f.cin, f.Ca, f.Cb, f.mlp[0], h->fp_wb_raw[l], st); });
+  }
   if (off > h->derived_floats) return fail(LSDM_ENOMEM, "derived weight arena too small");
   CK(cudaPeekAtLastError());
   // TF32-rounded (round-to-nearest) copy of every weight: the cp.async-fed tensor GEMM reads operands without touching them
@@ -698,6 +721,7 @@ LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
   CK(cudaMemcpyAsync(h->host_tail.data() + 768, h->W("pcd_backbone.conv2.bias"), sizeof(float) * 3, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));  // one-off, load time only
   h->finalized = true;
+  h->fold_dirty = false;
   return LSDM_OK;
 }
 
@@ -736,12 +760,90 @@ LSDM_API int lsdm_set_workspace(lsdm_handle* h, void* workspace, size_t bytes) {
   return LSDM_OK;
 }
 
+// Train-mode PointNet++ dense layers (model.train(): reference pointnet2_utils.py:192-195,308-311, pointnet2.py:76): every
+// conv is followed by BatchNorm with BATCH statistics over all 9B clouds, running statistics are updated in the handle's
+// weight arena, and the backbone head applies the caller's Dropout(0.5) mask.  Layers run un-fused: conv (GEMM, raw weights)
+// -> column statistics -> normalise + ReLU (+ max-pool).
+int dense_phase_train(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, const float* drop_mask, cudaStream_t st) {
+  Workspace& w = h->ws;
+  const int C = h->cfg.batch_local * NOBJ;
+  const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
+  const float* feat[5] = {clouds, w.feat[1], w.feat[2], w.feat[3], w.feat[4]};
+  auto mut = [&](const std::string& k) { return const_cast<float*>(h->W(k)); };
+  auto bn = [&](const std::string& key, float* y, int64_t M, int N, const float* mask, float* pooled) {
+    prof_launch(h, st, K_OTHER, [&] { return launch_col_stats(y, M, N, w.bn_stats, st); });
+    prof_launch(h, st, K_OTHER, [&] {
+      return launch_bn_apply(y, M, N, w.bn_stats, h->W(key + ".weight"), h->W(key + ".bias"), mut(key + ".running_mean"),
+                             mut(key + ".running_var"), mask, NPTS, pooled, 0, st);
+    });
+  };
+  for (int l = 0; l < 4; ++l) {
+    const SASpec& s = kSA[l];
+    const std::string p = std::string("pcd_backbone.") + s.name;
+    const int N = s.N, S = s.npoint, C1 = s.mlp[0], C2 = s.mlp[1], C3 = s.mlp[2];
+    const float* b0 = h->W(p + ".mlp_convs.0.bias");
+    const float* P = nullptr;
+    if (l > 0) {
+      GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf_raw[l], s.cin - 3, w.tP, C1, b0, C * N, C1, s.cin - 3, ACT_NONE));
+      P = w.tP;
+    }
+    prof_launch(h, st, K_GATHER, [&] {
+      return launch_sa_gather(P, h->sa_wx_raw[l], h->sa_wf_raw[l], b0, xyz[l], xyz[l + 1], q.grp[l], C, N, S, C1, w.tA, 0, st, 0);
+    });
+    const int rows = C * S * 32;
+    bn(p + ".mlp_bns.0", w.tA, rows, C1, nullptr, nullptr);
+    GE(gemm(h, st, w.tA, C1, h->W(p + ".mlp_convs.1.weight"), C1, w.tB, C2, h->W(p + ".mlp_convs.1.bias"), rows, C2, C1, ACT_NONE));
+    bn(p + ".mlp_bns.1", w.tB, rows, C2, nullptr, nullptr);
+    GE(gemm(h, st, w.tB, C2, h->W(p + ".mlp_convs.2.weight"), C2, w.tA, C3, h->W(p + ".mlp_convs.2.bias"), rows, C3, C2, ACT_NONE));
+    bn(p + ".mlp_bns.2", w.tA, rows, C3, nullptr, w.feat[l + 1]);
+  }
+  const int fine[4] = {3, 2, 1, 0};
+  const int fineN[4] = {64, 256, 1024, 1024}, coarseN[4] = {16, 64, 256, 1024};
+  const float* coarse_feat = w.feat[4];
+  float* outs[4] = {w.g3, w.g2, w.g1, w.tA};
+  for (int l = 0; l < 4; ++l) {
+    const FPSpec& s = kFP[l];
+    const std::string p = std::string("pcd_backbone.") + s.name;
+    const int N = fineN[l], S = coarseN[l], C1 = s.mlp[0];
+    const float* b0 = h->W(p + ".mlp_convs.0.bias");
+    const float* Pa = nullptr;
+    if (s.Ca > 0) {
+      GE(gemm(h, st, feat[fine[l]], s.Ca, h->fp_wa_raw[l], s.Ca, w.tA, C1, b0, C * N, C1, s.Ca, ACT_NONE));
+      Pa = w.tA;
+    }
+    GE(gemm(h, st, coarse_feat, s.Cb, h->fp_wb_raw[l], s.Cb, w.tB, C1, nullptr, C * S, C1, s.Cb, ACT_NONE));
+    prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, b0, w.tB, q.nn_idx[l], q.nn_w[l], C, N, S, C1, w.tP, 0, st, 0); });
+    bn(p + ".mlp_bns.0", w.tP, (int64_t)C * N, C1, nullptr, nullptr);
+    GE(gemm(h, st, w.tP, C1, h->W(p + ".mlp_convs.1.weight"), C1, outs[l], s.mlp[1], h->W(p + ".mlp_convs.1.bias"), C * N, s.mlp[1], C1,
+            ACT_NONE));
+    bn(p + ".mlp_bns.1", outs[l], (int64_t)C * N, s.mlp[1], nullptr, nullptr);
+    coarse_feat = outs[l];
+    if (l == 3) {
+      GE(gemm(h, st, w.tA, 128, h->W(p + ".mlp_convs.2.weight"), 128, w.tP, 128, h->W(p + ".mlp_convs.2.bias"), C * N, 128, 128, ACT_NONE));
+      bn(p + ".mlp_bns.2", w.tP, (int64_t)C * N, 128, nullptr, nullptr);
+      GE(gemm(h, st, w.tP, 128, h->W("pcd_backbone.conv1.weight"), 128, w.tA, 128, h->W("pcd_backbone.conv1.bias"), C * N, 128, 128, ACT_NONE));
+      bn("pcd_backbone.bn1", w.tA, (int64_t)C * N, 128, drop_mask, nullptr);
+      prof_launch(h, st, K_HEAD, [&] {
+        return launch_head3(w.tA, h->W("pcd_backbone.conv2.weight"), h->W("pcd_backbone.conv2.bias"), (int64_t)C * N, w.backbone, st);
+      });
+    }
+  }
+  h->fold_dirty = true;
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
 // Everything of the condition encoder except the selection chain (which the caller has already enqueued for set `si`).
 static int encode_dense(lsdm_handle* h, const float* text, const float* objs, const float* cats, const float* mask_global, int si,
-                        cudaStream_t st) {
+                        cudaStream_t st, const float* train_drop_mask = nullptr) {
   Workspace& w = h->ws;
   const int B = h->cfg.batch_local;
-  GE(dense_phase(h, w.sel[si], objs, st));
+  if (train_drop_mask) {
+    GE(dense_phase_train(h, w.sel[si], objs, train_drop_mask, st));
+  } else {
+    if (h->fold_dirty) GE(lsdm_finalize_weights(h, st));  // running statistics moved since the last fold
+    GE(dense_phase(h, w.sel[si], objs, st));
+  }
   SceneWeights sw{h->W("pcd_attention.k_proj_weight"), h->W("pcd_attention.v_proj_weight"), h->W("pcd_attention.in_proj_bias"),
                   h->W("pcd_attention.out_proj.weight"), h->W("pcd_attention.out_proj.bias"),
                   h->W("point_wise_trans_layer.0.weight"), h->W("point_wise_trans_layer.0.bias")};
@@ -760,6 +862,25 @@ LSDM_API int lsdm_encode_conditions(lsdm_handle* h, const float* text, const flo
   cudaStream_t st = (cudaStream_t)stream;
   GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start, st));
   return encode_dense(h, text, objs, cats, mask_global, 0, st);
+}
+
+LSDM_API int lsdm_encode_conditions_train(lsdm_handle* h, const float* text, const float* objs, const float* cats,
+                                          const float* mask_global, const int64_t* fps_start, const float* drop_mask, void* stream) {
+  GE(check_ready(h, false));
+  if (!text || !objs || !cats || !mask_global || !fps_start || !drop_mask) return fail(LSDM_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start, st));
+  return encode_dense(h, text, objs, cats, mask_global, 0, st, drop_mask);
+}
+
+LSDM_API int lsdm_read_weight(lsdm_handle* h, const char* key, float* dst, int64_t numel, void* stream) {
+  if (!h || !key || !dst) return fail(LSDM_EINVAL, "null argument");
+  auto it = h->index.find(key);
+  if (it == h->index.end() || h->entries[it->second].off < 0) return fail(LSDM_EINVAL, std::string("unknown key: ") + key);
+  const WEntry& e = h->entries[it->second];
+  if (numel != e.numel) return fail(LSDM_EINVAL, std::string("size mismatch for ") + key);
+  CK(cudaMemcpyAsync(dst, h->arena + e.off, sizeof(float) * e.numel, cudaMemcpyDefault, (cudaStream_t)stream));
+  return LSDM_OK;
 }
 
 LSDM_API int lsdm_denoise_step(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,

@@ -19,10 +19,10 @@ int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, i
 // P == nullptr (sa1): P is replaced by bias[ch] + Wf[ch,0:3] . xyz[c,j]   (features are the coordinates)
 int launch_sa_gather(const float* P, const float* Wx, const float* Wf3, const float* bias, const float* xyz,
                      const float* new_xyz, const int* group, int n_clouds, int N, int S, int C1, float* h1,
-                     int round_out, cudaStream_t st);
+                     int round_out, cudaStream_t st, int apply_relu = 1);
 // h[(c,n), ch] = relu(Pa[(c,n), ch] + sum_k w[c,n,k] * Pb[c*S + idx[c,n,k], ch]);  Pa == nullptr -> bias[ch]
 int launch_fp_combine(const float* Pa, const float* bias, const float* Pb, const int* nn_idx, const float* nn_w,
-                      int n_clouds, int N, int S, int C1, float* h, int round_out, cudaStream_t st);
+                      int n_clouds, int N, int S, int C1, float* h, int round_out, cudaStream_t st, int apply_relu = 1);
 // out[row, 0:3] = h[row, 0:128] . W[3,128]^T + b
 int launch_head3(const float* h, const float* W, const float* b, int64_t rows, float* out, cudaStream_t st);
 // eval-mode BatchNorm folded into the preceding 1x1 conv: Wf = W * s, bf = (b - mean) * s + beta, s = gamma / sqrt(var + eps)
@@ -45,6 +45,13 @@ int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float*
 // [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]
 int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const float* Wh, const float* h_consts, int64_t rows,
                     float* out, cudaStream_t st);
+
+// ---- bn_train.cu ------------------------------------------------------------------------------
+// train-mode BatchNorm: column statistics (double), then normalise + ReLU [+ dropout mask] [+ 32-row max-pool] and the
+// running-statistics update (momentum 0.1, unbiased variance)
+int launch_col_stats(const float* y, int64_t M, int N, double* sums, cudaStream_t st);
+int launch_bn_apply(float* y, int64_t M, int N, const double* sums, const float* gamma, const float* beta, float* run_mean,
+                    float* run_var, const float* drop_mask, int mask_points, float* pooled, int round_out, cudaStream_t st);
 
 // ---- cond.cu --------------------------------------------------------------------------------
 struct CondWeights {

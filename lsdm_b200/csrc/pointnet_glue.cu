@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
                                                         const float* __restrict__ Wf3, const float* __restrict__ bias,
                                                         const float* __restrict__ xyz, const float* __restrict__ new_xyz,
                                                         const int* __restrict__ group, int64_t rows, int N, int S, int C1,
-                                                        float* __restrict__ h1, int round_out) {
+                                                        float* __restrict__ h1, int round_out, int apply_relu) {
   extern __shared__ float sw[];  // Wx[C1][3] (+ Wf3[C1][3] + bias[C1] when P == nullptr)
   for (int i = threadIdx.x; i < C1 * 3; i += blockDim.x) sw[i] = Wx[i];
   if (P == nullptr) {
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
         v = fmaf(sw[ch * 3 + 0], rx, v);
         v = fmaf(sw[ch * 3 + 1], ry, v);
         v = fmaf(sw[ch * 3 + 2], rz, v);
-        v = fmaxf(v, 0.0f);
+        if (apply_relu) v = fmaxf(v, 0.0f);
         out[ch] = round_out ? tc::rna_tf32(v) : v;
       }
     } else {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
         v = fmaf(sw[C1 * 3 + ch * 3 + 0], jx, v);
         v = fmaf(sw[C1 * 3 + ch * 3 + 1], jy, v);
         v = fmaf(sw[C1 * 3 + ch * 3 + 2], jz, v);
-        v = fmaxf(v, 0.0f);
+        if (apply_relu) v = fmaxf(v, 0.0f);
         out[ch] = round_out ? tc::rna_tf32(v) : v;
       }
     }
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) fp_combine_kernel(const float* __restrict__ Pa, const float* __restrict__ bias,
                                                          const float* __restrict__ Pb, const int* __restrict__ nn_idx,
                                                          const float* __restrict__ nn_w, int64_t rows, int N, int S, int C1,
-                                                         float* __restrict__ h, int round_out) {
+                                                         float* __restrict__ h, int round_out, int apply_relu) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) fp_combine_kernel(const float* __restrict
       float it = b0[ch] * w0;
       it = fmaf(b1[ch], w1, it);
       it = fmaf(b2[ch], w2, it);
-      float r = fmaxf(v + it, 0.0f);
+      float r = apply_relu ? fmaxf(v + it, 0.0f) : v + it;
       out[ch] = round_out ? tc::rna_tf32(r) : r;
     }
   }
@@ -150,17 +150,17 @@ inline int grid_for_warps(int64_t rows, int warps_per_cta) {
 
 int launch_sa_gather(const float* P, const float* Wx, const float* Wf3, const float* bias, const float* xyz,
                      const float* new_xyz, const int* group, int n_clouds, int N, int S, int C1, float* h1,
-                     int round_out, cudaStream_t st) {
+                     int round_out, cudaStream_t st, int apply_relu) {
   int64_t rows = (int64_t)n_clouds * S * 32;
   size_t smem = (size_t)C1 * 7 * sizeof(float);
-  sa_gather_kernel<<<grid_for_warps(rows, 8), 256, smem, st>>>(P, Wx, Wf3, bias, xyz, new_xyz, group, rows, N, S, C1, h1, round_out);
+  sa_gather_kernel<<<grid_for_warps(rows, 8), 256, smem, st>>>(P, Wx, Wf3, bias, xyz, new_xyz, group, rows, N, S, C1, h1, round_out, apply_relu);
   return 1;
 }
 
 int launch_fp_combine(const float* Pa, const float* bias, const float* Pb, const int* nn_idx, const float* nn_w,
-                      int n_clouds, int N, int S, int C1, float* h, int round_out, cudaStream_t st) {
+                      int n_clouds, int N, int S, int C1, float* h, int round_out, cudaStream_t st, int apply_relu) {
   int64_t rows = (int64_t)n_clouds * N;
-  fp_combine_kernel<<<grid_for_warps(rows, 8), 256, 0, st>>>(Pa, bias, Pb, nn_idx, nn_w, rows, N, S, C1, h, round_out);
+  fp_combine_kernel<<<grid_for_warps(rows, 8), 256, 0, st>>>(Pa, bias, Pb, nn_idx, nn_w, rows, N, S, C1, h, round_out, apply_relu);
   return 1;
 }
 

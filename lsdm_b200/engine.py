@@ -144,6 +144,26 @@ class Engine:
         if not fps_start.is_cuda:
             torch.cuda.current_stream(self.device).synchronize()  # pageable host source must outlive the copy
 
+    def encode_conditions_train(self, text_emb, given_objs, given_cats, mask_global, fps_start, drop_mask):
+        """model.train() condition encoder: BatchNorm batch statistics (+ running-stat update inside the handle) and the Dropout mask
+        ``drop_mask[9B,128,1024]`` (0 or 2) of the backbone head."""
+        B = self.batch_local
+        text_emb, given_objs, given_cats, mask_global, drop_mask = map(self._f32, (text_emb, given_objs, given_cats, mask_global, drop_mask))
+        assert drop_mask.shape == (B * N_OBJ, 128, N_POINTS), drop_mask.shape
+        fps_start = self._i64(fps_start)
+        assert fps_start.shape == (4, B * N_OBJ), fps_start.shape
+        self._cond_keep = (text_emb, given_objs, given_cats, mask_global, fps_start, drop_mask)
+        _lib.check(self.lib.lsdm_encode_conditions_train(self.h, _ptr(text_emb), _ptr(given_objs), _ptr(given_cats), _ptr(mask_global),
+                                                         _ptr(fps_start), _ptr(drop_mask), _stream(self.device)))
+        if not fps_start.is_cuda:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def read_weight(self, key, like):
+        """Current value of a state-dict entry inside the handle (BatchNorm running statistics after a train-mode forward)."""
+        out = torch.empty(like.shape, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.lsdm_read_weight(self.h, key.encode(), _ptr(out), out.numel(), _stream(self.device)))
+        return out
+
     def denoise_step(self, x, t, noise, sample_out=None, want_x0=True, want_guiding=True, clip_denoised=False):
         """x is mutated in place (x += pcd_out).  Returns (sample, x0, guiding)."""
         B = self.batch_local

@@ -237,18 +237,37 @@ class SceneDiffusionModel(nn.Module):
         draws = [torch.randint(0, n, (bg * N_OBJ,), dtype=torch.long) for n in FPS_LEVEL_N]
         return torch.stack([d.view(bg, N_OBJ)[off:off + batch_local].reshape(-1) for d in draws])
 
-    def encode(self, mask, given_objs, given_cats, y, fps_start=None, device=None):
+    def encode(self, mask, given_objs, given_cats, y, fps_start=None, device=None, drop_mask=None):
         """Step-invariant part of forward (reference sdm.py:147-203).  Returns the engine."""
-        if self.training:
-            raise NotImplementedError("train-mode BatchNorm statistics / dropout are not on the accelerated path yet; call .eval()")
         B = given_objs.shape[0]
         if device is None:
             device = given_objs.device if given_objs.is_cuda else next(self.parameters()).device
         eng = self.engine(B, device)
         if fps_start is None:
             fps_start = self.draw_fps_starts(B)
-        eng.encode_conditions(self._encode_text(y), given_objs, given_cats, mask, fps_start)
+        if self.training:
+            # model.train(): BatchNorm batch statistics over all 9B clouds + Dropout(0.5) in the backbone head.  The mask is what
+            # F.dropout would draw for the reference's [9B,128,1024] activation (same generator, same shape).
+            if self._shard is not None:
+                raise NotImplementedError("train-mode BatchNorm couples all clouds of the batch; sharded statistics (SyncBN) are not built")
+            if drop_mask is None:
+                drop_mask = torch.nn.functional.dropout(torch.ones(B * N_OBJ, 128, N_POINTS, device=eng.device), 0.5, True)
+            eng.encode_conditions_train(self._encode_text(y), given_objs, given_cats, mask, fps_start, drop_mask)
+            self._pull_bn_stats(eng)
+        else:
+            eng.encode_conditions(self._encode_text(y), given_objs, given_cats, mask, fps_start)
         return eng
+
+    def _pull_bn_stats(self, eng):
+        """Mirror the running statistics the library just updated into this module's BatchNorm buffers (nn.BatchNorm semantics)."""
+        with torch.no_grad():
+            for name, mod in self.pcd_backbone.named_modules():
+                if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                    key = "pcd_backbone." + name
+                    mod.running_mean.copy_(eng.read_weight(key + ".running_mean", mod.running_mean))
+                    mod.running_var.copy_(eng.read_weight(key + ".running_var", mod.running_var))
+                    mod.num_batches_tracked += 1
+        self._weights_sig = self._sig()  # the handle already holds these values
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, mask, timesteps, given_objs, given_cats, y=None, force_mask=False):

@@ -239,3 +239,11 @@ def make_step_randoms(seed: int, batch: int, steps: int = 1):
     ).astype(np.int64)
     noise = rs.standard_normal((steps, batch, N_POINTS, 3)).astype(np.float32)
     return torch.from_numpy(fps), torch.from_numpy(noise)
+
+
+def make_dropout_mask(seed: int, batch: int):
+    """Dropout(0.5) mask of the backbone head (reference pointnet2.py:76) in the reference's layout ``[9B,128,1024]``:
+    0 where dropped, 2 (= 1/(1-p)) where kept."""
+    rs = np.random.RandomState(seed)
+    keep = rs.rand(batch * N_OBJ, 128, N_POINTS) < 0.5
+    return torch.from_numpy(keep.astype(np.float32) * 2.0)

@@ -267,17 +267,33 @@ def _gather(points, idx):
     return points[ar, idx]
 
 
-def _conv_bn_relu(sd, prefix, i, x):
-    """1x1 conv + eval-mode BatchNorm + ReLU on channel-last rows (pointnet2_utils.py:192-195,308-311)."""
+def _batch_norm(sd, bn, y, train):
+    """nn.BatchNorm{1,2}d on channel-last rows.  eval: running statistics.  train (a dict): batch statistics over every
+    row (biased variance), and the running-stat update torch applies (momentum 0.1, unbiased variance,
+    num_batches_tracked + 1) is recorded in train['updates']."""
+    if train is None:
+        mean, var = sd[bn + ".running_mean"], sd[bn + ".running_var"]
+    else:
+        flat = y.reshape(-1, y.shape[-1])
+        n = flat.shape[0]
+        mean = flat.mean(0)
+        var = flat.var(0, unbiased=False)
+        upd = train.setdefault("updates", {})
+        upd[bn + ".running_mean"] = 0.9 * sd[bn + ".running_mean"] + 0.1 * mean
+        upd[bn + ".running_var"] = 0.9 * sd[bn + ".running_var"] + 0.1 * var * (n / (n - 1))
+        upd[bn + ".num_batches_tracked"] = sd[bn + ".num_batches_tracked"] + 1
+    return (y - mean) / torch.sqrt(var + BN_EPS) * sd[bn + ".weight"] + sd[bn + ".bias"]
+
+
+def _conv_bn_relu(sd, prefix, i, x, train=None):
+    """1x1 conv + BatchNorm + ReLU on channel-last rows (pointnet2_utils.py:192-195,308-311)."""
     w = sd[f"{prefix}.mlp_convs.{i}.weight"]
     w = w.reshape(w.shape[0], w.shape[1])
     y = x @ w.T + sd[f"{prefix}.mlp_convs.{i}.bias"]
-    bn = f"{prefix}.mlp_bns.{i}"
-    y = (y - sd[bn + ".running_mean"]) / torch.sqrt(sd[bn + ".running_var"] + BN_EPS) * sd[bn + ".weight"] + sd[bn + ".bias"]
-    return torch.relu(y)
+    return torch.relu(_batch_norm(sd, f"{prefix}.mlp_bns.{i}", y, train))
 
 
-def set_abstraction(sd, name, npoint, radius, nsample, xyz, feats, start, trace=None):
+def set_abstraction(sd, name, npoint, radius, nsample, xyz, feats, start, trace=None, train=None):
     """pointnet2_utils.py:107-135,174-199: FPS -> ball query -> [rel-xyz || feat] -> 3x(conv+BN+ReLU) -> max."""
     fps_idx = farthest_point_sample(xyz, npoint, start)
     new_xyz = _gather(xyz, fps_idx)
@@ -285,7 +301,7 @@ def set_abstraction(sd, name, npoint, radius, nsample, xyz, feats, start, trace=
     g_xyz = _gather(xyz, grp) - new_xyz[:, :, None, :]
     h = torch.cat([g_xyz, _gather(feats, grp)], dim=-1)
     for i in range(3):
-        h = _conv_bn_relu(sd, f"pcd_backbone.{name}", i, h)
+        h = _conv_bn_relu(sd, f"pcd_backbone.{name}", i, h, train)
     out = h.max(dim=2)[0]
     if trace is not None:
         trace[name + ".fps_idx"] = fps_idx
@@ -295,7 +311,7 @@ def set_abstraction(sd, name, npoint, radius, nsample, xyz, feats, start, trace=
     return new_xyz, out
 
 
-def feature_propagation(sd, name, nlayer, xyz1, xyz2, feats1, feats2, trace=None):
+def feature_propagation(sd, name, nlayer, xyz1, xyz2, feats1, feats2, trace=None, train=None):
     """pointnet2_utils.py:273-312: 3-NN inverse-distance interpolation (w = 1/(d+1e-8), normalised),
     concat skip features, conv+BN+ReLU chain."""
     d = square_distance(xyz1, xyz2)
@@ -305,7 +321,7 @@ def feature_propagation(sd, name, nlayer, xyz1, xyz2, feats1, feats2, trace=None
     interp = (_gather(feats2, ik) * w[..., None]).sum(dim=2)
     h = interp if feats1 is None else torch.cat([feats1, interp], dim=-1)
     for i in range(nlayer):
-        h = _conv_bn_relu(sd, f"pcd_backbone.{name}", i, h)
+        h = _conv_bn_relu(sd, f"pcd_backbone.{name}", i, h, train)
     if trace is not None:
         trace[name + ".nn_idx"] = ik
         trace[name + ".nn_w"] = w
@@ -313,23 +329,24 @@ def feature_propagation(sd, name, nlayer, xyz1, xyz2, feats1, feats2, trace=None
     return h
 
 
-def pointnet2_backbone(sd, clouds, fps_starts, trace=None):
-    """model/pcd_backbone/pointnet2.py:61-80 in eval mode: clouds[C,1024,3] -> [C,1024,3]."""
+def pointnet2_backbone(sd, clouds, fps_starts, trace=None, train=None, drop_mask=None):
+    """model/pcd_backbone/pointnet2.py:61-80: clouds[C,1024,3] -> [C,1024,3].  ``train`` (dict) switches the 22 BatchNorm layers to
+    batch statistics; ``drop_mask[C,128,1024]`` (values 0 or 2) is the Dropout(0.5) mask of drop1 (:76) in train mode."""
     l0_xyz, l0_f = clouds, clouds
     xyzs, feats = [l0_xyz], [l0_f]
     for (name, npoint, r, ns), start in zip(SA_SPECS, fps_starts):
-        nx, nf = set_abstraction(sd, name, npoint, r, ns, xyzs[-1], feats[-1], start, trace)
+        nx, nf = set_abstraction(sd, name, npoint, r, ns, xyzs[-1], feats[-1], start, trace, train)
         xyzs.append(nx)
         feats.append(nf)
-    f3 = feature_propagation(sd, "fp4", 2, xyzs[3], xyzs[4], feats[3], feats[4], trace)
-    f2 = feature_propagation(sd, "fp3", 2, xyzs[2], xyzs[3], feats[2], f3, trace)
-    f1 = feature_propagation(sd, "fp2", 2, xyzs[1], xyzs[2], feats[1], f2, trace)
-    f0 = feature_propagation(sd, "fp1", 3, xyzs[0], xyzs[1], None, f1, trace)
+    f3 = feature_propagation(sd, "fp4", 2, xyzs[3], xyzs[4], feats[3], feats[4], trace, train)
+    f2 = feature_propagation(sd, "fp3", 2, xyzs[2], xyzs[3], feats[2], f3, trace, train)
+    f1 = feature_propagation(sd, "fp2", 2, xyzs[1], xyzs[2], feats[1], f2, trace, train)
+    f0 = feature_propagation(sd, "fp1", 3, xyzs[0], xyzs[1], None, f1, trace, train)
     w1 = sd["pcd_backbone.conv1.weight"][:, :, 0]
     h = f0 @ w1.T + sd["pcd_backbone.conv1.bias"]
-    bn = "pcd_backbone.bn1"
-    h = (h - sd[bn + ".running_mean"]) / torch.sqrt(sd[bn + ".running_var"] + BN_EPS) * sd[bn + ".weight"] + sd[bn + ".bias"]
-    h = torch.relu(h)
+    h = torch.relu(_batch_norm(sd, "pcd_backbone.bn1", h, train))
+    if drop_mask is not None:
+        h = h * drop_mask.permute(0, 2, 1).to(h.dtype)
     return h @ sd["pcd_backbone.conv2.weight"][:, :, 0].T + sd["pcd_backbone.conv2.bias"]
 
 
@@ -396,7 +413,7 @@ def point_net(sd, z, emb):
 # forward / sampling / training
 # --------------------------------------------------------------------------------------
 def encode_conditions(sd, mask_global, given_objs, given_cats, text, fps_starts, b_offset=0,
-                      as_written=False, trace=None):
+                      as_written=False, trace=None, train=None, drop_mask=None):
     """Everything in model/sdm.py:147-203 that does not depend on x or t.
     Returns dict(enc, out_cat, w, pcd_out) where pcd_out is the quantity added to x in place."""
     B = given_objs.shape[0]
@@ -404,7 +421,7 @@ def encode_conditions(sd, mask_global, given_objs, given_cats, text, fps_starts,
     out_cat = predict_category(sd, enc)
     emb_cat = _gelu(_lin(sd, "embed_cat.0", given_cats))
     hm = human_decoder(sd, given_objs[:, 0])
-    Fb = pointnet2_backbone(sd, given_objs.reshape(B * N_OBJ, N_PTS, 3), fps_starts, trace).reshape(B, N_OBJ, N_PTS * 3)
+    Fb = pointnet2_backbone(sd, given_objs.reshape(B * N_OBJ, N_PTS, 3), fps_starts, trace, train, drop_mask).reshape(B, N_OBJ, N_PTS * 3)
     w = object_attention_weights(sd, enc, emb_cat, mask_global, b_offset)
     tr = translation_params(sd, enc, emb_cat)
     p1 = scramble1(Fb, w)
@@ -418,7 +435,7 @@ def encode_conditions(sd, mask_global, given_objs, given_cats, text, fps_starts,
 
 
 def forward(sd, x, mask, t, given_objs, given_cats, text, fps_starts, mask_global=None, b_offset=0,
-            as_written=False, trace=None, cond=None):
+            as_written=False, trace=None, cond=None, train=None, drop_mask=None):
     """model/sdm.py:131-218.  MUTATES ``x`` in place (x += pcd_out, :204) like the reference.
     Returns (out_cat[B,1,C], x0[B,1024,3], guiding[B,1024,3])."""
     dtype = x.dtype
@@ -426,7 +443,7 @@ def forward(sd, x, mask, t, given_objs, given_cats, text, fps_starts, mask_globa
         mask_global = mask
     if cond is None:
         cond = encode_conditions(sd, mask_global.to(dtype), given_objs.to(dtype), given_cats.to(dtype), text.to(dtype),
-                                 fps_starts, b_offset, as_written, trace)
+                                 fps_starts, b_offset, as_written, trace, train, drop_mask)
     ts = timestep_embedding(sd, t)
     emb = upsample_embedding(sd, ts, cond["enc"])
     x += cond["pcd_out"]

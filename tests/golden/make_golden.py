@@ -152,6 +152,32 @@ def case_train(kind, B=4, seed_in=7, seed_rng=8):
     return {k: np.float64(float(terms[k])) for k in ("cat_loss", "mse", "loss")}
 
 
+def case_train_forward(kind="wellcond", B=3, seed_in=13, seed_rng=14, seed_drop=15):
+    """model.train() forward: BatchNorm batch statistics + running-stat updates, Dropout(0.5) in the backbone head with an injected
+    mask (model/pcd_backbone/pointnet2.py:76), and training_losses on top (gaussian_diffusion.py:1256-1342)."""
+    ns = rh.load_reference()
+    sd = syn.make_state_dict(SEED_W, kind)
+    m = rh.build_reference_model(sd)
+    m.train()
+    diff = ns.model_util.create_gaussian_diffusion(ns.model_util.get_default_diffusion())
+    inp = syn.make_inputs(seed_in, B, training=True)
+    fps, noise = syn.make_step_randoms(seed_rng, B, 1)
+    mask = syn.make_dropout_mask(seed_drop, B)
+    with torch.no_grad(), rh.injected_rng(fps_starts=list(fps[0]), dropout_masks=[mask]):
+        terms = diff.training_losses(m, inp["x_start"].clone(), inp["mask"], inp["t"], inp["given_objs"], inp["given_cats"],
+                                     inp["target_cat"], y=inp["text_emb"], noise=noise[0])
+    new = m.state_dict()
+    out = {k: np.float64(float(terms[k])) for k in ("cat_loss", "mse", "loss")}
+    for key in ("pcd_backbone.sa1.mlp_bns.0", "pcd_backbone.sa2.mlp_bns.2", "pcd_backbone.sa4.mlp_bns.1", "pcd_backbone.fp4.mlp_bns.0",
+                "pcd_backbone.fp2.mlp_bns.1", "pcd_backbone.fp1.mlp_bns.2", "pcd_backbone.bn1"):
+        out[key + ".running_mean"] = npf(new[key + ".running_mean"])
+        out[key + ".running_var"] = npf(new[key + ".running_var"])
+        out[key + ".num_batches_tracked"] = npf(new[key + ".num_batches_tracked"])
+    out["saved_cat"] = npf(m.saved_cat)
+    out["guiding"] = npf(m.saved_guiding_points)
+    return out
+
+
 def case_tables():
     """Schedule tables (gaussian_diffusion.py:166-202) for T=1000 and two respacings (respace.py:8-87)."""
     ns = rh.load_reference()
@@ -194,6 +220,7 @@ def main():
         "loop8_wellcond": lambda: case_loop("wellcond"),
         "train_wellcond": lambda: case_train("wellcond"),
         "shard_wellcond": case_shard,
+        "trainmode_wellcond": case_train_forward,
     }
     only = sys.argv[1:]
     for name, fn in jobs.items():

@@ -134,12 +134,24 @@ def build_reference_model(state_dict, max_cats: int = 13):
 
 
 @contextlib.contextmanager
-def injected_rng(fps_starts=None, noises=None):
+def injected_rng(fps_starts=None, noises=None, dropout_masks=None):
     """Feed ``torch.randint`` (FPS starts) and ``torch.randn_like`` (sampling noise)
     from queues, in the order the reference draws them."""
     fq = list(fps_starts) if fps_starts is not None else None
     nq = list(noises) if noises is not None else None
     o_randint, o_randn_like = torch.randint, torch.randn_like
+    dq = list(dropout_masks) if dropout_masks is not None else None
+    o_dropout = torch.nn.functional.dropout
+
+    def dropout(x, p=0.5, training=True, inplace=False):
+        if dq is not None and training:
+            assert dq, "dropout mask queue exhausted"
+            m = dq.pop(0)
+            assert m.shape == x.shape, (m.shape, x.shape)
+            return x * m.to(x.dtype)
+        return o_dropout(x, p, training, inplace)
+
+    torch.nn.functional.dropout = dropout
 
     def randint(*a, **k):
         if fq is not None:
@@ -163,3 +175,4 @@ def injected_rng(fps_starts=None, noises=None):
         yield
     finally:
         torch.randint, torch.randn_like = o_randint, o_randn_like
+        torch.nn.functional.dropout = o_dropout

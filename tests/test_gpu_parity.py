@@ -317,3 +317,44 @@ def test_training_losses_batch64_properties():
     assert abs(whole - halves) < 1e-5 * whole
     ref = O.chamfer_distance(a[:4].cpu(), b[:4].cpu())
     assert abs(float(eng.chamfer(a[:4], b[:4])) - float(ref)) < 1e-4 * float(ref)
+
+
+def test_train_mode_forward_vs_reference_golden(mode):
+    """model.train(): BatchNorm batch statistics + running-stat updates + Dropout mask, against the live-reference fixture."""
+    g = golden("trainmode_wellcond")
+    m, diff = _model("wellcond")
+    m.train()
+    B = 3
+    inp = _cuda(syn.make_inputs(13, B, training=True))
+    fps, noise = syn.make_step_randoms(14, B, 1)
+    drop = syn.make_dropout_mask(15, B).cuda()
+    x_t = diff._engine(m, B, torch.device("cuda", torch.cuda.current_device())).q_sample(inp["x_start"], inp["t"], noise[0].cuda())
+    m.encode(inp["mask"], inp["given_objs"], inp["given_cats"], inp["text_emb"], fps[0], device=x_t.device, drop_mask=drop)
+    eng = m._engine
+    out_cat, x0, guiding = eng.forward(x_t, inp["t"])
+    cat_loss = float(eng.cat_loss(out_cat, inp["target_cat"])) * 0.1
+    mse = float(eng.chamfer(x0, inp["x_start"]))
+    tol = 1e-3
+    assert abs(cat_loss - float(g["cat_loss"])) < tol * float(g["cat_loss"])
+    assert abs(mse - float(g["mse"])) < tol * float(g["mse"])
+    assert rel_l2(guiding.cpu(), g["guiding"]) < TOL_E2E
+    sd = m.state_dict()
+    for k in g:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel_l2(sd[k].cpu(), g[k]) < TOL_STAGE[mode], k
+        elif k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(g[k])
+    # back to eval: the handle re-folds BatchNorm with the UPDATED running statistics
+    m.eval()
+    sd_new = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    inp2 = syn.make_inputs(1, 2)
+    fps2, _ = syn.make_step_randoms(2, 2, 1)
+    xo = inp2["x_T"].clone()
+    t2 = torch.tensor([999, 0])
+    _, x0o, _ = O.forward(sd_new, xo, inp2["mask"], t2, inp2["given_objs"], inp2["given_cats"], inp2["text_emb"], list(fps2[0]))
+    g2 = _cuda(inp2)
+    x = g2["x_T"].clone()
+    with injected_rng(fps_starts=list(fps2[0])):
+        _, x0 = m(x, g2["mask"], t2.cuda(), g2["given_objs"], g2["given_cats"], g2["text_emb"])
+    assert rel_l2(x0.cpu(), x0o) < TOL_E2E
+    assert rel_l2(x.cpu(), xo) < TOL_E2E

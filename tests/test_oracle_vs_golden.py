@@ -130,3 +130,27 @@ def test_as_written_attention_equals_collapsed():
     a = O.point_attention(sd, tr, p1, as_written=True)
     b = O.point_attention(sd, tr, p1, as_written=False)
     assert rel_l2(a, b) < 1e-5
+
+
+def test_train_mode_forward_and_bn_updates():
+    """model.train(): BatchNorm batch statistics, running-stat updates (momentum 0.1, unbiased var), Dropout(0.5) mask injected."""
+    g = golden("trainmode_wellcond")
+    sd = syn.make_state_dict(0, "wellcond")
+    B = 3
+    inp = syn.make_inputs(13, B, training=True)
+    fps, noise = syn.make_step_randoms(14, B, 1)
+    mask = syn.make_dropout_mask(15, B)
+    tables = O.diffusion_tables(O.cosine_betas(1000))
+    tr = {}
+    terms = O.training_losses(sd, tables, inp["x_start"], inp["mask"], inp["t"], inp["given_objs"], inp["given_cats"], inp["target_cat"],
+                              inp["text_emb"], list(fps[0]), noise[0], train=tr, drop_mask=mask)
+    for k in ("cat_loss", "mse", "loss"):
+        assert abs(float(terms[k]) - float(g[k])) <= 2e-5 * abs(float(g[k])), k
+    n = 0
+    for k in g:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel_l2(tr["updates"][k], g[k]) < TOL, k
+            n += 1
+        elif k.endswith("num_batches_tracked"):
+            assert int(tr["updates"][k]) == int(g[k])
+    assert n == 14 and len([k for k in tr["updates"] if k.endswith("running_mean")]) == 22
