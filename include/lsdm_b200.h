@@ -102,6 +102,13 @@ LSDM_API int lsdm_encode_conditions(lsdm_handle* h, const float* text_emb, const
 LSDM_API int lsdm_encode_conditions_train(lsdm_handle* h, const float* text_emb, const float* given_objs, const float* given_cats,
                                           const float* mask_global, const int64_t* fps_start, const float* drop_mask, void* stream);
 
+/* SyncBN hook for data-parallel train-mode forwards: called (on the host, while kernels are being enqueued) once per BatchNorm
+ * layer with a DEVICE buffer of n doubles (per-channel sums and sums of squares of this shard); it must enqueue, on the stream
+ * passed to lsdm_encode_conditions_train, an in-place SUM all-reduce over the shards and return 0.  Shards must be equal-sized
+ * (batch_global / batch_local of them).  NULL disables it (per-shard statistics). */
+typedef int (*lsdm_allreduce_fn)(void* ctx, double* device_buf, int32_t n);
+LSDM_API int lsdm_set_allreduce(lsdm_handle* h, lsdm_allreduce_fn fn, void* ctx);
+
 /* Current value of a state-dict entry held by the handle (e.g. BatchNorm running statistics after a train-mode forward);
  * dst host or device, numel must match. */
 LSDM_API int lsdm_read_weight(lsdm_handle* h, const char* key, float* dst, int64_t numel, void* stream);

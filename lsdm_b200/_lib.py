@@ -43,6 +43,7 @@ PROTOTYPES = {
     "lsdm_set_workspace": (C.c_int, [_P, _P, C.c_size_t]),
     "lsdm_encode_conditions": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "lsdm_encode_conditions_train": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "lsdm_set_allreduce": (C.c_int, [_P, _P, _P]),
     "lsdm_read_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, _P]),
     "lsdm_denoise_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "lsdm_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
@@ -62,6 +63,8 @@ PROTOTYPES = {
     "lsdm_profile_report": (C.c_char_p, [_P]),
     "lsdm_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_double)]),
 }
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int32)
 
 _lib = None
 

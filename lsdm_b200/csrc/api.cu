@@ -93,7 +93,9 @@ struct lsdm_handle {
   float *sa_w[4][3], *sa_b[4][3], *sa_wx[4], *sa_wf[4];
   float *fp_w[4][3], *fp_b[4][3], *fp_wa[4], *fp_wb[4];
   float *sa_wx_raw[4], *sa_wf_raw[4], *fp_wa_raw[4], *fp_wb_raw[4];  // un-folded first-layer splits (train-mode BatchNorm)
-  bool fold_dirty = false;  // running statistics changed (train-mode forward): re-fold before the next eval-mode encode
+  bool fold_dirty = false;
+  lsdm_allreduce_fn allreduce = nullptr;  // SyncBN hook: sums the train-mode BatchNorm statistics over data-parallel shards
+  void* allreduce_ctx = nullptr;  // running statistics changed (train-mode forward): re-fold before the next eval-mode encode
   float *head_w, *head_b;
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
@@ -770,10 +772,15 @@ int dense_phase_train(lsdm_handle* h, const Workspace::Sel& q, const float* clou
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   const float* feat[5] = {clouds, w.feat[1], w.feat[2], w.feat[3], w.feat[4]};
   auto mut = [&](const std::string& k) { return const_cast<float*>(h->W(k)); };
+  // statistics are over the GLOBAL batch: with a SyncBN hook the per-shard (sum, sum of squares) are all-reduced and the
+  // row count is scaled by the number of (equal-sized) shards
+  const int64_t shards = h->allreduce ? h->cfg.batch_global / h->cfg.batch_local : 1;
+  int hook_err = 0;
   auto bn = [&](const std::string& key, float* y, int64_t M, int N, const float* mask, float* pooled) {
     prof_launch(h, st, K_OTHER, [&] { return launch_col_stats(y, M, N, w.bn_stats, st); });
+    if (h->allreduce && h->allreduce(h->allreduce_ctx, w.bn_stats, 2 * N) != 0) hook_err = 1;
     prof_launch(h, st, K_OTHER, [&] {
-      return launch_bn_apply(y, M, N, w.bn_stats, h->W(key + ".weight"), h->W(key + ".bias"), mut(key + ".running_mean"),
+      return launch_bn_apply(y, M, M * shards, N, w.bn_stats, h->W(key + ".weight"), h->W(key + ".bias"), mut(key + ".running_mean"),
                              mut(key + ".running_var"), mask, NPTS, pooled, 0, st);
     });
   };
@@ -829,6 +836,7 @@ int dense_phase_train(lsdm_handle* h, const Workspace::Sel& q, const float* clou
     }
   }
   h->fold_dirty = true;
+  if (hook_err) return fail(LSDM_EINVAL, "all-reduce hook failed");
   CK(cudaPeekAtLastError());
   return LSDM_OK;
 }
@@ -871,6 +879,13 @@ LSDM_API int lsdm_encode_conditions_train(lsdm_handle* h, const float* text, con
   cudaStream_t st = (cudaStream_t)stream;
   GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start, st));
   return encode_dense(h, text, objs, cats, mask_global, 0, st, drop_mask);
+}
+
+LSDM_API int lsdm_set_allreduce(lsdm_handle* h, lsdm_allreduce_fn fn, void* ctx) {
+  if (!h) return fail(LSDM_EINVAL, "null handle");
+  h->allreduce = fn;
+  h->allreduce_ctx = ctx;
+  return LSDM_OK;
 }
 
 LSDM_API int lsdm_read_weight(lsdm_handle* h, const char* key, float* dst, int64_t numel, void* stream) {

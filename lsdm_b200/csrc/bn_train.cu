@@ -29,21 +29,21 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
 
 // y <- [mask *] relu((y - mean) * rstd * gamma + beta); optional out[g, col] = max over rows [32g, 32g+32)
 // block 0 also folds the batch statistics into the running statistics.
-__global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, int64_t M, int N, const double* __restrict__ sums,
+__global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ y, int64_t M, int64_t Ms, int N, const double* __restrict__ sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ run_mean, float* __restrict__ run_var, float eps,
                                                        float momentum, const float* __restrict__ drop_mask, int mask_points,
                                                        float* __restrict__ pooled, int round_out) {
   extern __shared__ float s_par[];  // scale[N], shift[N]
   for (int c = threadIdx.x; c < N; c += blockDim.x) {
-    double mean = sums[c] / (double)M;
-    double var = sums[N + c] / (double)M - mean * mean;
+    double mean = sums[c] / (double)Ms;  // Ms: rows behind the statistics (all shards when SyncBN is on)
+    double var = sums[N + c] / (double)Ms - mean * mean;
     if (var < 0.0) var = 0.0;
     float sc = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
     s_par[c] = sc;
     s_par[N + c] = beta[c] - (float)mean * sc;
     if (blockIdx.x == 0) {
-      double unb = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+      double unb = Ms > 1 ? var * ((double)Ms / (double)(Ms - 1)) : var;
       run_mean[c] = (1.0f - momentum) * run_mean[c] + momentum * (float)mean;
       run_var[c] = (1.0f - momentum) * run_var[c] + momentum * (float)unb;
     }
@@ -96,11 +96,11 @@ int launch_col_stats(const float* y, int64_t M, int N, double* sums, cudaStream_
   return 1;
 }
 
-int launch_bn_apply(float* y, int64_t M, int N, const double* sums, const float* gamma, const float* beta, float* run_mean,
+int launch_bn_apply(float* y, int64_t M, int64_t M_stat, int N, const double* sums, const float* gamma, const float* beta, float* run_mean,
                     float* run_var, const float* drop_mask, int mask_points, float* pooled, int round_out, cudaStream_t st) {
   int64_t g = (M + 63) / 64;
   if (g > 148 * 8) g = 148 * 8;
-  bn_apply_kernel<<<(unsigned)g, 256, 2 * N * sizeof(float), st>>>(y, M, N, sums, gamma, beta, run_mean, run_var, 1e-5f, 0.1f, drop_mask,
+  bn_apply_kernel<<<(unsigned)g, 256, 2 * N * sizeof(float), st>>>(y, M, M_stat, N, sums, gamma, beta, run_mean, run_var, 1e-5f, 0.1f, drop_mask,
                                                                 mask_points, pooled, round_out);
   return 1;
 }

@@ -50,7 +50,7 @@ int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const flo
 // train-mode BatchNorm: column statistics (double), then normalise + ReLU [+ dropout mask] [+ 32-row max-pool] and the
 // running-statistics update (momentum 0.1, unbiased variance)
 int launch_col_stats(const float* y, int64_t M, int N, double* sums, cudaStream_t st);
-int launch_bn_apply(float* y, int64_t M, int N, const double* sums, const float* gamma, const float* beta, float* run_mean,
+int launch_bn_apply(float* y, int64_t M, int64_t M_stat, int N, const double* sums, const float* gamma, const float* beta, float* run_mean,
                     float* run_var, const float* drop_mask, int mask_points, float* pooled, int round_out, cudaStream_t st);
 
 // ---- cond.cu --------------------------------------------------------------------------------

@@ -158,6 +158,29 @@ class Engine:
         if not fps_start.is_cuda:
             torch.cuda.current_stream(self.device).synchronize()
 
+    def set_allreduce(self, process_group=None, enabled=True):
+        """SyncBN for sharded train-mode forwards: BatchNorm (sum, sum-of-squares) buffers are all-reduced over ``process_group``
+        (torch.distributed, NCCL) between the statistics and the normalisation kernels of every layer."""
+        if not enabled:
+            _lib.check(self.lib.lsdm_set_allreduce(self.h, None, None))
+            self._allreduce_cb = None
+            return
+        import torch.distributed as dist
+
+        def hook(_ctx, ptr, n):
+            try:
+                off = int(ptr) - self._ws.data_ptr()
+                buf = self._ws[off:off + 8 * n].view(torch.float64)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=process_group)
+                return 0
+            except Exception:  # pragma: no cover
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._allreduce_cb = _lib.ALLREDUCE_FN(hook)  # keep alive
+        _lib.check(self.lib.lsdm_set_allreduce(self.h, C.cast(self._allreduce_cb, C.c_void_p), None))
+
     def read_weight(self, key, like):
         """Current value of a state-dict entry inside the handle (BatchNorm running statistics after a train-mode forward)."""
         out = torch.empty(like.shape, dtype=torch.float32, device=self.device)

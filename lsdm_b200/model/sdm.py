@@ -178,6 +178,7 @@ class SceneDiffusionModel(nn.Module):
         self._engine_sig = None
         self._weights_sig = None
         self._shard = None  # (batch_global, batch_offset)
+        self._sync_bn_group = None
         self._text_encoder = None
         if use_cuda and torch.cuda.is_available():
             self.to(self.device)
@@ -194,10 +195,11 @@ class SceneDiffusionModel(nn.Module):
         """``fn(list[str]) -> [B,512]`` float tensor; stands in for the frozen CLIP text tower (out of scope)."""
         self._text_encoder = fn
 
-    def set_shard(self, batch_global=None, batch_offset=0):
+    def set_shard(self, batch_global=None, batch_offset=0, sync_bn_group=None):
         """Data-parallel sharding: this process holds samples [offset, offset+B) of a global batch; ``mask`` arguments
         must then be the GLOBAL ``[batch_global, 9]`` mask (the reference's mask scrambles index it)."""
         self._shard = None if batch_global is None else (int(batch_global), int(batch_offset))
+        self._sync_bn_group = sync_bn_group  # torch.distributed group (or True for the default group) for train-mode SyncBN
 
     def _encode_text(self, y):
         if torch.is_tensor(y):
@@ -249,9 +251,14 @@ class SceneDiffusionModel(nn.Module):
             # model.train(): BatchNorm batch statistics over all 9B clouds + Dropout(0.5) in the backbone head.  The mask is what
             # F.dropout would draw for the reference's [9B,128,1024] activation (same generator, same shape).
             if self._shard is not None:
-                raise NotImplementedError("train-mode BatchNorm couples all clouds of the batch; sharded statistics (SyncBN) are not built")
+                # BatchNorm couples all 9B clouds of the GLOBAL batch: SyncBN over the data-parallel group
+                if self._sync_bn_group is None:
+                    raise NotImplementedError("sharded train-mode forward needs set_shard(..., sync_bn_group=<process group>) (SyncBN)")
+                eng.set_allreduce(self._sync_bn_group if self._sync_bn_group is not True else None)
             if drop_mask is None:
-                drop_mask = torch.nn.functional.dropout(torch.ones(B * N_OBJ, 128, N_POINTS, device=eng.device), 0.5, True)
+                bg, off = self._shard if self._shard is not None else (B, 0)
+                full = torch.nn.functional.dropout(torch.ones(bg * N_OBJ, 128, N_POINTS, device=eng.device), 0.5, True)
+                drop_mask = full[off * N_OBJ:(off + B) * N_OBJ].contiguous()
             eng.encode_conditions_train(self._encode_text(y), given_objs, given_cats, mask, fps_start, drop_mask)
             self._pull_bn_stats(eng)
         else:

@@ -221,6 +221,7 @@ def main():
         "train_wellcond": lambda: case_train("wellcond"),
         "shard_wellcond": case_shard,
         "trainmode_wellcond": case_train_forward,
+        "trainmode_b4_wellcond": lambda: case_train_forward("wellcond", 4, 16, 17, 18),
     }
     only = sys.argv[1:]
     for name, fn in jobs.items():

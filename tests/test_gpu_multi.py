@@ -21,3 +21,13 @@ def test_bench_two_ranks_nccl():
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 16 and line["value"] > 0
     assert line["gpu_launches"] > 0 and line["scaling"] == "weak" and line["e2e"]["value"] > 0
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_train_mode_syncbn_two_ranks():
+    """Sharded train-mode forward (global batch 4 over 2 ranks): BatchNorm statistics all-reduced over NCCL reproduce the
+    unsharded reference's running statistics, guiding points and losses."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "tests", "multi_train_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0 and "SYNCBN_OK" in out.stdout, out.stderr[-3000:]
