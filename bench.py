@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -210,14 +210,14 @@ def run_ours(args):
         return eng.sample_loop(xbuf, g["text_emb"], g["given_objs"], g["given_cats"], g["mask"], fps_dev[first_k:first_k + n],
                                noise_dev[first_k:first_k + n], T - 1 - first_k, hoisted)
 
-    # warm-up (untimed)
+    # warm-up (untimed); the clock sampler starts here so that it holds samples taken under load (warm-up + timed region)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     run_steps(0, W, x)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     l0 = eng.launch_count()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -321,7 +321,7 @@ def run_ours(args):
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_port_rate(2, 1)
+            cb = cpu_port_rate(4, 1)
             cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
