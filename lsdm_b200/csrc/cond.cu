@@ -11,13 +11,23 @@ namespace {
 template <int ACT>
 __device__ __forceinline__ void cta_linear(const float* __restrict__ W, const float* __restrict__ b, const float* x,
                                            float* y, int N, int K) {
+  // four outputs per warp iteration: their weight-row loads are issued together, so one L2 round trip covers four rows
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int n = warp; n < N; n += nw) {
-    const float* w = W + (int64_t)n * K;
-    float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc = fmaf(w[k], x[k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) y[n] = apply_act<ACT>(acc + (b ? b[n] : 0.f));
+  for (int n0 = warp * 4; n0 < N; n0 += nw * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < K; k += 32) {
+      const float xv = x[k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + j < N ? n0 + j : N - 1;
+        acc[j] = fmaf(W[(int64_t)n * K + k], xv, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = warp_sum(acc[j]);
+      if (lane == 0 && n0 + j < N) y[n0 + j] = apply_act<ACT>(a + (b ? b[n0 + j] : 0.f));
+    }
   }
   __syncthreads();
 }
@@ -143,39 +153,35 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------
 constexpr int HS = 64;  // points per CTA
 
-// stats[b][layer][group][2] (double): sum, sumsq
-__device__ __forceinline__ void group_stats_accumulate(const float (&acc)[16], int p_valid, int chq, double* stats_out,
-                                                        double* s_red) {
-  // thread holds 16 consecutive channels (2 groups) of one point
-  double s0 = 0, q0 = 0, s1 = 0, q1 = 0;
-  if (p_valid) {
+// stats[b][layer][group][2] (double): sum, sumsq.  A thread holds channels ch = e*4 + chq (e = 0..15) of one point, i.e. two
+// channels of every one of the 8 groups (group = ch / 8 = e / 2).
+__device__ __forceinline__ void group_stats_accumulate(const float (&acc)[16], int p_valid, double* stats_out, double* s_red) {
+  double s[8], q[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      s0 += acc[e];
-      q0 += (double)acc[e] * acc[e];
-      s1 += acc[8 + e];
-      q1 += (double)acc[8 + e] * acc[8 + e];
+  for (int g = 0; g < 8; ++g) {
+    const double a0 = p_valid ? (double)acc[2 * g] : 0.0, a1 = p_valid ? (double)acc[2 * g + 1] : 0.0;
+    s[g] = a0 + a1;
+    q[g] = a0 * a0 + a1 * a1;
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    for (int o = 16; o > 0; o >>= 1) {
+      s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+      q[g] += __shfl_xor_sync(0xffffffffu, q[g], o);
+    }
+  const int tid = threadIdx.x;
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      s_red[((tid >> 5) * 8 + g) * 2] = s[g];
+      s_red[((tid >> 5) * 8 + g) * 2 + 1] = q[g];
     }
   }
-  // reduce over the points of the CTA: threads with equal chq (tid % 4)
-  const int tid = threadIdx.x;
-  for (int o = 4; o < 32; o <<= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-  }
-  if ((tid & 31) < 4) {
-    double* r = s_red + ((tid >> 5) * 4 + chq) * 4;
-    r[0] = s0; r[1] = q0; r[2] = s1; r[3] = q1;
-  }
   __syncthreads();
-  if (tid < 16) {  // 4 chq x 4 values
-    int q = tid >> 2, v = tid & 3;
+  if (tid < 16) {  // 8 groups x (sum, sumsq)
     double t = 0;
-    for (int w = 0; w < 8; ++w) t += s_red[(w * 4 + q) * 4 + v];
-    int group = q * 2 + (v >> 1);
-    atomicAdd(&stats_out[group * 2 + (v & 1)], t);
+    for (int w = 0; w < 8; ++w) t += s_red[(w * 8 + (tid >> 1)) * 2 + (tid & 1)];
+    atomicAdd(&stats_out[tid], t);
   }
 }
 
@@ -183,7 +189,7 @@ __device__ __forceinline__ void group_stats_accumulate(const float (&acc)[16], i
 __global__ void __launch_bounds__(256) human_l0_kernel(HumanWeights w, const float* __restrict__ objs, float* __restrict__ y0,
                                                        double* __restrict__ stats) {
   __shared__ float s_w[64 * 3], s_b[64];
-  __shared__ double s_red[8 * 4 * 4];
+  __shared__ double s_red[8 * 8 * 2];
   const int b = blockIdx.y, p0 = blockIdx.x * HS, tid = threadIdx.x;
   if (tid < 192) s_w[tid] = w.w0[tid];
   if (tid < 64) s_b[tid] = w.b0[tid];
@@ -194,13 +200,13 @@ __global__ void __launch_bounds__(256) human_l0_kernel(HumanWeights w, const flo
   float acc[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
-    int ch = chq * 16 + e;
+    int ch = e * 4 + chq;
     acc[e] = fmaf(s_w[ch * 3 + 2], z, fmaf(s_w[ch * 3 + 1], y, fmaf(s_w[ch * 3], x, s_b[ch])));
   }
-  float* o = y0 + ((int64_t)b * NPTS + p) * 64 + chq * 16;
+  float* o = y0 + ((int64_t)b * NPTS + p) * 64 + chq;
 #pragma unroll
-  for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
-  group_stats_accumulate(acc, 1, chq, stats + ((int64_t)b * 3 + 0) * 16, s_red);
+  for (int e = 0; e < 16; ++e) o[e * 4] = acc[e];
+  group_stats_accumulate(acc, 1, stats + ((int64_t)b * 3 + 0) * 16, s_red);
 }
 
 // layers 1, 2: y = W relu(gn(prev)) + b over npts points (64 -> 64), stats
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict_
   __shared__ __align__(16) float s_w[64 * 68];  // [ch][k], row stride 68 floats (16B aligned, conflict-free float4 reads)
   __shared__ __align__(16) float s_a[HS * 68];  // normalised + ReLU input slab [p][k], row stride 68 (conflict-free float4 reads)
   __shared__ float s_b[64], s_scale[64], s_shift[64];
-  __shared__ double s_red[8 * 4 * 4];
+  __shared__ double s_red[8 * 8 * 2];
   const int b = blockIdx.y, p0 = blockIdx.x * HS, tid = threadIdx.x;
   for (int i = tid; i < 64 * 64; i += 256) s_w[(i >> 6) * 68 + (i & 63)] = Wl[i];
   if (tid < 64) {
@@ -237,22 +243,23 @@ __global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict_
   const int pl = tid >> 2, chq = tid & 3, p = p0 + pl;
   float acc[16];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = s_b[chq * 16 + e];
+  for (int e = 0; e < 16; ++e) acc[e] = s_b[e * 4 + chq];
+  // channel ch = e*4 + chq: the 4 lanes of a point read 4 consecutive weight rows (stride 68 floats -> distinct banks)
 #pragma unroll 4
   for (int k = 0; k < 64; k += 4) {
     float4 a4 = *reinterpret_cast<const float4*>(&s_a[pl * 68 + k]);
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-      float4 w4 = *reinterpret_cast<const float4*>(&s_w[(chq * 16 + e) * 68 + k]);
+      float4 w4 = *reinterpret_cast<const float4*>(&s_w[(e * 4 + chq) * 68 + k]);
       acc[e] = fmaf(w4.w, a4.w, fmaf(w4.z, a4.z, fmaf(w4.y, a4.y, fmaf(w4.x, a4.x, acc[e]))));
     }
   }
   if (p < npts) {
-    float* o = out + ((int64_t)b * NPTS + p) * 64 + chq * 16;
+    float* o = out + ((int64_t)b * NPTS + p) * 64 + chq;
 #pragma unroll
-    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+    for (int e = 0; e < 16; ++e) o[e * 4] = acc[e];
   }
-  group_stats_accumulate(acc, p < npts, chq, stats + ((int64_t)b * 3 + slot_out) * 16, s_red);
+  group_stats_accumulate(acc, p < npts, stats + ((int64_t)b * 3 + slot_out) * 16, s_red);
 }
 
 // final: hm[2p], hm[2p+1] = W3 relu(gn(y2[p])) + b3 for p < 512 (64 -> 3, nearest x2 upsample, first 1024 kept)

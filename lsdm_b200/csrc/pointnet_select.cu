@@ -136,17 +136,12 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
                                                          int n_clouds, int N, int S, float r2, int* __restrict__ group) {
-  extern __shared__ float sm[];  // x[N], y[N], z[N], n2[N]
-  float* sx = sm;
-  float* sy = sm + N;
-  float* sz = sm + 2 * N;
-  float* s2 = sm + 3 * N;
+  extern __shared__ float4 sp[];  // (x, y, z, |p|^2) per source point: one 128-bit shared load per pair test
   const int c = blockIdx.y;
   const float* src = xyz + (int64_t)c * N * 3;
   for (int p = threadIdx.x; p < N; p += blockDim.x) {
     float x = src[p * 3], y = src[p * 3 + 1], z = src[p * 3 + 2];
-    sx[p] = x; sy[p] = y; sz[p] = z;
-    s2[p] = sqnorm3(x, y, z);
+    sp[p] = make_float4(x, y, z, sqnorm3(x, y, z));
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -160,7 +155,8 @@ __global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict
       int p = base + lane;
       bool in = false;
       if (p < N) {
-        float d = sqdist_expanded(qx, qy, qz, q2, sx[p], sy[p], sz[p], s2[p]);
+        const float4 v = sp[p];
+        float d = sqdist_expanded(qx, qy, qz, q2, v.x, v.y, v.z, v.w);
         in = !(d > r2);
       }
       unsigned m = __ballot_sync(0xffffffffu, in);
@@ -180,45 +176,61 @@ __global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // 3-NN inverse-distance weights for feature propagation: for every fine point the 3 smallest
 // expanded-form distances to the S coarse points (ascending, lowest index on ties),
-// w_k = (1/(d_k+1e-8)) / sum_k (1/(d_k+1e-8)).
+// w_k = (1/(d_k+1e-8)) / sum_k (1/(d_k+1e-8)).  Two fine points per thread share each shared-memory load.
 // ---------------------------------------------------------------------------------------------
+struct Top3 {
+  float d0, d1, d2;
+  int i0, i1, i2;
+  __device__ __forceinline__ void init() {
+    d0 = d1 = d2 = INFINITY;
+    i0 = i1 = i2 = 0;
+  }
+  __device__ __forceinline__ void push(float d, int s) {
+    if (d < d2) {
+      if (d < d1) {
+        d2 = d1; i2 = i1;
+        if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = s; }
+        else { d1 = d; i1 = s; }
+      } else { d2 = d; i2 = s; }
+    }
+  }
+  __device__ __forceinline__ void store(int* nn_idx, float* nn_w, int64_t o) const {
+    float r0 = 1.0f / (d0 + 1e-8f), r1 = 1.0f / (d1 + 1e-8f), r2 = 1.0f / (d2 + 1e-8f);
+    float norm = (r0 + r1) + r2;
+    nn_idx[o] = i0; nn_idx[o + 1] = i1; nn_idx[o + 2] = i2;
+    nn_w[o] = r0 / norm; nn_w[o + 1] = r1 / norm; nn_w[o + 2] = r2 / norm;
+  }
+};
+
 __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                                                        int n_clouds, int N, int S, int* __restrict__ nn_idx,
                                                        float* __restrict__ nn_w) {
-  extern __shared__ float sm[];
-  float* sx = sm;
-  float* sy = sm + S;
-  float* sz = sm + 2 * S;
-  float* s2 = sm + 3 * S;
+  extern __shared__ float4 sp[];
   const int c = blockIdx.y;
   const float* src = xyz2 + (int64_t)c * S * 3;
   for (int p = threadIdx.x; p < S; p += blockDim.x) {
     float x = src[p * 3], y = src[p * 3 + 1], z = src[p * 3 + 2];
-    sx[p] = x; sy[p] = y; sz[p] = z;
-    s2[p] = sqnorm3(x, y, z);
+    sp[p] = make_float4(x, y, z, sqnorm3(x, y, z));
   }
   __syncthreads();
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-    const float* q = xyz1 + ((int64_t)c * N + n) * 3;
-    float qx = q[0], qy = q[1], qz = q[2];
-    float q2 = sqnorm3(qx, qy, qz);
-    float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
-    int i0 = 0, i1 = 0, i2 = 0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += 2 * stride) {
+    const int n2 = n + stride;
+    const bool two = n2 < N;
+    const float* qa = xyz1 + ((int64_t)c * N + n) * 3;
+    const float* qb = xyz1 + ((int64_t)c * N + (two ? n2 : n)) * 3;
+    const float ax = qa[0], ay = qa[1], az = qa[2], a2 = sqnorm3(ax, ay, az);
+    const float bx = qb[0], by = qb[1], bz = qb[2], b2 = sqnorm3(bx, by, bz);
+    Top3 ta, tb;
+    ta.init();
+    tb.init();
     for (int s = 0; s < S; ++s) {
-      float d = sqdist_expanded(qx, qy, qz, q2, sx[s], sy[s], sz[s], s2[s]);
-      if (d < d2) {
-        if (d < d1) {
-          d2 = d1; i2 = i1;
-          if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = s; }
-          else { d1 = d; i1 = s; }
-        } else { d2 = d; i2 = s; }
-      }
+      const float4 v = sp[s];
+      ta.push(sqdist_expanded(ax, ay, az, a2, v.x, v.y, v.z, v.w), s);
+      tb.push(sqdist_expanded(bx, by, bz, b2, v.x, v.y, v.z, v.w), s);
     }
-    float r0 = 1.0f / (d0 + 1e-8f), r1 = 1.0f / (d1 + 1e-8f), r2 = 1.0f / (d2 + 1e-8f);
-    float norm = (r0 + r1) + r2;
-    int64_t o = ((int64_t)c * N + n) * 3;
-    nn_idx[o] = i0; nn_idx[o + 1] = i1; nn_idx[o + 2] = i2;
-    nn_w[o] = r0 / norm; nn_w[o + 1] = r1 / norm; nn_w[o + 2] = r2 / norm;
+    ta.store(nn_idx, nn_w, ((int64_t)c * N + n) * 3);
+    if (two) tb.store(nn_idx, nn_w, ((int64_t)c * N + n2) * 3);
   }
 }
 
@@ -237,15 +249,15 @@ int launch_ball_query(const float* xyz, const float* new_xyz, int n_clouds, int 
   int gx = (S + warps - 1) / warps;
   if (gx > 16) gx = 16;
   dim3 grid(gx, n_clouds);
-  ball_query_kernel<<<grid, warps * 32, 4 * N * sizeof(float), st>>>(xyz, new_xyz, n_clouds, N, S, r2, group);
+  ball_query_kernel<<<grid, warps * 32, N * sizeof(float4), st>>>(xyz, new_xyz, n_clouds, N, S, r2, group);
   return 1;
 }
 
 int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, int S, int* nn_idx, float* nn_w,
                     cudaStream_t st) {
-  int threads = N >= 256 ? 256 : 64;
-  dim3 grid((N + threads - 1) / threads, n_clouds);
-  three_nn_kernel<<<grid, threads, 4 * S * sizeof(float), st>>>(xyz1, xyz2, n_clouds, N, S, nn_idx, nn_w);
+  int threads = N >= 512 ? 256 : 64;
+  dim3 grid((N + 2 * threads - 1) / (2 * threads), n_clouds);  // two fine points per thread
+  three_nn_kernel<<<grid, threads, S * sizeof(float4), st>>>(xyz1, xyz2, n_clouds, N, S, nn_idx, nn_w);
   return 1;
 }
 
