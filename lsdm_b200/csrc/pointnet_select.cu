@@ -19,7 +19,10 @@ template <int N, int NP>
 __device__ __forceinline__ void fps_level(const float* sx, const float* sy, const float* sz, int start, int* s_idx,
                                           unsigned long long* s_red, int tid) {
   constexpr int PER = (N + FPS_T - 1) / FPS_T;
+  constexpr bool PACKED = (N % FPS_T == 0) && (PER % 2 == 0);  // two points per instruction (fp32x2), every slot valid
+  constexpr int PER2 = PACKED ? PER / 2 : 1;
   float px[PER], py[PER], pz[PER], dist[PER];
+  float2 qx[PER2], qy[PER2], qz[PER2], qd[PER2];
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     int p = tid + k * FPS_T;
@@ -29,25 +32,49 @@ __device__ __forceinline__ void fps_level(const float* sx, const float* sy, cons
     pz[k] = ok ? sz[p] : 0.f;
     dist[k] = 1e10f;
   }
+  if (PACKED) {
+#pragma unroll
+    for (int j = 0; j < PER2; ++j) {
+      qx[j] = make_float2(px[2 * j], px[2 * j + 1]);
+      qy[j] = make_float2(py[2 * j], py[2 * j + 1]);
+      qz[j] = make_float2(pz[2 * j], pz[2 * j + 1]);
+      qd[j] = make_float2(1e10f, 1e10f);
+    }
+  }
   int far = start;
   const int lane = tid & 31, warp = tid >> 5;
   for (int it = 0; it < NP; ++it) {
     if (tid == 0) s_idx[it] = far;
     float cx = sx[far], cy = sy[far], cz = sz[far];
     unsigned best_bits = 0u;
-    unsigned best_idx = 0xffffffffu;
+    unsigned best_idx = PACKED ? (unsigned)tid : 0xffffffffu;
+    if (PACKED) {
+      // x - c == x + (-c) exactly; every op is an IEEE round-to-nearest add / mul, same as the scalar path (no FMA)
+      const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      int p = tid + k * FPS_T;
-      if (p < N) {
-        float dx = __fsub_rn(px[k], cx), dy = __fsub_rn(py[k], cy), dz = __fsub_rn(pz[k], cz);
-        float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        float nd = (d < dist[k]) ? d : dist[k];
-        dist[k] = nd;
-        unsigned b = __float_as_uint(nd);  // nd >= 0: unsigned bit order == float order
-        if (best_idx == 0xffffffffu || b > best_bits) {
-          best_bits = b;
-          best_idx = (unsigned)p;
+      for (int j = 0; j < PER2; ++j) {
+        float2 dx = __fadd2_rn(qx[j], ncx), dy = __fadd2_rn(qy[j], ncy), dz = __fadd2_rn(qz[j], ncz);
+        float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+        float n0 = fminf(d.x, qd[j].x), n1 = fminf(d.y, qd[j].y);
+        qd[j] = make_float2(n0, n1);
+        unsigned b0 = __float_as_uint(n0), b1 = __float_as_uint(n1);  // >= 0: unsigned bit order == float order
+        if (b0 > best_bits) { best_bits = b0; best_idx = (unsigned)(tid + (2 * j) * FPS_T); }
+        if (b1 > best_bits) { best_bits = b1; best_idx = (unsigned)(tid + (2 * j + 1) * FPS_T); }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        int p = tid + k * FPS_T;
+        if (p < N) {
+          float dx = __fsub_rn(px[k], cx), dy = __fsub_rn(py[k], cy), dz = __fsub_rn(pz[k], cz);
+          float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          float nd = (d < dist[k]) ? d : dist[k];
+          dist[k] = nd;
+          unsigned b = __float_as_uint(nd);
+          if (best_idx == 0xffffffffu || b > best_bits) {
+            best_bits = b;
+            best_idx = (unsigned)p;
+          }
         }
       }
     }
@@ -224,10 +251,16 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
     Top3 ta, tb;
     ta.init();
     tb.init();
+    // both queries against the same coarse point in packed fp32x2: identical IEEE operations to sqdist_expanded
+    // (fma(z, fma(y, x*x')), then (-2*dot + |q|^2) + |p|^2), two results per instruction
+    const float2 qx2 = make_float2(ax, bx), qy2 = make_float2(ay, by), qz2 = make_float2(az, bz), qn2 = make_float2(a2, b2);
+    const float2 m2 = make_float2(-2.0f, -2.0f);
     for (int s = 0; s < S; ++s) {
       const float4 v = sp[s];
-      ta.push(sqdist_expanded(ax, ay, az, a2, v.x, v.y, v.z, v.w), s);
-      tb.push(sqdist_expanded(bx, by, bz, b2, v.x, v.y, v.z, v.w), s);
+      float2 dot = __ffma2_rn(qz2, make_float2(v.z, v.z), __ffma2_rn(qy2, make_float2(v.y, v.y), __fmul2_rn(qx2, make_float2(v.x, v.x))));
+      float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(m2, dot), qn2), make_float2(v.w, v.w));
+      ta.push(d.x, s);
+      tb.push(d.y, s);
     }
     ta.store(nn_idx, nn_w, ((int64_t)c * N + n) * 3);
     if (two) tb.store(nn_idx, nn_w, ((int64_t)c * N + n2) * 3);
