@@ -77,13 +77,21 @@ __global__ void __launch_bounds__(256) fp_combine_kernel(const float* __restrict
     const float* b1 = Pb + (c * S + i1) * C1;
     const float* b2 = Pb + (c * S + i2) * C1;
     float* out = h + row * C1;
-    for (int ch = lane; ch < C1; ch += 32) {
-      float v = (Pa != nullptr) ? Pa[row * C1 + ch] : bias[ch];
-      float it = b0[ch] * w0;
-      it = fmaf(b1[ch], w1, it);
-      it = fmaf(b2[ch], w2, it);
-      float r = apply_relu ? fmaxf(v + it, 0.0f) : v + it;
-      out[ch] = round_out ? tc::rna_tf32(r) : r;
+    // 128-bit accesses: a lane owns 4 consecutive channels per iteration (C1 is 128 or 256)
+    for (int c4 = lane; c4 < (C1 >> 2); c4 += 32) {
+      const float4 v = (Pa != nullptr) ? *reinterpret_cast<const float4*>(Pa + row * C1 + c4 * 4)
+                                       : *reinterpret_cast<const float4*>(bias + c4 * 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(b0 + c4 * 4);
+      const float4 x1 = *reinterpret_cast<const float4*>(b1 + c4 * 4);
+      const float4 x2 = *reinterpret_cast<const float4*>(b2 + c4 * 4);
+      float r[4] = {v.x + fmaf(x2.x, w2, fmaf(x1.x, w1, x0.x * w0)), v.y + fmaf(x2.y, w2, fmaf(x1.y, w1, x0.y * w0)),
+                    v.z + fmaf(x2.z, w2, fmaf(x1.z, w1, x0.z * w0)), v.w + fmaf(x2.w, w2, fmaf(x1.w, w1, x0.w * w0))};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (apply_relu) r[e] = fmaxf(r[e], 0.0f);
+        if (round_out) r[e] = tc::rna_tf32(r[e]);
+      }
+      *reinterpret_cast<float4*>(out + c4 * 4) = make_float4(r[0], r[1], r[2], r[3]);
     }
   }
 }

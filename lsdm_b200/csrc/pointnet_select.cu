@@ -178,20 +178,31 @@ __global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict
     float q2 = sqnorm3(qx, qy, qz);
     int* out = group + ((int64_t)c * S + s) * 32;
     int cnt = 0, first = N;
-    for (int base = 0; base < N && cnt < 32; base += 32) {
-      int p = base + lane;
-      bool in = false;
-      if (p < N) {
-        const float4 v = sp[p];
-        float d = sqdist_expanded(qx, qy, qz, q2, v.x, v.y, v.z, v.w);
-        in = !(d > r2);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, in);
+    // 64 source points per warp iteration: each lane tests points base+lane and base+32+lane with packed fp32x2 math
+    // (same IEEE operations as sqdist_expanded); the two 32-point halves are committed in index order
+    const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz), qn2 = make_float2(q2, q2);
+    const float2 m2 = make_float2(-2.0f, -2.0f);
+    for (int base = 0; base < N && cnt < 32; base += 64) {
+      const int p0 = base + lane, p1 = base + 32 + lane;
+      const float4 v0 = sp[p0 < N ? p0 : 0], v1 = sp[p1 < N ? p1 : 0];
+      float2 dot = __ffma2_rn(qz2, make_float2(v0.z, v1.z), __ffma2_rn(qy2, make_float2(v0.y, v1.y), __fmul2_rn(qx2, make_float2(v0.x, v1.x))));
+      float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(m2, dot), qn2), make_float2(v0.w, v1.w));
+      const bool in0 = p0 < N && !(d.x > r2), in1 = p1 < N && !(d.y > r2);
+      unsigned m = __ballot_sync(0xffffffffu, in0);
       if (m) {
         if (first == N) first = base + __ffs(m) - 1;
         int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        if (in && pos < 32) out[pos] = p;
+        if (in0 && pos < 32) out[pos] = p0;
         cnt += __popc(m);
+      }
+      if (cnt < 32) {
+        m = __ballot_sync(0xffffffffu, in1);
+        if (m) {
+          if (first == N) first = base + 32 + __ffs(m) - 1;
+          int pos = cnt + __popc(m & ((1u << lane) - 1u));
+          if (in1 && pos < 32) out[pos] = p1;
+          cnt += __popc(m);
+        }
       }
     }
     if (cnt > 32) cnt = 32;
