@@ -1,11 +1,11 @@
 // Persistent, warp-specialised tcgen05 implementation of the generic linear-layer GEMM (gemm.cuh):
 //   C[M,N] = act(A[M,K] . W[N,K]^T + bias),  TF32 (operands rounded to nearest) or 3xTF32, fp32 accumulate in TMEM.
-// One CTA per SM loops over 128 x BN output tiles.  Nine warps, three roles:
+// One CTA per SM loops over 128 x BN output tiles.  Thirteen warps, three roles:
 //   warps 0-3  producers : ld.global (next k-block prefetched in registers) -> cvt.rna.tf32 [-> hi/lo split] ->
 //                          swizzled st.shared into an NSTAGE ring (K-major SWIZZLE_128B k-blocks) -> mbarrier "full"
-//   warp  8    MMA issuer: one thread; waits "full", issues tcgen05.mma (M=128, N=BN, K=8), tcgen05.commit -> "empty";
+//   warp  12   MMA issuer: one thread; waits "full", issues tcgen05.mma (M=128, N=BN, K=8), tcgen05.commit -> "empty";
 //                          after the last k-block commits the tile's accumulator -> "acc_full"
-//   warps 4-7  epilogue  : tcgen05.ld of the finished accumulator (two TMEM buffers alternate, so the epilogue of tile i
+//   warps 4-11 epilogue  : tcgen05.ld of the finished accumulator (two TMEM buffers alternate, so the epilogue of tile i
 //                          overlaps the loads + MMAs of tile i+1), bias / activation, then either a shared-memory
 //                          transpose for coalesced 128-bit stores or the 32-row group max (redux.sync) -> "acc_empty"
 #include "gemm.cuh"
@@ -19,17 +19,26 @@ using namespace tc;
 
 constexpr int WBM = 128, WBK = 32;
 constexpr int W_A_STAGE = WBM * 128;  // bytes of one A k-block
-constexpr int WS_THREADS = 288;
+constexpr int NPROD = 128;             // producer threads (4 warps)
+constexpr int NEPI = 256;              // epilogue threads: 8 warps, two per TMEM lane quarter (each takes half of the columns);
+                                       // with 4 warps the epilogue (not the MMA) bounded every tile
+constexpr int WS_THREADS = NPROD + NEPI + 32;  // producers | epilogue warps | 1 MMA-issuer warp
 constexpr int WSTG = 36;              // epilogue transpose row stride (floats)
+
+// shared-memory plan: the (SPLIT, BN=256) ring is 2 x 96 KB, which leaves room for only four staging buffers
+__host__ __device__ constexpr int ws_epi_warps(int bn, bool split) { return (split && bn == 256) ? 4 : 8; }
+__host__ __device__ constexpr int ws_nstage(int bn, bool split, bool async) { return split ? 2 : ((async && bn < 256) ? 4 : 3); }
 
 template <int BN, bool SPLIT, bool ASYNC>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int tiles_m, int tiles_n, int total_tiles) {
-  constexpr int NSTAGE = SPLIT ? 2 : (ASYNC ? 4 : 3);
+  constexpr int NSTAGE = ws_nstage(BN, SPLIT, ASYNC);
+  constexpr int EPW = ws_epi_warps(BN, SPLIT);
   constexpr int W_STAGE = BN * 128;
   constexpr int HALF = W_A_STAGE + W_STAGE;          // [A | W]; SPLIT appends [A_lo | W_lo]
   constexpr int STAGE = HALF * (SPLIT ? 2 : 1);
   constexpr uint32_t TCOLS_PER = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  constexpr int A_PER = WBM * 8 / 128, W_PER = BN * 8 / 128;
+  constexpr int A_PER = WBM * 8 / NPROD, W_PER = BN * 8 / NPROD;
+  constexpr int PW = NPROD / 32;  // producer warps
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_full[NSTAGE], s_empty[NSTAGE], s_accf[2], s_acce[2];
   __shared__ uint32_t s_tmem;
@@ -43,12 +52,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
   if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 2 * TCOLS_PER);
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(smem_u32(&s_full[i]), 128);
+      mbar_init(smem_u32(&s_full[i]), NPROD);
       mbar_init(smem_u32(&s_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s_accf[i]), 1);
-      mbar_init(smem_u32(&s_acce[i]), 128);
+      mbar_init(smem_u32(&s_acce[i]), EPW * 32);
     }
     fence_mbar_init();
   }
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
     n0 = (r % tiles_n) * BN;
   };
 
-  if (warp < 4 && ASYNC) {
+  if (warp < PW && ASYNC) {
     // ============ producers, pre-rounded operands: cp.async straight into the swizzled ring, NSTAGE k-blocks in flight ============
     int t = blockIdx.x, kb = 0;
     uint32_t it = 0;
@@ -82,7 +91,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       const int k0 = kb * WBK;
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
-        int q = tid + i * 128;
+        int q = tid + i * NPROD;
         int r = q >> 3, c = q & 7;
         int m = m0 + r;
         m = m < g.M ? m : g.M - 1;
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       }
 #pragma unroll
       for (int i = 0; i < W_PER; ++i) {
-        int q = tid + i * 128;
+        int q = tid + i * NPROD;
         int r = q >> 3, c = q & 7;
         cp_async16(sW + sw128_off(r, c), W + (int64_t)(n0 + r) * g.ldw + k0 + c * 4);
       }
@@ -102,7 +111,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       ++it;
     }
     cp_async_wait<0>();
-  } else if (warp < 4) {
+  } else if (warp < PW) {
     // =============================== producers ===============================
     float4 ra[A_PER], rw[W_PER];
     auto fetch = [&](int t, int kb) {
@@ -113,7 +122,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       const int k0 = kb * WBK;
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
-        int q = tid + i * 128;
+        int q = tid + i * NPROD;
         int r = q >> 3, c = q & 7;
         int m = m0 + r;
         m = m < g.M ? m : g.M - 1;
@@ -121,7 +130,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       }
 #pragma unroll
       for (int i = 0; i < W_PER; ++i) {
-        int q = tid + i * 128;
+        int q = tid + i * NPROD;
         int r = q >> 3, c = q & 7;
         rw[i] = *reinterpret_cast<const float4*>(W + (int64_t)(n0 + r) * g.ldw + k0 + c * 4);
       }
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       const uint32_t sA = base + s * STAGE, sW = sA + W_A_STAGE;
 #pragma unroll
       for (int i = 0; i < A_PER; ++i) {
-        int q = tid + i * 128;
+        int q = tid + i * NPROD;
         uint32_t off = sw128_off(q >> 3, q & 7);
         float4 hi = rna_tf32(ra[i]);
         st_shared_v4(sA + off, hi);
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       }
 #pragma unroll
       for (int i = 0; i < W_PER; ++i) {
-        int q = tid + i * 128;
+        int q = tid + i * NPROD;
         uint32_t off = sw128_off(q >> 3, q & 7);
         float4 hi = rna_tf32(rw[i]);
         st_shared_v4(sW + off, hi);
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       mbar_arrive(smem_u32(&s_full[s]));
       ++it;
     }
-  } else if (warp == 8) {
+  } else if (warp == PW + NEPI / 32) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(WBM, BN);
@@ -194,10 +203,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
         umma_commit(smem_u32(&s_accf[b]));
       }
     }
-  } else {
+  } else if (warp - PW < EPW) {
     // =============================== epilogue ===============================
-    const int q4 = warp - 4;  // TMEM lane quarter == warp % 4
-    float* stg = reinterpret_cast<float*>(base_ptr + NSTAGE * STAGE) + q4 * 32 * WSTG;
+    const int ew = warp - PW;           // 0..EPW-1
+    const int q4 = ew & 3;              // TMEM lane quarter == warp % 4 (PW is a multiple of 4)
+    const int chalf = ew >> 2;          // which half of the tile's columns this warp drains
+    float* stg = reinterpret_cast<float*>(base_ptr + NSTAGE * STAGE) + ew * 32 * WSTG;
     uint32_t ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
       int m0, n0, z;
@@ -209,8 +220,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
       const int row = m0 + q4 * 32 + lane;
       const float rbias = (g.bias_mode == 2 && row < g.M) ? g.bias[row] : 0.0f;
       const uint32_t tl = tmem + b * TCOLS_PER + ((uint32_t)(q4 * 32) << 16);
+      constexpr int CH = BN / 32;  // 32-column chunks; chunk i goes to the warp pair member (i * 2 / CH)
+      const int ci0 = (EPW == 8) ? chalf * ((CH + 1) / 2) : 0;
+      const int ci1 = (EPW == 8 && chalf == 0) ? (CH + 1) / 2 : CH;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int ci = ci0; ci < ci1; ++ci) {
+        const int c0 = ci * 32;
         uint32_t v[32];
         tmem_ld32(tl + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -251,8 +266,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
 
 template <int BN, bool SPLIT, bool ASYNC>
 int launch_ws2(const GemmArgs& g, cudaStream_t st) {
-  constexpr int nstage = SPLIT ? 2 : (ASYNC ? 4 : 3);
-  constexpr int smem = nstage * (W_A_STAGE + BN * 128) * (SPLIT ? 2 : 1) + 4 * 32 * WSTG * 4 + 1024;
+  constexpr int nstage = ws_nstage(BN, SPLIT, ASYNC);
+  constexpr int smem = nstage * (W_A_STAGE + BN * 128) * (SPLIT ? 2 : 1) + ws_epi_warps(BN, SPLIT) * 32 * WSTG * 4 + 1024;
   static_assert(smem <= 227 * 1024 - 8 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {

@@ -358,3 +358,23 @@ def test_train_mode_forward_vs_reference_golden(mode):
         _, x0 = m(x, g2["mask"], t2.cuda(), g2["given_objs"], g2["given_cats"], g2["text_emb"])
     assert rel_l2(x0.cpu(), x0o) < TOL_E2E
     assert rel_l2(x.cpu(), xo) < TOL_E2E
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_odd_batch_sizes_vs_oracle(B, mode):
+    """run/test_sdm.py samples with batch 1 and run/train_sdm.py with batch 6: no tile-size assumption on B."""
+    sd = syn.make_state_dict(0, "wellcond")
+    inp = syn.make_inputs(50 + B, B)
+    fps, noise = syn.make_step_randoms(60 + B, B, 1)
+    tables = O.diffusion_tables(O.cosine_betas(1000))
+    t = torch.full((B,), 17, dtype=torch.long)
+    xo = inp["x_T"].clone()
+    ref = O.p_sample(sd, tables, xo, inp["mask"], t, inp["given_objs"], inp["given_cats"], inp["text_emb"], list(fps[0]), noise[0])
+    m, diff = _model("wellcond")
+    g = _cuda(inp)
+    x = g["x_T"].clone()
+    with injected_rng(fps_starts=list(fps[0]), noises=[noise[0]]):
+        out = diff.p_sample(m, x, g["mask"], t.cuda(), g["given_objs"], g["given_cats"], g["text_emb"], clip_denoised=False)
+    assert rel_l2(out["sample"].cpu(), ref["sample"]) < TOL_E2E
+    assert rel_l2(out["pred_xstart"].cpu(), ref["pred_xstart"]) < TOL_E2E
+    assert rel_l2(x.cpu(), xo) < TOL_E2E
