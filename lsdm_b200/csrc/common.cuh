@@ -48,9 +48,8 @@ __device__ __forceinline__ void epi_chunk_t(float (&f)[32], const uint32_t (&v)[
     if (cbias) x += cbias[j];
     x = apply_act<ACT>(x);
     if (ROUND) {
-      uint32_t r;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-      x = __uint_as_float(r);
+      // == cvt.rna.tf32.f32 for finite x (two integer ops instead of the FSETP + IADD + LOP3 the cvt expands to)
+      x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     }
     f[j] = x;
   }

@@ -109,18 +109,25 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
   };
   Pre cur = load_pts(t0, load_idx(t0));
   int j1 = load_idx(t0 + 1);
+  // the whole projected row P[j, 0:C1] of the NEXT tile is fetched into registers while this tile's MMAs and epilogues
+  // run (one CTA of 128 threads per SM leaves 255 registers per thread), so no L2 round trip sits on the tile's critical path
+  float4 prow[FIRST ? 1 : C1 / 4];
+  auto load_row = [&](int tile, int j) {
+    if (!FIRST && tile < t1) {
+      const int64_t c = (((int64_t)tile * 128 + tid) >> 5) / a.S;
+      const float4* p = reinterpret_cast<const float4*>(a.P + (c * a.N + j) * C1);
+#pragma unroll
+      for (int q = 0; q < C1 / 4; ++q) prow[q] = p[q];
+    }
+  };
+  load_row(t0, cur.j);
   for (int tile = t0; tile < t1; ++tile) {
     // ---------------- gather + first layer (CUDA cores, exact fp32 geometry) ----------------
     const Pre nxt = load_pts(tile + 1, j1);
     j1 = load_idx(tile + 2);
-    const int64_t row = (int64_t)tile * 128 + tid;
-    const int64_t cs = row >> 5;
-    const int64_t c = cs / a.S;
-    const int j = cur.j;
     const float jx = cur.jx, jy = cur.jy, jz = cur.jz;
     const float rx = jx - cur.cx, ry = jy - cur.cy, rz = jz - cur.cz;
-    const float* prow = FIRST ? nullptr : a.P + (c * a.N + j) * C1;
-#pragma unroll 1
+#pragma unroll
     for (int kb = 0; kb < KB2; ++kb) {
       uint32_t v[32];
 #pragma unroll
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
         if (FIRST) {
           p4 = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
-          p4 = *reinterpret_cast<const float4*>(prow + kb * 32 + q * 4);
+          p4 = prow[kb * 8 + q];
         }
         float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
             x = fmaf(s_wf[ch * 3 + 1], jy, x);
             x = fmaf(s_wf[ch * 3 + 2], jz, x);
           }
-          v[q * 4 + e] = __float_as_uint(rna_tf32(fmaxf(x, 0.0f)));
+          v[q * 4 + e] = rna_tf32_mma(fmaxf(x, 0.0f));
         }
       }
       if (A_TMEM) {
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
       }
     }
     if (A_TMEM) tmem_st_wait(); else fence_proxy_async();
+    load_row(tile + 1, nxt.j);
     tc_fence_before();
     __syncthreads();
     // ---------------- layer 2 on the tensor core ----------------
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 32; ++e)
-        v[e] = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(v[e]) + s_b2[kb * 32 + e], 0.0f)));
+        v[e] = rna_tf32_mma(fmaxf(__uint_as_float(v[e]) + s_b2[kb * 32 + e], 0.0f));
       if (A_TMEM) {
         tmem_st32(tlane + COL_D2 + kb * 32, v);  // in place: the accumulator columns become the next A operand
       } else {
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
         uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(x));
         if (lane == e) res = mx;
       }
-      orow[c0 + lane] = a.round_out ? rna_tf32(__uint_as_float(res)) : __uint_as_float(res);
+      orow[c0 + lane] = a.round_out ? rna_tf32_fin(__uint_as_float(res)) : __uint_as_float(res);
     }
     tc_fence_before();  // the next tile's MMAs overwrite D2/D3 only after every thread's loads above
     cur = nxt;
@@ -352,14 +360,21 @@ __global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(Sa
   };
   Pre cur = load_pts(t0, load_idx(t0));
   int j1 = load_idx(t0 + 1);
+  float4 prow[FIRST ? 1 : C1 / 4];  // projected row of the next tile, in flight during this tile's MMAs / epilogues
+  auto load_row = [&](int tile, int j) {
+    if (!FIRST && tile < t1) {
+      const int64_t c = (((int64_t)tile * 128 + tid) >> 5) / a.S;
+      const float4* p = reinterpret_cast<const float4*>(a.P + (c * a.N + j) * C1);
+#pragma unroll
+      for (int q = 0; q < C1 / 4; ++q) prow[q] = p[q];
+    }
+  };
+  load_row(t0, cur.j);
   for (int tile = t0; tile < t1; ++tile) {
     const Pre nxt = load_pts(tile + 1, j1);
     j1 = load_idx(tile + 2);
-    const int64_t cs = ((int64_t)tile * 128 + tid) >> 5;
-    const int64_t c = cs / a.S;
     const float jx = cur.jx, jy = cur.jy, jz = cur.jz;
     const float rx = jx - cur.cx, ry = jy - cur.cy, rz = jz - cur.cz;
-    const float* prow = FIRST ? nullptr : a.P + (c * a.N + cur.j) * C1;
     // ---- gather + first layer: thread = grouped row, constant-bank weights ----
 #pragma unroll
     for (int kb = 0; kb < KB2; ++kb) {
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(Sa
       for (int q = 0; q < 8; ++q) {
         float pv[4] = {0.f, 0.f, 0.f, 0.f};
         if (!FIRST) {
-          float4 p4 = *reinterpret_cast<const float4*>(prow + kb * 32 + q * 4);
+          const float4 p4 = prow[FIRST ? 0 : kb * 8 + q];
           pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
         }
 #pragma unroll
@@ -383,12 +398,13 @@ __global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(Sa
             x = fmaf(k.wf[FIRST ? ch * 3 + 1 : 0], jy, x);
             x = fmaf(k.wf[FIRST ? ch * 3 + 2 : 0], jz, x);
           }
-          v[q * 4 + e] = __float_as_uint(rna_tf32(fmaxf(x, 0.0f)));
+          v[q * 4 + e] = rna_tf32_mma(fmaxf(x, 0.0f));
         }
       }
       tmem_st32(tlane + COL_H1 + kb * 32, v);
     }
     tmem_st_wait();
+    load_row(tile + 1, nxt.j);
     tc_fence_before();
     __syncthreads();
     // ---- layer 2: D2[point, ch] = h1 . W2^T (A from TMEM) ----
@@ -415,10 +431,10 @@ __global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(Sa
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float4 o;
-        o.x = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 0]) + k.b2[kb * 32 + q * 4 + 0], 0.0f));
-        o.y = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 1]) + k.b2[kb * 32 + q * 4 + 1], 0.0f));
-        o.z = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 2]) + k.b2[kb * 32 + q * 4 + 2], 0.0f));
-        o.w = rna_tf32(fmaxf(__uint_as_float(v[q * 4 + 3]) + k.b2[kb * 32 + q * 4 + 3], 0.0f));
+        o.x = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 0]) + k.b2[kb * 32 + q * 4 + 0], 0.0f)));
+        o.y = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 1]) + k.b2[kb * 32 + q * 4 + 1], 0.0f)));
+        o.z = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 2]) + k.b2[kb * 32 + q * 4 + 2], 0.0f)));
+        o.w = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 3]) + k.b2[kb * 32 + q * 4 + 3], 0.0f)));
         st_shared_v4(sH2 + kb * (128 * 128) + sw128_off(tid, q), o);
       }
     }
@@ -451,7 +467,7 @@ __global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(Sa
 #pragma unroll
         for (int e = 1; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
         const float r = fmaxf(m + bias3, 0.0f);
-        a.out[((int64_t)tile * 4 + g) * C3 + tid] = a.round_out ? rna_tf32(r) : r;
+        a.out[((int64_t)tile * 4 + g) * C3 + tid] = a.round_out ? rna_tf32_fin(r) : r;
       }
     }
     tc_fence_before();
@@ -599,10 +615,10 @@ __global__ void __launch_bounds__(128, 1) fp1_tail_kernel(const float* __restric
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         float4 p = *reinterpret_cast<const float4*>(src + kb * 32 + q * 4);
-        v[q * 4 + 0] = __float_as_uint(rna_tf32(p.x));
-        v[q * 4 + 1] = __float_as_uint(rna_tf32(p.y));
-        v[q * 4 + 2] = __float_as_uint(rna_tf32(p.z));
-        v[q * 4 + 3] = __float_as_uint(rna_tf32(p.w));
+        v[q * 4 + 0] = rna_tf32_mma(p.x);
+        v[q * 4 + 1] = rna_tf32_mma(p.y);
+        v[q * 4 + 2] = rna_tf32_mma(p.z);
+        v[q * 4 + 3] = rna_tf32_mma(p.w);
       }
       tmem_st32(tlane + kb * 32, v);
     }
@@ -617,7 +633,7 @@ __global__ void __launch_bounds__(128, 1) fp1_tail_kernel(const float* __restric
       tmem_ld32(tlane + 128 + kb * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(v[e]) + k.b2[kb * 32 + e], 0.0f)));
+      for (int e = 0; e < 32; ++e) v[e] = rna_tf32_mma(fmaxf(__uint_as_float(v[e]) + k.b2[kb * 32 + e], 0.0f));
       tmem_st32(tlane + 128 + kb * 32, v);
     }
     tmem_st_wait();
@@ -630,7 +646,7 @@ __global__ void __launch_bounds__(128, 1) fp1_tail_kernel(const float* __restric
       tmem_ld32(tlane + kb * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(v[e]) + k.b3[kb * 32 + e], 0.0f)));
+      for (int e = 0; e < 32; ++e) v[e] = rna_tf32_mma(fmaxf(__uint_as_float(v[e]) + k.b3[kb * 32 + e], 0.0f));
       tmem_st32(tlane + kb * 32, v);
     }
     tmem_st_wait();

@@ -68,6 +68,11 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 __device__ __forceinline__ float4 rna_tf32(float4 v) { return make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w)); }
+// Cheaper forms for FINITE inputs (cvt.rna compiles to FSETP + predicated IADD + LOP3):
+//  * rna_tf32_fin : add half a TF32 ulp to the magnitude bits, clear the low 13 bits -> bit-identical to cvt.rna
+//  * rna_tf32_mma : the add alone; for operands that only a TF32 MMA reads (it ignores the low 13 mantissa bits)
+__device__ __forceinline__ float rna_tf32_fin(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ uint32_t rna_tf32_mma(float x) { return __float_as_uint(x) + 0x1000u; }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
