@@ -75,6 +75,7 @@ struct Workspace {
   float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out[2];  // pcd_out: one per selection set (the step of k reads it while dense(k+1) writes the other)
   // step
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
+  float *H1_lo, *H2_lo, *embpre_lo, *cat_lo, *h1_lo, *c1_lo, *c2_lo;  // 3xTF32 residual planes of the step network's activations
   size_t bytes;
 };
 
@@ -87,6 +88,7 @@ struct lsdm_handle {
   float* arena = nullptr;    // raw state-dict tensors
   float* derived = nullptr;  // folded / split tensors
   int64_t round_delta = 0;   // float offset from a weight in (arena|derived) to its TF32-rounded copy (tensor path)
+  int64_t lo_delta = 0;      // ... and to its 3xTF32 residual plane rna(w - rna(w))
   int64_t arena_floats = 0, derived_floats = 0;
   bool finalized = false, have_sched = false, have_cond = false;
   // folded weights
@@ -271,12 +273,19 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   const size_t rows = B * NPTS;
   w->s256 = a.take<float>(B * 256);
   w->H1 = a.take<float>(B * 256 * 128);
+  w->H1_lo = a.take<float>(B * 256 * 128);
   w->H2 = a.take<float>(B * 256 * 512);
+  w->H2_lo = a.take<float>(B * 256 * 512);
   w->embpre = a.take<float>(rows * 256);
+  w->embpre_lo = a.take<float>(rows * 256);
   w->cat = a.take<float>(2 * rows * 256);
+  w->cat_lo = a.take<float>(2 * rows * 256);
   w->h1 = a.take<float>(2 * rows * 64);
+  w->h1_lo = a.take<float>(2 * rows * 64);
   w->c1 = a.take<float>(2 * rows * 192);
+  w->c1_lo = a.take<float>(2 * rows * 192);
   w->c2 = a.take<float>(2 * rows * 128);
+  w->c2_lo = a.take<float>(2 * rows * 128);
   w->f1 = a.take<float>(2 * rows * 64);
   w->x0 = a.take<float>(rows * 3);
   w->guiding = a.take<float>(rows * 3);
@@ -314,7 +323,8 @@ extern "C" LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream);
 enum GemmFlags { GF_A_ROUNDED = 1, GF_ROUND_OUT = 2 };
 
 int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const float* W, int64_t ldw, float* C,
-         int64_t ldc, const float* bias, int M, int N, int K, int act, int group_max = 0, int prec = -1, int flags = 0) {
+         int64_t ldc, const float* bias, int M, int N, int K, int act, int group_max = 0, int prec = -1, int flags = 0,
+         const float* A_lo = nullptr, float* C_lo = nullptr) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.strideA = 0;
   g.W = W; g.ldw = ldw; g.strideW = 0;
@@ -329,6 +339,12 @@ int gemm(lsdm_handle* h, cudaStream_t st, const float* A, int64_t lda, const flo
       g.W = W + h->round_delta;
       g.w_rounded = 1;
     }
+  }
+  if (g.precision == 2 && A_lo != nullptr) {  // pre-split activations (hi = A, lo = A_lo) x pre-split weights, all fed by cp.async
+    g.A_lo = A_lo;
+    g.W = W + h->round_delta;
+    g.W_lo = W + h->lo_delta;
+    g.C_lo = C_lo;
   }
   char tag[64];
   snprintf(tag, sizeof(tag), "gemm p%d N%d K%d%s", g.precision, N, K, group_max ? " gmax" : "");
@@ -471,12 +487,16 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   const int B = h->cfg.batch_local;
   const int rows = B * NPTS;
   if (t != w.t_dev) CK(cudaMemcpyAsync(w.t_dev, t, sizeof(int64_t) * B, cudaMemcpyDefault, st));
+  // 3xTF32 step network with pre-split planes: every activation of the chain is stored as hi + lo by its producer, so the
+  // GEMMs stage all four operand planes with cp.async (no per-tile splitting in registers)
+  const bool sp = h->precision_step == 2 && g_gemm_async != 0;
+  const int ps = h->precision_step;
   prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
                                    h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
                                    h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.sel[si].enc, h->W("upsampling_layer.0.weight"),
-                                   h->W("upsampling_layer.0.bias"), B, w.s256, w.H1, st); });
+                                   h->W("upsampling_layer.0.bias"), B, w.s256, w.H1, sp ? w.H1_lo : nullptr, st); });
   GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), B * 256, 512,
-          128, ACT_GELU, 0, h->precision_step));
+          128, ACT_GELU, 0, ps, 0, sp ? w.H1_lo : nullptr, sp ? w.H2_lo : nullptr));
   {
     // embpre[b][p][s] = gelu(sum_k U4[p][k] H2[b][s][k] + b4[p]): the upsampler's last layer written point-major
     GemmArgs g{};
@@ -484,31 +504,42 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
     g.W = w.H2; g.ldw = 512; g.strideW = 256 * 512;
     g.C = w.embpre; g.ldc = 256; g.strideC = (int64_t)NPTS * 256;
     g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
-    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0; g.precision = h->precision_step;
+    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0; g.precision = ps;
+    if (sp) {
+      g.A_lo = g.A + h->lo_delta;
+      g.A = g.A + h->round_delta;
+      g.W_lo = w.H2_lo;
+      g.C_lo = w.embpre_lo;
+    }
     int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); }, "gemm p2 upsampler N256 K512 batched",
                         2.0 * g.M * (double)g.N * g.K * g.batch);
     if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
     if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
   }
   GE(gemm(h, st, w.embpre, 256, h->W("combine_extraction.0.weight"), 256, w.cat + 128, 256,
-          h->W("combine_extraction.0.bias"), rows, 128, 256, ACT_GELU, 0, h->precision_step));
+          h->W("combine_extraction.0.bias"), rows, 128, 256, ACT_GELU, 0, ps, 0, sp ? w.embpre_lo : nullptr, sp ? w.cat_lo + 128 : nullptr));
   const int M = want_guiding ? 2 * rows : rows;
-  if (want_guiding)
+  if (want_guiding) {
     CK(cudaMemcpy2DAsync(w.cat + (size_t)rows * 256 + 128, 256 * sizeof(float), w.cat + 128, 256 * sizeof(float),
                          128 * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+    if (sp)
+      CK(cudaMemcpy2DAsync(w.cat_lo + (size_t)rows * 256 + 128, 256 * sizeof(float), w.cat_lo + 128, 256 * sizeof(float),
+                           128 * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+  }
   prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(x, w.pcd_out[si], h->W("input_process.pose_embedding.0.weight"),
-                                    h->W("input_process.pose_embedding.0.bias"), rows, w.h1, st); });
+                                    h->W("input_process.pose_embedding.0.bias"), rows, w.h1, sp ? w.h1_lo : nullptr, st); });
   if (want_guiding)
     prof_launch(h, st, K_DENOISE, [&] { return launch_pose_embed0(w.pcd_out[si], nullptr, h->W("input_process.pose_embedding.0.weight"),
-                                      h->W("input_process.pose_embedding.0.bias"), rows, w.h1 + (size_t)rows * 64, st); });
+                                      h->W("input_process.pose_embedding.0.bias"), rows, w.h1 + (size_t)rows * 64,
+                                      sp ? w.h1_lo + (size_t)rows * 64 : nullptr, st); });
   GE(gemm(h, st, w.h1, 64, h->W("input_process.pose_embedding.2.weight"), 64, w.cat, 256,
-          h->W("input_process.pose_embedding.2.bias"), M, 128, 64, ACT_SIGMOID, 0, h->precision_step));
+          h->W("input_process.pose_embedding.2.bias"), M, 128, 64, ACT_SIGMOID, 0, ps, 0, sp ? w.h1_lo : nullptr, sp ? w.cat_lo : nullptr));
   GE(gemm(h, st, w.cat, 256, h->W("input_process.combination_extraction.0.weight"), 256, w.c1, 192,
-          h->W("input_process.combination_extraction.0.bias"), M, 192, 256, ACT_SIGMOID, 0, h->precision_step));
+          h->W("input_process.combination_extraction.0.bias"), M, 192, 256, ACT_SIGMOID, 0, ps, 0, sp ? w.cat_lo : nullptr, sp ? w.c1_lo : nullptr));
   GE(gemm(h, st, w.c1, 192, h->W("input_process.combination_extraction.2.weight"), 192, w.c2, 128,
-          h->W("input_process.combination_extraction.2.bias"), M, 128, 192, ACT_SIGMOID, 0, h->precision_step));
+          h->W("input_process.combination_extraction.2.bias"), M, 128, 192, ACT_SIGMOID, 0, ps, 0, sp ? w.c1_lo : nullptr, sp ? w.c2_lo : nullptr));
   GE(gemm(h, st, w.c2, 128, h->W("output_process.pose_final.0.weight"), 128, w.f1, 64,
-          h->W("output_process.pose_final.0.bias"), M, 64, 128, ACT_GELU, 0, h->precision_step));
+          h->W("output_process.pose_final.0.bias"), M, 64, 128, ACT_GELU, 0, ps, 0, sp ? w.c2_lo : nullptr, nullptr));
   float* x0 = x0_out ? x0_out : w.x0;
   prof_launch(h, st, K_DENOISE, [&] { return launch_final3(w.f1, h->W("output_process.pose_final.2.weight"), h->W("output_process.pose_final.2.bias"), rows,
                                x0, x, w.t_dev, h->sched, h->sched ? h->sched + h->T : nullptr, h->sched ? h->sched + 2 * h->T : nullptr, noise,
@@ -523,13 +554,21 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   return LSDM_OK;
 }
 
-__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dst_lo, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
+    uint32_t r, l;
+    const float x = src[i];
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     dst[i] = __uint_as_float(r);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - __uint_as_float(r)));
+    dst_lo[i] = __uint_as_float(l);
   }
+}
+
+__global__ void add_planes_kernel(const float* __restrict__ hi, const float* __restrict__ lo, float* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = hi[i] + lo[i];
 }
 
 __global__ void fill_t_kernel(int64_t* t, int n, int64_t v) {
@@ -556,8 +595,9 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
   build_registry(h);
   // derived (folded) weights: generous upper bound = all backbone conv weights + biases again
   h->derived_floats = 2700000;
-  cudaError_t e = cudaMalloc(&h->arena, sizeof(float) * 2 * (h->arena_floats + h->derived_floats));
+  cudaError_t e = cudaMalloc(&h->arena, sizeof(float) * 3 * (h->arena_floats + h->derived_floats));
   h->round_delta = h->arena_floats + h->derived_floats;
+  h->lo_delta = 2 * h->round_delta;
   if (e != cudaSuccess) {
     delete h;
     return fail(LSDM_ENOMEM, std::string("cudaMalloc weights: ") + cudaGetErrorString(e));
@@ -700,7 +740,7 @@ LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
   // TF32-rounded (round-to-nearest) copy of every weight: the cp.async-fed tensor GEMM reads operands without touching them
   prof_launch(h, st, K_OTHER, [&] {
     int64_t n = h->round_delta;
-    round_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->arena, h->arena + h->round_delta, n);
+    round_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->arena, h->arena + h->round_delta, h->arena + h->lo_delta, n);
     return 1;
   });
   // host copies of the small per-channel vectors of sa1 / sa2 (kernel parameters of the v2 fused kernels)
@@ -1043,6 +1083,10 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
       size_t bytes = (size_t)t.count * t.esz;
       if (dst) {
         if (dst_bytes < bytes) return fail(LSDM_EINVAL, "destination too small");
+        if (t.p == (const void*)w.cat && h->precision_step == 2 && g_gemm_async) {  // stored as hi + lo planes
+          add_planes_kernel<<<(unsigned)((t.count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w.cat, w.cat_lo, (float*)dst, t.count);
+          return t.count;
+        }
         cudaError_t e = cudaMemcpyAsync(dst, t.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
         if (e != cudaSuccess) return fail(LSDM_ECUDA, cudaGetErrorString(e));
       }

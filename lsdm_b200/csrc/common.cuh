@@ -38,6 +38,13 @@ __device__ __forceinline__ float apply_act_rt(float x, int act) {
   }
 }
 
+// x == hi + lo (to ~2^-22 relative): hi = x rounded to nearest TF32, lo = the residual rounded to TF32 (finite inputs)
+__device__ __forceinline__ float tf32_round_fin(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = tf32_round_fin(x);
+  lo = tf32_round_fin(x - hi);
+}
+
 // Epilogue transform of one 32-column accumulator chunk: f = [round_tf32](act(v + row_bias + col_bias)).
 // The activation / rounding selectors are resolved ONCE per chunk (switch outside the unrolled element loop).
 template <int ACT, bool ROUND>

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
                                                          const float* __restrict__ b2, const int64_t* __restrict__ t,
                                                          const float* __restrict__ enc, const float* __restrict__ up0_w,
                                                          const float* __restrict__ up0_b, float* __restrict__ s256,
-                                                         float* __restrict__ H1) {
+                                                         float* __restrict__ H1, float* __restrict__ H1_lo) {
   __shared__ float s_pe[LAT], s_h[LAT], s_s[2 * LAT];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int64_t tt = t[b];
@@ -141,7 +141,16 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
   for (int i = tid; i < 2 * LAT; i += blockDim.x) s256[(int64_t)b * 2 * LAT + i] = s_s[i];
   for (int i = tid; i < 2 * LAT * 128; i += blockDim.x) {
     int s = i >> 7, j = i & 127;
-    H1[((int64_t)b * 2 * LAT + s) * 128 + j] = gelu_erf(fmaf(s_s[s], up0_w[j], up0_b[j]));
+    const float v = gelu_erf(fmaf(s_s[s], up0_w[j], up0_b[j]));
+    const int64_t o = ((int64_t)b * 2 * LAT + s) * 128 + j;
+    if (H1_lo != nullptr) {  // consumer is a pre-split 3xTF32 GEMM
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      H1[o] = hi;
+      H1_lo[o] = lo;
+    } else {
+      H1[o] = v;
+    }
   }
 }
 
@@ -307,8 +316,8 @@ int launch_cond(const CondWeights& w, const float* text, const float* cats, cons
 
 int launch_time_embed(const float* pe, const float* w1, const float* b1, const float* w2, const float* b2,
                       const int64_t* t, const float* enc, const float* up0_w, const float* up0_b, int B, float* s256,
-                      float* H1, cudaStream_t st) {
-  time_embed_kernel<<<B, 256, 0, st>>>(pe, w1, b1, w2, b2, t, enc, up0_w, up0_b, s256, H1);
+                      float* H1, float* H1_lo, cudaStream_t st) {
+  time_embed_kernel<<<B, 256, 0, st>>>(pe, w1, b1, w2, b2, t, enc, up0_w, up0_b, s256, H1, H1_lo);
   return 1;
 }
 

@@ -11,7 +11,7 @@ namespace {
 // one thread per (row, 4 output channels): 16 threads per row.
 __global__ void __launch_bounds__(256) pose_embed0_kernel(float* __restrict__ x, const float* __restrict__ add,
                                                           const float* __restrict__ w, const float* __restrict__ b,
-                                                          int64_t rows, float* __restrict__ h1) {
+                                                          int64_t rows, float* __restrict__ h1, float* __restrict__ h1_lo) {
   __shared__ float sw[64 * 3], sb[64];
   for (int i = threadIdx.x; i < 192; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
@@ -44,6 +44,12 @@ __global__ void __launch_bounds__(256) pose_embed0_kernel(float* __restrict__ x,
     int ch = q * 4 + j;
     float v = fmaf(sw[ch * 3 + 2], vz, fmaf(sw[ch * 3 + 1], vy, fmaf(sw[ch * 3], vx, sb[ch])));
     o[j] = sigmoidf_(v);
+  }
+  if (h1_lo != nullptr) {  // consumer is a pre-split 3xTF32 GEMM: store hi and lo planes
+    float l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_tf32(o[j], o[j], l[j]);
+    *reinterpret_cast<float4*>(h1_lo + row * 64 + q * 4) = make_float4(l[0], l[1], l[2], l[3]);
   }
   *reinterpret_cast<float4*>(h1 + row * 64 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
@@ -96,10 +102,10 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const int64_t* __r
 
 }  // namespace
 
-int launch_pose_embed0(float* x, const float* add, const float* w, const float* b, int64_t rows, float* h1,
+int launch_pose_embed0(float* x, const float* add, const float* w, const float* b, int64_t rows, float* h1, float* h1_lo,
                        cudaStream_t st) {
   int64_t n = rows * 16;
-  pose_embed0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, add, w, b, rows, h1);
+  pose_embed0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, add, w, b, rows, h1, h1_lo);
   return 1;
 }
 

@@ -24,6 +24,12 @@ struct GemmArgs {
   int a_rounded;  // A already holds TF32-representable values (its producer rounded them)  } both set: operands can be
   int w_rounded;  // W points at the TF32-rounded weight copy made at finalize                } staged by cp.async, no registers
   int round_out;  // epilogue rounds C to TF32 (round-to-nearest) because C feeds another tensor-core GEMM
+  // 3xTF32 with PRE-SPLIT operands (precision 2): x == hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi).  When both
+  // A_lo and W_lo are given, A / W point at the hi planes and all four planes are staged by cp.async (same strides);
+  // when C_lo is given the epilogue writes the result as a hi plane (C) and a lo plane (C_lo) for the next GEMM.
+  const float* A_lo;
+  const float* W_lo;
+  float* C_lo;
 };
 
 // Launches the GEMM on `stream`; returns the number of kernels launched (1) or a negative value on bad arguments.

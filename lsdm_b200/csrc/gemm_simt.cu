@@ -172,8 +172,9 @@ int g_gemm_async = 1;
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.precision >= 1 && gemm_tc_eligible(g)) {
-    const bool async_ok = g.precision == 1 && g.a_rounded && g.w_rounded && g_gemm_async && g.N <= 1024;
-    return (g_gemm_ws || async_ok) ? launch_gemm_ws(g, stream) : launch_gemm_tc(g, stream);
+    const bool async_ok = g_gemm_async && g.N <= 1024 &&
+                          ((g.precision == 1 && g.a_rounded && g.w_rounded) || (g.precision == 2 && g.A_lo && g.W_lo));
+    return (g_gemm_ws || async_ok || g.C_lo != nullptr) ? launch_gemm_ws(g, stream) : launch_gemm_tc(g, stream);
   }
   return launch_gemm_simt(g, stream);
 }

@@ -27,7 +27,9 @@ constexpr int WSTG = 36;              // epilogue transpose row stride (floats)
 
 // shared-memory plan: the (SPLIT, BN=256) ring is 2 x 96 KB, which leaves room for only four staging buffers
 __host__ __device__ constexpr int ws_epi_warps(int bn, bool split) { return (split && bn == 256) ? 4 : 8; }
-__host__ __device__ constexpr int ws_nstage(int bn, bool split, bool async) { return split ? 2 : ((async && bn < 256) ? 4 : 3); }
+__host__ __device__ constexpr int ws_nstage(int bn, bool split, bool async) {
+  return split ? (async ? (bn <= 32 ? 4 : (bn <= 64 ? 3 : 2)) : 2) : ((async && bn < 256) ? 4 : 3);
+}
 
 template <int BN, bool SPLIT, bool ASYNC>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int tiles_m, int tiles_n, int total_tiles) {
@@ -95,13 +97,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
         int r = q >> 3, c = q & 7;
         int m = m0 + r;
         m = m < g.M ? m : g.M - 1;
-        cp_async16(sA + sw128_off(r, c), A + (int64_t)m * g.lda + k0 + c * 4);
+        const int64_t go = (int64_t)m * g.lda + k0 + c * 4;
+        const uint32_t so = sw128_off(r, c);
+        cp_async16(sA + so, A + go);
+        if (SPLIT) cp_async16(sA + HALF + so, g.A_lo + (int64_t)z * g.strideA + go);
       }
 #pragma unroll
       for (int i = 0; i < W_PER; ++i) {
         int q = tid + i * NPROD;
         int r = q >> 3, c = q & 7;
-        cp_async16(sW + sw128_off(r, c), W + (int64_t)(n0 + r) * g.ldw + k0 + c * 4);
+        const int64_t go = (int64_t)(n0 + r) * g.ldw + k0 + c * 4;
+        const uint32_t so = sw128_off(r, c);
+        cp_async16(sW + so, W + go);
+        if (SPLIT) cp_async16(sW + HALF + so, g.W_lo + (int64_t)z * g.strideW + go);
       }
       cp_async_mbar_arrive(smem_u32(&s_full[s]));
       if (++kb == nkb) {
@@ -231,7 +239,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
         tmem_ld_wait();
         float f[32];
         epi_chunk(f, v, rbias, g.bias_mode == 1 ? &s_bias[n0 + c0] : nullptr, g.act, g.round_out);
-        if (g.group_max) {
+        if (SPLIT && g.C_lo != nullptr) {
+          // the consumer is another 3xTF32 GEMM: store x as its hi and lo planes (two passes through the staging tile)
+          float* __restrict__ Cl = g.C_lo + (int64_t)z * g.strideC;
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float hi = tf32_round_fin(f[4 * q + e]);
+                o[e] = pass == 0 ? hi : tf32_round_fin(f[4 * q + e] - hi);
+              }
+              *reinterpret_cast<float4*>(stg + lane * WSTG + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+            float* __restrict__ dst = pass == 0 ? C : Cl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              int r = 4 * j + (lane >> 3), q = lane & 7;
+              float4 val = *reinterpret_cast<const float4*>(stg + r * WSTG + q * 4);
+              int m = m0 + q4 * 32 + r;
+              if (m < g.M) *reinterpret_cast<float4*>(dst + (int64_t)m * g.ldc + n0 + c0 + q * 4) = val;
+            }
+            __syncwarp();
+          }
+        } else if (g.group_max) {
           uint32_t res = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -290,7 +324,10 @@ int launch_ws2(const GemmArgs& g, cudaStream_t st) {
 }
 template <int BN>
 int launch_ws(const GemmArgs& g, cudaStream_t st) {
-  if (g.precision >= 2) return launch_ws2<BN, true, false>(g, st);
+  if (g.precision >= 2) {
+    if (g.A_lo && g.W_lo && g_gemm_async) return launch_ws2<BN, true, true>(g, st);
+    return launch_ws2<BN, true, false>(g, st);
+  }
   if (g.a_rounded && g.w_rounded && g_gemm_async) return launch_ws2<BN, false, true>(g, st);
   return launch_ws2<BN, false, false>(g, st);
 }

@@ -68,7 +68,7 @@ int launch_cond(const CondWeights& w, const float* text, const float* cats, cons
 // ts[B,128] = W2 silu(W1 pe[t] + b1) + b2 ; also writes s[B,256] = [ts || enc] and H1[B*256,128] = gelu(s*w0 + b0)
 int launch_time_embed(const float* pe, const float* w1, const float* b1, const float* w2, const float* b2,
                       const int64_t* t, const float* enc, const float* up0_w, const float* up0_b, int B, float* s256,
-                      float* H1, cudaStream_t st);
+                      float* H1, float* H1_lo /* nullable: 3xTF32 residual plane, H1 then holds the hi plane */, cudaStream_t st);
 struct HumanWeights {
   const float *w0, *b0, *g0, *be0;  // 3->64 + GroupNorm(8)
   const float *w1, *b1, *g1, *be1;  // 64->64
@@ -95,7 +95,7 @@ int launch_scene_mix(const float* pw, const float* hm, const float* mask_global,
 // ---- denoise.cu -----------------------------------------------------------------------------
 // xin = x (+ pcd_out, written back to x when add != nullptr); h1[row,64] = sigmoid(E0 xin + b)
 int launch_pose_embed0(float* x, const float* add, const float* w, const float* b, int64_t rows, float* h1,
-                       cudaStream_t st);
+                       float* h1_lo /* nullable, as above */, cudaStream_t st);
 // x0 = gelu(F2 f1 + b) (64->3); optional posterior + ancestral sample (gaussian_diffusion.py:266-269,545-560):
 // sample = c1[t] x0 + c2[t] xin + [t != 0] exp(0.5 logvar[t]) noise
 int launch_final3(const float* f1, const float* w, const float* b, int64_t rows, float* x0_out, const float* xin,
