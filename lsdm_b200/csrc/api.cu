@@ -428,7 +428,8 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       int r = prof_launch(h, st, K_GEMM, [&] {
         if (h->sa_fused == 3 && l <= 1)
           return launch_sa_fused_v2(l, P, xyz[l], xyz[l + 1], q.grp[l], h->host_wx[l].data(), h->host_wf[l].data(), h->host_b1[l].data(),
-                                    h->host_b2[l].data(), h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], h->precision == 1, st);
+                                    h->host_b2[l].data(), h->sa_wx[l], h->sa_b[l][0], h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1],
+                                    h->precision == 1, st);
         return launch_sa_fused(l, h->sa_fused >= 2, P, xyz[l], xyz[l + 1], q.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
                                h->sa_w[l][1], h->sa_b[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], h->precision == 1, st);
       }, l == 0 ? "sa_fused sa1" : (l == 1 ? "sa_fused sa2" : "sa_fused sa3"), 2.0 * C * S * 32 * ((double)C1 * C2 + (double)C2 * C3));

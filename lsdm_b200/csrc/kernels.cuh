@@ -38,8 +38,8 @@ int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, co
                     const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
 
 int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp, const float* h_wx,
-                       const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
-                       int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
+                       const float* h_wf, const float* h_b1, const float* h_b2, const float* d_wx, const float* d_b1, const float* W2,
+                       const float* W3, const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
 
 // fused tail of the backbone: fp1 layers 2-3 + conv1/bn1 head + conv2, TF32 tensor cores; h_consts is a HOST array
 // [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]

@@ -34,11 +34,17 @@ struct SaArgs {
   float* out;            // [C*S, C3]
   int n_tiles, N, S;
   int round_out;  // pooled features feed a tensor-core GEMM next: store them rounded to TF32
+  int s_shift;    // log2(S): S is a power of two at every level (1024 / 256 / 64)
 };
 
-template <int C1, int C2, int C3, bool FIRST, bool A_TMEM>
-__global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
+template <int C1, int C2, int C3, bool FIRST, bool A_TMEM, int NT>
+__global__ void __launch_bounds__(NT) sa_fused_kernel(SaArgs a) {
+  // NT = 128: thread == grouped row.  NT = 256: two warps per TMEM lane quarter, each thread handles HALF of its row's
+  // channels in the gather and in both epilogues (twice the issue parallelism for the wide level, whose single CTA per SM
+  // otherwise leaves one warp per scheduler)
+  constexpr int NH = NT / 128;
   constexpr int KB2 = C1 / 32, KB3 = C2 / 32;         // k-blocks of layer 2 / layer 3
+  static_assert(KB2 % NH == 0 && KB3 % NH == 0 && (C3 / 32) % NH == 0, "column split");
   constexpr int W2_BYTES = C2 * C1 * 4, W3_BYTES = C3 * C2 * 4;
   constexpr int H_BYTES = A_TMEM ? 0 : 128 * C1 * 4;  // h1 tile in smem (SS path)
   constexpr int H2_BYTES = A_TMEM ? 0 : 128 * C2 * 4;
@@ -52,6 +58,9 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
   __shared__ float s_wx[C1 * 3], s_wf[FIRST ? C1 * 3 : 1], s_b1[FIRST ? C1 : 1], s_b2[C2], s_b3[C3];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rit = tid & 127;      // row in tile == TMEM lane
+  const int wq = warp & 3;        // TMEM lane quarter of this warp
+  const int half = tid >> 7;      // which share of the channels (0 when NT == 128)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW2 = base, sW3 = sW2 + W2_BYTES, sH1 = sW3 + W3_BYTES, sH2 = sH1 + H_BYTES;
   const uint32_t bar = smem_u32(&s_bar);
@@ -62,30 +71,30 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
     fence_mbar_init();
   }
   // weights -> smem, K-major SW128 k-blocks [rows x 32 floats], rounded to TF32 (RNA) once
-  for (int q = tid; q < C2 * C1 / 4; q += 128) {
+  for (int q = tid; q < C2 * C1 / 4; q += NT) {
     int n = q / (C1 / 4), k4 = q % (C1 / 4);
     float4 v = *reinterpret_cast<const float4*>(a.W2 + (int64_t)n * C1 + k4 * 4);
     st_shared_v4(sW2 + (k4 >> 3) * (C2 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
   }
-  for (int q = tid; q < C3 * C2 / 4; q += 128) {
+  for (int q = tid; q < C3 * C2 / 4; q += NT) {
     int n = q / (C2 / 4), k4 = q % (C2 / 4);
     float4 v = *reinterpret_cast<const float4*>(a.W3 + (int64_t)n * C2 + k4 * 4);
     st_shared_v4(sW3 + (k4 >> 3) * (C3 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
   }
-  for (int i = tid; i < C1 * 3; i += 128) {
+  for (int i = tid; i < C1 * 3; i += NT) {
     s_wx[i] = a.Wx[i];
     if (FIRST) s_wf[i] = a.Wf3[i];
   }
   if (FIRST)
-    for (int i = tid; i < C1; i += 128) s_b1[i] = a.b1[i];
-  for (int i = tid; i < C2; i += 128) s_b2[i] = a.b2[i];
-  for (int i = tid; i < C3; i += 128) s_b3[i] = a.b3[i];
+    for (int i = tid; i < C1; i += NT) s_b1[i] = a.b1[i];
+  for (int i = tid; i < C2; i += NT) s_b2[i] = a.b2[i];
+  for (int i = tid; i < C3; i += NT) s_b3[i] = a.b3[i];
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's lane quarter
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);  // this warp's lane quarter
   constexpr uint32_t idesc2 = umma_idesc_tf32(128, C2), idesc3 = umma_idesc_tf32(128, C3);
   uint32_t phase = 0;
 
@@ -95,12 +104,12 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
   const int per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
   const int t0 = blockIdx.x * per, t1 = (t0 + per < a.n_tiles) ? t0 + per : a.n_tiles;
   struct Pre { int j; float jx, jy, jz, cx, cy, cz; };
-  auto load_idx = [&](int tile) -> int { return tile < t1 ? a.grp[(int64_t)tile * 128 + tid] : 0; };
+  auto load_idx = [&](int tile) -> int { return tile < t1 ? a.grp[(int64_t)tile * 128 + rit] : 0; };
   auto load_pts = [&](int tile, int j) -> Pre {
     Pre p{j, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (tile < t1) {
-      const int64_t cs = ((int64_t)tile * 128 + tid) >> 5;
-      const float* pj = a.xyz + ((cs / a.S) * a.N + j) * 3;
+      const int64_t cs = ((int64_t)tile * 128 + rit) >> 5;
+      const float* pj = a.xyz + ((cs >> a.s_shift) * a.N + j) * 3;
       const float* pc = a.new_xyz + cs * 3;
       p.jx = pj[0]; p.jy = pj[1]; p.jz = pj[2];
       p.cx = pc[0]; p.cy = pc[1]; p.cz = pc[2];
@@ -109,15 +118,16 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
   };
   Pre cur = load_pts(t0, load_idx(t0));
   int j1 = load_idx(t0 + 1);
-  // the whole projected row P[j, 0:C1] of the NEXT tile is fetched into registers while this tile's MMAs and epilogues
-  // run (one CTA of 128 threads per SM leaves 255 registers per thread), so no L2 round trip sits on the tile's critical path
-  float4 prow[FIRST ? 1 : C1 / 4];
+  // this thread's share of the projected row P[j, :] of the NEXT tile is fetched into registers while this tile's MMAs
+  // and epilogues run, so no L2 round trip sits on the tile's critical path
+  constexpr int PQ = C1 / 4 / NH;
+  float4 prow[FIRST ? 1 : PQ];
   auto load_row = [&](int tile, int j) {
     if (!FIRST && tile < t1) {
-      const int64_t c = (((int64_t)tile * 128 + tid) >> 5) / a.S;
-      const float4* p = reinterpret_cast<const float4*>(a.P + (c * a.N + j) * C1);
+      const int64_t c = (((int64_t)tile * 128 + rit) >> 5) >> a.s_shift;
+      const float4* p = reinterpret_cast<const float4*>(a.P + (c * a.N + j) * C1) + half * PQ;
 #pragma unroll
-      for (int q = 0; q < C1 / 4; ++q) prow[q] = p[q];
+      for (int q = 0; q < PQ; ++q) prow[q] = p[q];
     }
   };
   load_row(t0, cur.j);
@@ -128,7 +138,8 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
     const float jx = cur.jx, jy = cur.jy, jz = cur.jz;
     const float rx = jx - cur.cx, ry = jy - cur.cy, rz = jz - cur.cz;
 #pragma unroll
-    for (int kb = 0; kb < KB2; ++kb) {
+    for (int kl = 0; kl < KB2 / NH; ++kl) {
+      const int kb = half * (KB2 / NH) + kl;
       uint32_t v[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
         if (FIRST) {
           p4 = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
-          p4 = prow[kb * 8 + q];
+          p4 = prow[FIRST ? 0 : kl * 8 + q];
         }
         float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
       } else {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          st_shared_v4(sH1 + kb * (128 * 128) + sw128_off(tid, q),
+          st_shared_v4(sH1 + kb * (128 * 128) + sw128_off(rit, q),
                        make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
                                    __uint_as_float(v[q * 4 + 3])));
       }
@@ -191,7 +202,8 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
     tc_fence_after();
     // ---------------- epilogue 2: bias + ReLU + TF32 rounding -> A operand of layer 3 ----------------
 #pragma unroll 1
-    for (int kb = 0; kb < KB3; ++kb) {
+    for (int kl = 0; kl < KB3 / NH; ++kl) {
+      const int kb = half * (KB3 / NH) + kl;
       uint32_t v[32];
       tmem_ld32(tlane + COL_D2 + kb * 32, v);
       tmem_ld_wait();
@@ -203,7 +215,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
       } else {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          st_shared_v4(sH2 + kb * (128 * 128) + sw128_off(tid, q),
+          st_shared_v4(sH2 + kb * (128 * 128) + sw128_off(rit, q),
                        make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
                                    __uint_as_float(v[q * 4 + 3])));
       }
@@ -232,21 +244,24 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---------------- epilogue 3: bias + ReLU + max over the warp's 32 samples ----------------
-    float* orow = a.out + ((int64_t)tile * 4 + warp) * C3;
+    // ---------------- epilogue 3: bias, max over the warp's 32 samples, ReLU ----------------
+    float* orow = a.out + ((int64_t)tile * 4 + wq) * C3;
 #pragma unroll 1
-    for (int c0 = 0; c0 < C3; c0 += 32) {
+    for (int cl = 0; cl < C3 / 32 / NH; ++cl) {
+      const int c0 = (half * (C3 / 32 / NH) + cl) * 32;
       uint32_t v[32];
       tmem_ld32(tlane + COL_D3 + c0, v);
       tmem_ld_wait();
-      uint32_t res = 0;
+      // max as SIGNED integers of the biased values: exact whenever the true maximum is >= 0, and some negative value
+      // otherwise -- which the ReLU that follows maps to the same 0
+      int res = 0;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        float x = fmaxf(__uint_as_float(v[e]) + s_b3[c0 + e], 0.0f);  // >= 0: uint order == float order
-        uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(x));
+        const int mx = __reduce_max_sync(0xffffffffu, __float_as_int(__uint_as_float(v[e]) + s_b3[c0 + e]));
         if (lane == e) res = mx;
       }
-      orow[c0 + lane] = a.round_out ? rna_tf32_fin(__uint_as_float(res)) : __uint_as_float(res);
+      const float r = fmaxf(__int_as_float(res), 0.0f);
+      orow[c0 + lane] = a.round_out ? rna_tf32_fin(r) : r;
     }
     tc_fence_before();  // the next tile's MMAs overwrite D2/D3 only after every thread's loads above
     cur = nxt;
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(128) sa_fused_kernel(SaArgs a) {
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int C1, int C2, int C3, bool FIRST, bool A_TMEM>
+template <int C1, int C2, int C3, bool FIRST, bool A_TMEM, int NT = 128>
 int launch_t(const SaArgs& a, cudaStream_t st) {
   constexpr int need = C2 * C1 * 4 + C3 * C2 * 4 + (A_TMEM ? 0 : 128 * (C1 + C2) * 4) + 1024;
   constexpr uint32_t cols_need = (A_TMEM ? C1 : 0) + C2 + C3;
@@ -271,7 +286,7 @@ int launch_t(const SaArgs& a, cudaStream_t st) {
   constexpr int smem = need > floor_smem ? need : floor_smem;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+    if (cudaFuncSetAttribute(sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
       return -1;
     attr_done = true;
@@ -281,7 +296,7 @@ int launch_t(const SaArgs& a, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms * per_sm;
   if (grid > a.n_tiles) grid = a.n_tiles;
-  sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM><<<grid, 128, smem, st>>>(a);
+  sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM, NT><<<grid, NT, smem, st>>>(a);
   return 1;
 }
 
@@ -301,18 +316,28 @@ struct SaConst {
   float b2[C2];
 };
 
-template <int C1, int C2, int C3, bool FIRST>
-__global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(SaArgs a, const __grid_constant__ SaConst<C1, C2, C3, FIRST> k) {
+template <int V>
+struct IntC { static constexpr int value = V; };
+
+template <int C1, int C2, int C3, bool FIRST, int NT>
+__global__ void __launch_bounds__(NT, FIRST ? 4 : 2) sa_fused_v2_kernel(SaArgs a, const __grid_constant__ SaConst<C1, C2, C3, FIRST> k) {
   static_assert(C3 <= 128 && C1 + C2 <= 128, "v2 covers sa1 / sa2");
+  // NT = 256: two warps per TMEM lane quarter; each thread does HALF of its row's channels (gather, epilogue 2) and half of
+  // its channel's centroids (epilogue 3).  The share is a compile-time constant of each code path (IntC) so that the
+  // per-channel vectors stay constant-bank immediates.
+  constexpr int NH = NT / 128;
   constexpr int KB2 = C1 / 32, KB3 = C2 / 32;
+  static_assert(KB2 % NH == 0 && KB3 % NH == 0 && 4 % NH == 0 && (!FIRST || (NH == 1 && C1 == 32)), "column split");
   constexpr int W2_BYTES = C2 * C1 * 4, W3_BYTES = 128 * C2 * 4, H2_BYTES = 128 * C2 * 4;
   constexpr uint32_t COL_H1 = 0, COL_D2 = C1, COL_D3T = 0, TCOLS = 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar;
   __shared__ uint32_t s_tmem;
   __shared__ float s_b3[128];
+  __shared__ __align__(16) float s_cc[FIRST ? 4 * 32 : 4];  // sa1: per-warp (== per-centroid) constant part of layer 1
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rit = tid & 127, wq = warp & 3, half = tid >> 7;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW2 = base, sW3 = sW2 + W2_BYTES, sH2 = sW3 + W3_BYTES;
   const uint32_t bar = smem_u32(&s_bar);
@@ -322,168 +347,202 @@ __global__ void __launch_bounds__(128, (C2 <= 32) ? 4 : 2) sa_fused_v2_kernel(Sa
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  for (int q = tid; q < C2 * C1 / 4; q += 128) {
+  for (int q = tid; q < C2 * C1 / 4; q += NT) {
     int n = q / (C1 / 4), k4 = q % (C1 / 4);
     float4 v = *reinterpret_cast<const float4*>(a.W2 + (int64_t)n * C1 + k4 * 4);
     st_shared_v4(sW2 + (k4 >> 3) * (C2 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
   }
-  for (int q = tid; q < 128 * C2 / 4; q += 128) {  // W3 rows >= C3 are zero padding up to the UMMA M of 128
+  for (int q = tid; q < 128 * C2 / 4; q += NT) {  // W3 rows >= C3 are zero padding up to the UMMA M of 128
     int n = q / (C2 / 4), k4 = q % (C2 / 4);
     float4 v = n < C3 ? *reinterpret_cast<const float4*>(a.W3 + (int64_t)n * C2 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     st_shared_v4(sW3 + (k4 >> 3) * (128 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
   }
-  s_b3[tid] = tid < C3 ? a.b3[tid] : 0.f;
+  if (tid < 128) s_b3[tid] = tid < C3 ? a.b3[tid] : 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
   constexpr uint32_t idesc2 = umma_idesc_tf32(128, C2), idesc3 = umma_idesc_tf32(128, 128);
-  const float bias3 = s_b3[tid];
-  uint32_t phase = 0;
+  const float bias3 = s_b3[rit];
+  // sa1: layer 1 is  b1 + Wx.(p_j - c) + Wf.p_j  ==  (b1 - Wx.c) + (Wx + Wf).p_j.  The first term is per centroid (== per
+  // warp): lane ch computes it once per tile and the warp re-reads it as broadcast 128-bit shared loads; the second uses
+  // the host-summed k.wf -- 3 FFMA per channel instead of 6.
+  float my_wx0 = 0.f, my_wx1 = 0.f, my_wx2 = 0.f, my_b1 = 0.f;
+  if (FIRST) {
+    my_wx0 = a.Wx[lane * 3 + 0];
+    my_wx1 = a.Wx[lane * 3 + 1];
+    my_wx2 = a.Wx[lane * 3 + 2];
+    my_b1 = a.b1[lane];
+  }
 
   const int per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
   const int t0 = blockIdx.x * per, t1 = (t0 + per < a.n_tiles) ? t0 + per : a.n_tiles;
   struct Pre { int j; float jx, jy, jz, cx, cy, cz; };
-  auto load_idx = [&](int tile) -> int { return tile < t1 ? a.grp[(int64_t)tile * 128 + tid] : 0; };
+  auto load_idx = [&](int tile) -> int { return tile < t1 ? a.grp[(int64_t)tile * 128 + rit] : 0; };
   auto load_pts = [&](int tile, int j) -> Pre {
     Pre p{j, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (tile < t1) {
-      const int64_t cs = ((int64_t)tile * 128 + tid) >> 5;
-      const float* pj = a.xyz + ((cs / a.S) * a.N + j) * 3;
+      const int64_t cs = ((int64_t)tile * 128 + rit) >> 5;
+      const float* pj = a.xyz + ((cs >> a.s_shift) * a.N + j) * 3;
       const float* pc = a.new_xyz + cs * 3;
       p.jx = pj[0]; p.jy = pj[1]; p.jz = pj[2];
       p.cx = pc[0]; p.cy = pc[1]; p.cz = pc[2];
     }
     return p;
   };
-  Pre cur = load_pts(t0, load_idx(t0));
-  int j1 = load_idx(t0 + 1);
-  float4 prow[FIRST ? 1 : C1 / 4];  // projected row of the next tile, in flight during this tile's MMAs / epilogues
-  auto load_row = [&](int tile, int j) {
-    if (!FIRST && tile < t1) {
-      const int64_t c = (((int64_t)tile * 128 + tid) >> 5) / a.S;
-      const float4* p = reinterpret_cast<const float4*>(a.P + (c * a.N + j) * C1);
+
+  auto run = [&](auto HC) {
+    constexpr int H = decltype(HC)::value;
+    constexpr int PQ = C1 / 4 / NH;
+    uint32_t phase = 0;
+    Pre cur = load_pts(t0, load_idx(t0));
+    int j1 = load_idx(t0 + 1);
+    float4 prow[FIRST ? 1 : PQ];  // this thread's share of the projected row of the next tile, in flight during this tile
+    auto load_row = [&](int tile, int j) {
+      if (!FIRST && tile < t1) {
+        const int64_t c = (((int64_t)tile * 128 + rit) >> 5) >> a.s_shift;
+        const float4* p = reinterpret_cast<const float4*>(a.P + (c * a.N + j) * C1) + H * PQ;
 #pragma unroll
-      for (int q = 0; q < C1 / 4; ++q) prow[q] = p[q];
+        for (int q = 0; q < PQ; ++q) prow[q] = p[q];
+      }
+    };
+    load_row(t0, cur.j);
+    for (int tile = t0; tile < t1; ++tile) {
+      const Pre nxt = load_pts(tile + 1, j1);
+      j1 = load_idx(tile + 2);
+      const float jx = cur.jx, jy = cur.jy, jz = cur.jz;
+      const float rx = jx - cur.cx, ry = jy - cur.cy, rz = jz - cur.cz;
+      if (FIRST) {
+        s_cc[FIRST ? warp * 32 + lane : 0] = fmaf(-my_wx0, cur.cx, fmaf(-my_wx1, cur.cy, fmaf(-my_wx2, cur.cz, my_b1)));
+        __syncwarp();
+      }
+      // ---- gather + first layer: thread = grouped row, constant-bank weights ----
+#pragma unroll
+      for (int kl = 0; kl < KB2 / NH; ++kl) {
+        constexpr int KB0 = H * (KB2 / NH);
+        const int kb = KB0 + kl;
+        uint32_t v[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float pv[4];
+          if (FIRST) {
+            const float4 c4 = *reinterpret_cast<const float4*>(&s_cc[FIRST ? warp * 32 + q * 4 : 0]);
+            pv[0] = c4.x; pv[1] = c4.y; pv[2] = c4.z; pv[3] = c4.w;
+          } else {
+            const float4 p4 = prow[FIRST ? 0 : kl * 8 + q];
+            pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int ch = kb * 32 + q * 4 + e;
+            float x = pv[e];
+            if (FIRST) {
+              x = fmaf(k.wf[FIRST ? ch * 3 + 0 : 0], jx, x);
+              x = fmaf(k.wf[FIRST ? ch * 3 + 1 : 0], jy, x);
+              x = fmaf(k.wf[FIRST ? ch * 3 + 2 : 0], jz, x);
+            } else {
+              x = fmaf(k.wx[ch * 3 + 0], rx, x);
+              x = fmaf(k.wx[ch * 3 + 1], ry, x);
+              x = fmaf(k.wx[ch * 3 + 2], rz, x);
+            }
+            v[q * 4 + e] = rna_tf32_mma(fmaxf(x, 0.0f));
+          }
+        }
+        tmem_st32(tlane + COL_H1 + kb * 32, v);
+      }
+      tmem_st_wait();
+      load_row(tile + 1, nxt.j);
+      tc_fence_before();
+      __syncthreads();
+      // ---- layer 2: D2[point, ch] = h1 . W2^T (A from TMEM) ----
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB2; ++kb) {
+          const uint64_t db = umma_desc_sw128(sW2 + kb * (C2 * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32_ts(tmem + COL_D2, tmem + COL_H1 + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc2, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      // ---- epilogue 2: bias + ReLU + RNA -> h2 tile in smem (B operand of the transposed last layer) ----
+#pragma unroll
+      for (int kl = 0; kl < KB3 / NH; ++kl) {
+        constexpr int KB0 = H * (KB3 / NH);
+        const int kb = KB0 + kl;
+        uint32_t v[32];
+        tmem_ld32(tlane + COL_D2 + kb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          o.x = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 0]) + k.b2[kb * 32 + q * 4 + 0], 0.0f)));
+          o.y = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 1]) + k.b2[kb * 32 + q * 4 + 1], 0.0f)));
+          o.z = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 2]) + k.b2[kb * 32 + q * 4 + 2], 0.0f)));
+          o.w = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 3]) + k.b2[kb * 32 + q * 4 + 3], 0.0f)));
+          st_shared_v4(sH2 + kb * (128 * 128) + sw128_off(rit, q), o);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      // ---- layer 3, transposed: D3T[ch, point] = W3 . h2^T ----
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB3; ++kb) {
+          const uint64_t da = umma_desc_sw128(sW3 + kb * (128 * 128)), db = umma_desc_sw128(sH2 + kb * (128 * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32_ss(tmem + COL_D3T, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc3, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      // ---- epilogue 3: thread = channel; max over each centroid's 32 columns, then bias + ReLU (monotone, so after the max) ----
+      if (rit < C3) {
+#pragma unroll
+        for (int gl = 0; gl < 4 / NH; ++gl) {
+          constexpr int G0 = H * (4 / NH);
+          const int g = G0 + gl;
+          uint32_t v[32];
+          tmem_ld32(tlane + COL_D3T + g * 32, v);
+          tmem_ld_wait();
+          float m = __uint_as_float(v[0]);
+#pragma unroll
+          for (int e = 1; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
+          const float r = fmaxf(m + bias3, 0.0f);
+          a.out[((int64_t)tile * 4 + g) * C3 + rit] = a.round_out ? rna_tf32_fin(r) : r;
+        }
+      }
+      tc_fence_before();
+      cur = nxt;
     }
   };
-  load_row(t0, cur.j);
-  for (int tile = t0; tile < t1; ++tile) {
-    const Pre nxt = load_pts(tile + 1, j1);
-    j1 = load_idx(tile + 2);
-    const float jx = cur.jx, jy = cur.jy, jz = cur.jz;
-    const float rx = jx - cur.cx, ry = jy - cur.cy, rz = jz - cur.cz;
-    // ---- gather + first layer: thread = grouped row, constant-bank weights ----
-#pragma unroll
-    for (int kb = 0; kb < KB2; ++kb) {
-      uint32_t v[32];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float pv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!FIRST) {
-          const float4 p4 = prow[FIRST ? 0 : kb * 8 + q];
-          pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ch = kb * 32 + q * 4 + e;
-          float x = FIRST ? k.b1[FIRST ? ch : 0] : pv[e];
-          x = fmaf(k.wx[ch * 3 + 0], rx, x);
-          x = fmaf(k.wx[ch * 3 + 1], ry, x);
-          x = fmaf(k.wx[ch * 3 + 2], rz, x);
-          if (FIRST) {
-            x = fmaf(k.wf[FIRST ? ch * 3 + 0 : 0], jx, x);
-            x = fmaf(k.wf[FIRST ? ch * 3 + 1 : 0], jy, x);
-            x = fmaf(k.wf[FIRST ? ch * 3 + 2 : 0], jz, x);
-          }
-          v[q * 4 + e] = rna_tf32_mma(fmaxf(x, 0.0f));
-        }
-      }
-      tmem_st32(tlane + COL_H1 + kb * 32, v);
-    }
-    tmem_st_wait();
-    load_row(tile + 1, nxt.j);
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 2: D2[point, ch] = h1 . W2^T (A from TMEM) ----
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < KB2; ++kb) {
-        const uint64_t db = umma_desc_sw128(sW2 + kb * (C2 * 128));
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_tf32_ts(tmem + COL_D2, tmem + COL_H1 + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc2, (kb | kk) != 0 ? 1u : 0u);
-      }
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue 2: bias + ReLU + RNA -> h2 tile in smem (B operand of the transposed last layer) ----
-#pragma unroll
-    for (int kb = 0; kb < KB3; ++kb) {
-      uint32_t v[32];
-      tmem_ld32(tlane + COL_D2 + kb * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 o;
-        o.x = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 0]) + k.b2[kb * 32 + q * 4 + 0], 0.0f)));
-        o.y = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 1]) + k.b2[kb * 32 + q * 4 + 1], 0.0f)));
-        o.z = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 2]) + k.b2[kb * 32 + q * 4 + 2], 0.0f)));
-        o.w = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 3]) + k.b2[kb * 32 + q * 4 + 3], 0.0f)));
-        st_shared_v4(sH2 + kb * (128 * 128) + sw128_off(tid, q), o);
-      }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 3, transposed: D3T[ch, point] = W3 . h2^T ----
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < KB3; ++kb) {
-        const uint64_t da = umma_desc_sw128(sW3 + kb * (128 * 128)), db = umma_desc_sw128(sH2 + kb * (128 * 128));
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_tf32_ss(tmem + COL_D3T, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc3, (kb | kk) != 0 ? 1u : 0u);
-      }
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue 3: thread = channel; max over each centroid's 32 columns, then bias + ReLU (monotone, so after the max) ----
-    if (tid < C3) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[32];
-        tmem_ld32(tlane + COL_D3T + g * 32, v);
-        tmem_ld_wait();
-        float m = __uint_as_float(v[0]);
-#pragma unroll
-        for (int e = 1; e < 32; ++e) m = fmaxf(m, __uint_as_float(v[e]));
-        const float r = fmaxf(m + bias3, 0.0f);
-        a.out[((int64_t)tile * 4 + g) * C3 + tid] = a.round_out ? rna_tf32_fin(r) : r;
-      }
-    }
-    tc_fence_before();
-    cur = nxt;
+  if (NH == 1 || half == 0) {
+    run(IntC<0>{});
+  } else {
+    run(IntC<NH - 1>{});
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int C1, int C2, int C3, bool FIRST>
+template <int C1, int C2, int C3, bool FIRST, int NT>
 int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float* h_b1, const float* h_b2, cudaStream_t st) {
   SaConst<C1, C2, C3, FIRST> k;
   for (int i = 0; i < C1 * 3; ++i) k.wx[i] = h_wx[i];
   if (FIRST) {
-    for (int i = 0; i < C1 * 3; ++i) k.wf[i] = h_wf[i];
+    for (int i = 0; i < C1 * 3; ++i) k.wf[i] = h_wx[i] + h_wf[i];  // (Wx + Wf): see the kernel's layer-1 note
     for (int i = 0; i < C1; ++i) k.b1[i] = h_b1[i];
   } else {
     k.wf[0] = 0.f;
@@ -492,12 +551,13 @@ int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float
   for (int i = 0; i < C2; ++i) k.b2[i] = h_b2[i];
   constexpr int need = C2 * C1 * 4 + 2 * 128 * C2 * 4 + 1024;
   constexpr int by_smem = (227 * 1024) / (need + 1024);
-  constexpr int per_sm = by_smem < 4 ? by_smem : 4;  // 4 x 128 TMEM columns
+  constexpr int want = FIRST ? 4 : 2;  // == the kernel's __launch_bounds__ (4 x 128 TMEM columns at most)
+  constexpr int per_sm = by_smem < want ? by_smem : want;
   constexpr int floor_smem = (227 * 1024) / (per_sm + 1) + 1;
   constexpr int smem = need > floor_smem ? need : floor_smem;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(sa_fused_v2_kernel<C1, C2, C3, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(sa_fused_v2_kernel<C1, C2, C3, FIRST, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return -1;
     attr_done = true;
   }
@@ -506,7 +566,7 @@ int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms * per_sm;
   if (grid > a.n_tiles) grid = a.n_tiles;
-  sa_fused_v2_kernel<C1, C2, C3, FIRST><<<grid, 128, smem, st>>>(a, k);
+  sa_fused_v2_kernel<C1, C2, C3, FIRST, NT><<<grid, NT, smem, st>>>(a, k);
   return 1;
 }
 
@@ -516,20 +576,22 @@ int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float
 int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, const float* new_xyz, const int* grp,
                     const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
                     const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st) {
-  SaArgs a{P, xyz, new_xyz, grp, Wx, Wf3, b1, W2, b2, W3, b3, out, n_clouds * S / 4, N, S, round_out};
+  if (S <= 0 || (S & (S - 1)) != 0) return -1;
+  SaArgs a{P, xyz, new_xyz, grp, Wx, Wf3, b1, W2, b2, W3, b3, out, n_clouds * S / 4, N, S, round_out, __builtin_ctz(S)};
   if (level == 0) return a_tmem ? launch_t<32, 32, 64, true, true>(a, st) : launch_t<32, 32, 64, true, false>(a, st);
   if (level == 1) return a_tmem ? launch_t<64, 64, 128, false, true>(a, st) : launch_t<64, 64, 128, false, false>(a, st);
-  if (level == 2) return a_tmem ? launch_t<128, 128, 256, false, true>(a, st) : -1;
+  if (level == 2) return a_tmem ? launch_t<128, 128, 256, false, true, 256>(a, st) : -1;
   return -1;
 }
 
 // v2 (transposed last layer, constant-bank vectors) for levels 0 and 1; h_* are HOST copies of the small per-channel vectors.
 int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp, const float* h_wx,
-                       const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
-                       int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st) {
-  SaArgs a{P, xyz, new_xyz, grp, nullptr, nullptr, nullptr, W2, nullptr, W3, b3, out, n_clouds * S / 4, N, S, round_out};
-  if (level == 0) return launch_v2<32, 32, 64, true>(a, h_wx, h_wf, h_b1, h_b2, st);
-  if (level == 1) return launch_v2<64, 64, 128, false>(a, h_wx, h_wf, h_b1, h_b2, st);
+                       const float* h_wf, const float* h_b1, const float* h_b2, const float* d_wx, const float* d_b1, const float* W2,
+                       const float* W3, const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st) {
+  if (S <= 0 || (S & (S - 1)) != 0) return -1;
+  SaArgs a{P, xyz, new_xyz, grp, d_wx, nullptr, d_b1, W2, nullptr, W3, b3, out, n_clouds * S / 4, N, S, round_out, __builtin_ctz(S)};
+  if (level == 0) return launch_v2<32, 32, 64, true, 128>(a, h_wx, h_wf, h_b1, h_b2, st);
+  if (level == 1) return launch_v2<64, 64, 128, false, 256>(a, h_wx, h_wf, h_b1, h_b2, st);
   return -1;
 }
 
