@@ -170,6 +170,8 @@ LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32
  * activations staged in shared memory, 2 = fused with the activations kept in tensor memory (A-from-TMEM MMA), 3 = levels 1-2
  * with the transposed-last-layer variant (in-register max-pool, constant-bank weights), level 3 as in 2.
  * "fp_tail": 1 = the last two fp1 layers + conv1/bn1/conv2 head as one fused tensor-core kernel.
+ * "fp_fused": 1 = the fp2 level (fine half of conv 1 + 3-NN interpolation of the projected coarse features + conv 2) as one
+ *             fused tensor-core kernel.
  * "gemm_async" (process-wide): 1 = TF32 layers whose operands are pre-rounded by their producers use the cp.async-fed
  * persistent warp-specialised GEMM.
  * "gemm_ws" (process-wide): 1 = persistent warp-specialised tcgen05 GEMM (default), 0 = one-CTA-per-tile tcgen05 GEMM. */

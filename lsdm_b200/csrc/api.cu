@@ -101,6 +101,7 @@ struct lsdm_handle {
   float *head_w, *head_b;
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
+  int fp_fused = 0;              // 1: fused fp2 level (fine GEMM + interpolation + second conv in one kernel)
   std::vector<float> host_wx[2], host_wf[2], host_b1[2], host_b2[2];  // host copies for the v2 fused SA kernels (kernel params)
   // schedule
   float* sched = nullptr;  // 5 x T
@@ -452,11 +453,23 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     const FPSpec& s = kFP[l];
     const int N = fineN[l], S = coarseN[l], C1 = s.mlp[0];
     const float* Pa = nullptr;
-    if (s.Ca > 0) {
+    const bool fused_level = h->precision >= 1 && h->fp_fused && l == 2;  // fp2: both weight matrices fit in shared memory
+    if (s.Ca > 0 && !fused_level) {
       GE(gemm(h, st, feat[fine[l]], s.Ca, h->fp_wa[l], s.Ca, w.tA, C1, h->fp_b[l][0], C * N, C1, s.Ca, ACT_NONE, 0, -1, GF_A_ROUNDED));
       Pa = w.tA;
     }
     GE(gemm(h, st, coarse_feat, s.Cb, h->fp_wb[l], s.Cb, w.tB, C1, nullptr, C * S, C1, s.Cb, ACT_NONE, 0, -1, GF_A_ROUNDED));
+    if (fused_level) {
+      const double fl = 2.0 * C * N * ((double)s.Ca * C1 + (double)C1 * s.mlp[1]);
+      int r = prof_launch(h, st, K_GEMM, [&] {
+        return launch_fp_fused(feat[fine[l]], s.Ca, h->fp_wa[l], h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l], h->fp_w[l][1], h->fp_b[l][1],
+                               C, N, S, C1, s.mlp[1], outs[l], h->precision == 1, st);
+      }, "fp2_fused", fl);
+      if (r < 0) return fail(LSDM_EINVAL, "fused FP kernel unavailable for this level");
+      if (h->profiling) h->gemm_flops += fl;
+      coarse_feat = outs[l];
+      continue;
+    }
     prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l], C, N, S, C1, w.tP, h->precision == 1, st); });
     if (l < 3) {
       GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
@@ -1103,6 +1116,10 @@ LSDM_API const char* lsdm_profile_report(const lsdm_handle* h) { return h ? h->p
 
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   if (!h || !name) return fail(LSDM_EINVAL, "null argument");
+  if (strcmp(name, "fp_fused") == 0 && (value == 0 || value == 1)) {
+    h->fp_fused = value;
+    return LSDM_OK;
+  }
   if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 3) {
     h->sa_fused = value;
     return LSDM_OK;

@@ -1,0 +1,276 @@
+// Fused PointNet++ feature-propagation block (reference pointnet2_utils.py:266-316) for the level whose two weight
+// matrices fit in shared memory (fp2: 64 + 256 -> 256 -> 128 over the 1024 points of every cloud):
+//   h1  = ReLU( X.Wa^T + ba + sum_k w_k . Pb[nn_k] )        X  = fine-level features      [rows, CA]
+//   out = ReLU( h1.W1^T + b1 )                              Pb = coarse features already projected by the coarse half of
+//                                                                the first conv (linear, so projecting before interpolating
+//                                                                is the same map at 1/4 of the rows)
+// for 128 rows per tile with NOTHING but `out` leaving the SM: the unfused sequence (GEMM -> fp_combine -> GEMM) wrote and
+// re-read two [rows, 256] fp32 intermediates, 2.4 GB of HBM traffic per denoising step at batch 64.
+// One persistent CTA of 256 threads per SM; thread pair (t, t+128) owns tile row t&127 == TMEM lane and splits its columns:
+//   X half-row (prefetched one tile ahead) -> TF32 -> TMEM A operand -> MMA1 (A from TMEM, Wa resident in smem, N = C1)
+//   epilogue 1: tcgen05.ld chunk + bias + interpolated Pb chunk (gathered line-coalesced by all warps, exchanged through a
+//               swizzled shared-memory tile) -> ReLU -> TF32 -> tcgen05.st in place
+//   MMA2 (A from TMEM, W1 resident, N = C2) -> epilogue 2: bias + ReLU (+ TF32 rounding) -> global.
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+namespace lsdm {
+
+namespace {
+
+using namespace tc;
+
+struct FpArgs {
+  const float* X;       // [rows, CA]
+  const float* Wa;      // [C1, CA]
+  const float* ba;      // [C1]
+  const float* Pb;      // [n_clouds * S, C1]
+  const int* nn_idx;    // [rows, 3] indices into the cloud's S coarse points
+  const float* nn_w;    // [rows, 3]
+  const float* W1;      // [C2, C1]
+  const float* b1;      // [C2]
+  float* out;           // [rows, C2]
+  int n_tiles, S, n_shift;  // n_shift = log2(points per cloud at the fine level)
+  int round_out;
+};
+
+template <int CA, int C1, int C2>
+__global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
+  constexpr int KB1 = CA / 32, KB2 = C1 / 32;
+  static_assert(KB1 % 2 == 0 && (C1 / 32) % 2 == 0 && (C2 / 32) % 2 == 0, "column split between the two threads of a row");
+  constexpr int WA_BYTES = C1 * CA * 4, W1_BYTES = C2 * C1 * 4;
+  constexpr uint32_t COL_A1 = 0, COL_D1 = CA, COL_D2 = CA + C1;
+  static_assert(COL_D2 + C2 <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_ba[C1], s_b1[C2];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rit = tid & 127, wq = warp & 3, half = tid >> 7;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sWa = base, sW1 = sWa + WA_BYTES;
+  const uint32_t bar = smem_u32(&s_bar);
+
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (int q = tid; q < C1 * CA / 4; q += 256) {
+    int n = q / (CA / 4), k4 = q % (CA / 4);
+    float4 v = *reinterpret_cast<const float4*>(a.Wa + (int64_t)n * CA + k4 * 4);
+    st_shared_v4(sWa + (k4 >> 3) * (C1 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  for (int q = tid; q < C2 * C1 / 4; q += 256) {
+    int n = q / (C1 / 4), k4 = q % (C1 / 4);
+    float4 v = *reinterpret_cast<const float4*>(a.W1 + (int64_t)n * C1 + k4 * 4);
+    st_shared_v4(sW1 + (k4 >> 3) * (C2 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  for (int i = tid; i < C1; i += 256) s_ba[i] = a.ba[i];
+  for (int i = tid; i < C2; i += 256) s_b1[i] = a.b1[i];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+  constexpr uint32_t idesc1 = umma_idesc_tf32(128, C1), idesc2 = umma_idesc_tf32(128, C2);
+  uint32_t phase = 0;
+
+  const int per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = (t0 + per < a.n_tiles) ? t0 + per : a.n_tiles;
+
+  // Two roles per thread.  ROW role: thread pair (rit, half) owns tile row rit and half of its columns (TMEM lane == row).
+  // LOADER role (the 3-neighbour gather): lanes 8j..8j+7 of a warp read 128 contiguous bytes of ONE coarse row, so every
+  // L1 request is a full line (a row-per-lane gather would touch 32 lines per instruction and is L1-tag bound); the
+  // interpolated 32-column chunk is handed to the row role through a swizzled shared-memory tile, one per column half.
+  constexpr int XQ = CA / 4 / 2;
+  float4 xrow[XQ];  // ROW role: this thread's half of the X row, prefetched one tile ahead
+  int li[4][3];     // LOADER role: neighbours / weights of tile rows (tid>>3) + 32 i, prefetched one tile ahead
+  float lw[4][3];
+  const int lr0 = tid >> 3, lc4 = tid & 7;
+  auto prefetch = [&](int tile) {
+    if (tile < t1) {
+      const int64_t row = (int64_t)tile * 128 + rit;
+      const float4* p = reinterpret_cast<const float4*>(a.X + row * CA) + half * XQ;
+#pragma unroll
+      for (int q = 0; q < XQ; ++q) xrow[q] = p[q];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t r = (int64_t)tile * 128 + lr0 + 32 * i;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          li[i][j] = a.nn_idx[r * 3 + j];
+          lw[i][j] = a.nn_w[r * 3 + j];
+        }
+      }
+    }
+  };
+  float* stage = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + WA_BYTES + W1_BYTES);  // 2 x [128][32] floats
+  constexpr int CH1 = C1 / 32 / 2;  // 32-column chunks per column half
+  prefetch(t0);
+  for (int tile = t0; tile < t1; ++tile) {
+    const int64_t row = (int64_t)tile * 128 + rit;
+    const int64_t cbase = (((int64_t)tile * 128) >> a.n_shift) * a.S;  // a tile never straddles two clouds
+    // ---- A1: own half-row -> TMEM (the +half-ulp of rna_tf32_mma is a no-op on already rounded inputs) ----
+#pragma unroll
+    for (int kl = 0; kl < KB1 / 2; ++kl) {
+      uint32_t v[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 p = xrow[kl * 8 + q];
+        v[q * 4 + 0] = rna_tf32_mma(p.x);
+        v[q * 4 + 1] = rna_tf32_mma(p.y);
+        v[q * 4 + 2] = rna_tf32_mma(p.z);
+        v[q * 4 + 3] = rna_tf32_mma(p.w);
+      }
+      tmem_st32(tlane + COL_A1 + (half * (KB1 / 2) + kl) * 32, v);
+    }
+    tmem_st_wait();
+    // loader state of THIS tile (the prefetch below overwrites li / lw with the next tile's)
+    const float* gp[4][3];
+    float gw[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        gp[i][j] = a.Pb + (cbase + li[i][j]) * C1 + lc4 * 4;
+        gw[i][j] = lw[i][j];
+      }
+    prefetch(tile + 1);
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1: D1 = X . Wa^T ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB1; ++kb) {
+        const uint64_t db = umma_desc_sw128(sWa + kb * (C1 * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_tf32_ts(tmem + COL_D1, tmem + COL_A1 + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc1, (kb | kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar);
+    }
+    // gather registers: step s covers chunk s of BOTH column halves (hh = 0, 1): 4 rows x 2 halves x 3 neighbours
+    float4 nb[2][4][3];
+    auto gather = [&](int s) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) nb[hh][i][j] = *reinterpret_cast<const float4*>(gp[i][j] + (hh * CH1 + s) * 32);
+    };
+    gather(0);  // travels while the MMA runs
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 1: + bias + interpolated coarse projection, ReLU, TF32 -> A operand of layer 2 (in place) ----
+#pragma unroll 1
+    for (int s = 0; s < CH1; ++s) {
+      // LOADER: interpolate (same operation order as the unfused fp_combine) and publish
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x0 = nb[hh][i][0], x1 = nb[hh][i][1], x2 = nb[hh][i][2];
+          const float w0 = gw[i][0], w1 = gw[i][1], w2 = gw[i][2];
+          float4 o;
+          o.x = fmaf(x2.x, w2, fmaf(x1.x, w1, x0.x * w0));
+          o.y = fmaf(x2.y, w2, fmaf(x1.y, w1, x0.y * w0));
+          o.z = fmaf(x2.z, w2, fmaf(x1.z, w1, x0.z * w0));
+          o.w = fmaf(x2.w, w2, fmaf(x1.w, w1, x0.w * w0));
+          const int r = lr0 + 32 * i;
+          *reinterpret_cast<float4*>(stage + hh * (128 * 32) + r * 32 + ((lc4 ^ (r & 7)) << 2)) = o;
+        }
+      __syncthreads();
+      if (s + 1 < CH1) gather(s + 1);  // next step's rows are in flight during this step's TMEM round trip
+      // ROW: this thread's 32 columns of chunk s
+      const int c0 = (half * CH1 + s) * 32;
+      uint32_t v[32];
+      tmem_ld32(tlane + COL_D1 + c0, v);
+      tmem_ld_wait();
+      const float* srow = stage + half * (128 * 32) + rit * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 it = *reinterpret_cast<const float4*>(srow + ((q ^ (rit & 7)) << 2));
+        const float iv[4] = {it.x, it.y, it.z, it.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pa = __uint_as_float(v[q * 4 + e]) + s_ba[c0 + q * 4 + e];  // == the unfused GEMM's epilogue
+          v[q * 4 + e] = rna_tf32_mma(fmaxf(pa + iv[e], 0.0f));                    // == fp_combine
+        }
+      }
+      tmem_st32(tlane + COL_D1 + c0, v);
+      __syncthreads();  // the staging tiles are rewritten by the next step
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2: D2 = h1 . W1^T ----
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB2; ++kb) {
+        const uint64_t db = umma_desc_sw128(sW1 + kb * (C2 * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_tf32_ts(tmem + COL_D2, tmem + COL_D1 + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc2, (kb | kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 2: bias + ReLU (+ rounding for the next tensor-core consumer) -> global, 128 B per thread per chunk ----
+    float* orow = a.out + row * C2;
+#pragma unroll 1
+    for (int cl = 0; cl < C2 / 32 / 2; ++cl) {
+      const int c0 = (half * (C2 / 32 / 2) + cl) * 32;
+      uint32_t v[32];
+      tmem_ld32(tlane + COL_D2 + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float r = fmaxf(__uint_as_float(v[q * 4 + e]) + s_b1[c0 + q * 4 + e], 0.0f);
+          o[e] = a.round_out ? rna_tf32_fin(r) : r;
+        }
+        *reinterpret_cast<float4*>(orow + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    tc_fence_before();  // the next tile's tcgen05.st / MMAs reuse these columns
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+// fp2 of the reference backbone: CA = 64 (l1 features), C1 = 256, C2 = 128; N (fine points per cloud) must be a power of
+// two and a multiple of 128.  Returns the number of launches (1) or -1 when the shape is not covered.
+int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, const float* Pb, const int* nn_idx, const float* nn_w,
+                    const float* W1, const float* b1, int n_clouds, int N, int S, int C1, int C2, float* out, int round_out,
+                    cudaStream_t st) {
+  if (CA != 64 || C1 != 256 || C2 != 128 || N < 128 || (N & (N - 1)) != 0) return -1;
+  FpArgs a{X, Wa, ba, Pb, nn_idx, nn_w, W1, b1, out, n_clouds * (N / 128), S, __builtin_ctz(N), round_out};
+  constexpr int smem = 256 * 64 * 4 + 128 * 256 * 4 + 2 * 128 * 32 * 4 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(fp_fused_kernel<64, 256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms < a.n_tiles ? sms : a.n_tiles;
+  fp_fused_kernel<64, 256, 128><<<grid, 256, smem, st>>>(a);
+  return 1;
+}
+
+}  // namespace lsdm

@@ -41,6 +41,11 @@ int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float*
                        const float* h_wf, const float* h_b1, const float* h_b2, const float* d_wx, const float* d_b1, const float* W2,
                        const float* W3, const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
 
+// fused feature-propagation level (fp2): first conv (fine half on the tensor core + interpolated coarse projection) + second conv
+int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, const float* Pb, const int* nn_idx, const float* nn_w,
+                    const float* W1, const float* b1, int n_clouds, int N, int S, int C1, int C2, float* out, int round_out,
+                    cudaStream_t st);
+
 // fused tail of the backbone: fp1 layers 2-3 + conv1/bn1 head + conv2, TF32 tensor cores; h_consts is a HOST array
 // [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]
 int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const float* Wh, const float* h_consts, int64_t rows,
