@@ -54,7 +54,11 @@ __device__ __forceinline__ void fps_level(const float* sx, const float* sy, cons
 #pragma unroll
       for (int j = 0; j < PER2; ++j) {
         float2 dx = __fadd2_rn(qx[j], ncx), dy = __fadd2_rn(qy[j], ncy), dz = __fadd2_rn(qz[j], ncz);
-        float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+        // Products packed, sums SCALAR: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into a fused FFMA2 when the
+        // product has a single use, despite the explicit rounding modifiers (tools/probe/packed_fma_probe.cu: 21 % of the
+        // squared distances then differ from the reference's (dx^2 + dy^2) + dz^2).  Scalar add.rn is never contracted.
+        const float2 sxx = __fmul2_rn(dx, dx), syy = __fmul2_rn(dy, dy), szz = __fmul2_rn(dz, dz);
+        const float2 d = make_float2(__fadd_rn(__fadd_rn(sxx.x, syy.x), szz.x), __fadd_rn(__fadd_rn(sxx.y, syy.y), szz.y));
         float n0 = fminf(d.x, qd[j].x), n1 = fminf(d.y, qd[j].y);
         qd[j] = make_float2(n0, n1);
         unsigned b0 = __float_as_uint(n0), b1 = __float_as_uint(n1);  // >= 0: unsigned bit order == float order
@@ -158,63 +162,73 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------
-// Ball query: one warp per centroid scans the N source points in index order, keeps the first 32
-// with d <= r^2 (d in the expanded -2ab+a^2+b^2 form), pads with the first hit.
+// Shared layout for the two scans below: source points in PAIRS, A[i] = (x0, x1, y0, y1), B[i] = (z0, z1, |p0|^2, |p1|^2),
+// so that one broadcast 128-bit shared load yields ready-made fp32x2 operands.  The expanded distance
+//   d = ((-2 * (q.p)) + |q|^2) + |p|^2,   q.p = fma(qz, pz, fma(qy, py, qx * px))
+// is evaluated with packed fp32x2 instructions; fma(-2, dot, |q|^2) == (-2 * dot) + |q|^2 bit for bit because the product
+// by a power of two is exact.  Same IEEE operations and order as sqdist_expanded (common.cuh).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
-                                                         int n_clouds, int N, int S, float r2, int* __restrict__ group) {
-  extern __shared__ float4 sp[];  // (x, y, z, |p|^2) per source point: one 128-bit shared load per pair test
-  const int c = blockIdx.y;
+__device__ __forceinline__ float2 sqdist2(float2 qx, float2 qy, float2 qz, float2 qn, float4 a, float4 b) {
+  const float2 dot = __ffma2_rn(qz, make_float2(b.x, b.y), __ffma2_rn(qy, make_float2(a.z, a.w), __fmul2_rn(qx, make_float2(a.x, a.y))));
+  return __fadd2_rn(__ffma2_rn(make_float2(-2.0f, -2.0f), dot, qn), make_float2(b.z, b.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ball query: one THREAD per centroid scans the N source points in index order (every thread of the block reads the same
+// point pair: broadcast loads, no cross-lane traffic), keeps the first 32 with d <= r^2, pads with the first hit.
+// The per-thread result lists live in a transposed shared tile and leave as coalesced 128-byte rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int BQ_T = 128;  // centroids per block
+__global__ void __launch_bounds__(BQ_T) ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                                                          int n_clouds, int N, int S, float r2, int* __restrict__ group) {
+  extern __shared__ float4 sp[];                                  // [N/2] A | [N/2] B
+  __shared__ int s_out[32][BQ_T + 1];
+  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NP = N >> 1;
+  float4* sA = sp;
+  float4* sB = sp + NP;
   const float* src = xyz + (int64_t)c * N * 3;
-  for (int p = threadIdx.x; p < N; p += blockDim.x) {
-    float x = src[p * 3], y = src[p * 3 + 1], z = src[p * 3 + 2];
-    sp[p] = make_float4(x, y, z, sqnorm3(x, y, z));
+  for (int i = tid; i < NP; i += BQ_T) {
+    const float x0 = src[i * 6], y0 = src[i * 6 + 1], z0 = src[i * 6 + 2];
+    const float x1 = src[i * 6 + 3], y1 = src[i * 6 + 4], z1 = src[i * 6 + 5];
+    sA[i] = make_float4(x0, x1, y0, y1);
+    sB[i] = make_float4(z0, z1, sqnorm3(x0, y0, z0), sqnorm3(x1, y1, z1));
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int s = blockIdx.x * nwarp + warp; s < S; s += gridDim.x * nwarp) {
-    const float* q = new_xyz + ((int64_t)c * S + s) * 3;
-    float qx = q[0], qy = q[1], qz = q[2];
-    float q2 = sqnorm3(qx, qy, qz);
-    int* out = group + ((int64_t)c * S + s) * 32;
-    int cnt = 0, first = N;
-    // 64 source points per warp iteration: each lane tests points base+lane and base+32+lane with packed fp32x2 math
-    // (same IEEE operations as sqdist_expanded); the two 32-point halves are committed in index order
-    const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz), qn2 = make_float2(q2, q2);
-    const float2 m2 = make_float2(-2.0f, -2.0f);
-    for (int base = 0; base < N && cnt < 32; base += 64) {
-      const int p0 = base + lane, p1 = base + 32 + lane;
-      const float4 v0 = sp[p0 < N ? p0 : 0], v1 = sp[p1 < N ? p1 : 0];
-      float2 dot = __ffma2_rn(qz2, make_float2(v0.z, v1.z), __ffma2_rn(qy2, make_float2(v0.y, v1.y), __fmul2_rn(qx2, make_float2(v0.x, v1.x))));
-      float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(m2, dot), qn2), make_float2(v0.w, v1.w));
-      const bool in0 = p0 < N && !(d.x > r2), in1 = p1 < N && !(d.y > r2);
-      unsigned m = __ballot_sync(0xffffffffu, in0);
-      if (m) {
-        if (first == N) first = base + __ffs(m) - 1;
-        int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        if (in0 && pos < 32) out[pos] = p0;
-        cnt += __popc(m);
-      }
-      if (cnt < 32) {
-        m = __ballot_sync(0xffffffffu, in1);
-        if (m) {
-          if (first == N) first = base + 32 + __ffs(m) - 1;
-          int pos = cnt + __popc(m & ((1u << lane) - 1u));
-          if (in1 && pos < 32) out[pos] = p1;
-          cnt += __popc(m);
-        }
-      }
+  const int s = blockIdx.x * BQ_T + tid;
+  const bool valid = s < S;
+  const float* q = new_xyz + ((int64_t)c * S + (valid ? s : 0)) * 3;
+  const float qx = q[0], qy = q[1], qz = q[2];
+  const float q2 = sqnorm3(qx, qy, qz);
+  const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz), qn2 = make_float2(q2, q2);
+  int cnt = valid ? 0 : 32;
+  for (int i0 = 0; i0 < NP; i0 += 8) {
+    if (__all_sync(0xffffffffu, cnt >= 32)) break;  // every centroid of this warp has its 32 samples
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u;
+      const float2 d = sqdist2(qx2, qy2, qz2, qn2, sA[i], sB[i]);
+      if (!(d.x > r2) && cnt < 32) s_out[cnt++][tid] = 2 * i;
+      if (!(d.y > r2) && cnt < 32) s_out[cnt++][tid] = 2 * i + 1;
     }
-    if (cnt > 32) cnt = 32;
-    __syncwarp();
-    if (lane >= cnt) out[lane] = first;  // first == N only for an empty ball, which cannot happen (centroid is a source point)
+  }
+  if (valid) {
+    const int first = cnt > 0 ? s_out[0][tid] : N;  // an empty ball cannot happen (the centroid is a source point)
+    for (int k = cnt; k < 32; ++k) s_out[k][tid] = first;
+  }
+  __syncwarp();
+  // warp w owns centroids [32w, 32w+32) of the block: lane = sample slot, one 128-byte row per centroid
+  for (int j = 0; j < 32; ++j) {
+    const int sj = blockIdx.x * BQ_T + warp * 32 + j;
+    if (sj < S) group[((int64_t)c * S + sj) * 32 + lane] = s_out[lane][warp * 32 + j];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // 3-NN inverse-distance weights for feature propagation: for every fine point the 3 smallest
 // expanded-form distances to the S coarse points (ascending, lowest index on ties),
-// w_k = (1/(d_k+1e-8)) / sum_k (1/(d_k+1e-8)).  Two fine points per thread share each shared-memory load.
+// w_k = (1/(d_k+1e-8)) / sum_k (1/(d_k+1e-8)).  Two fine points (one fp32x2 pair) per thread share each broadcast load of a
+// coarse point.
 // ---------------------------------------------------------------------------------------------
 struct Top3 {
   float d0, d1, d2;
@@ -243,14 +257,17 @@ struct Top3 {
 __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                                                        int n_clouds, int N, int S, int* __restrict__ nn_idx,
                                                        float* __restrict__ nn_w) {
-  extern __shared__ float4 sp[];
+  extern __shared__ float4 sp[];  // per coarse point: (x, x, y, y) | (z, z, |p|^2, |p|^2)
   const int c = blockIdx.y;
   const float* src = xyz2 + (int64_t)c * S * 3;
   for (int p = threadIdx.x; p < S; p += blockDim.x) {
-    float x = src[p * 3], y = src[p * 3 + 1], z = src[p * 3 + 2];
-    sp[p] = make_float4(x, y, z, sqnorm3(x, y, z));
+    const float x = src[p * 3], y = src[p * 3 + 1], z = src[p * 3 + 2], w = sqnorm3(x, y, z);
+    sp[2 * p] = make_float4(x, x, y, y);
+    sp[2 * p + 1] = make_float4(z, z, w, w);
   }
   __syncthreads();
+  // two fine points per thread (one fp32x2 pair).  Each has its OWN insertion branch: an insertion happens ~3/s of the
+  // time at coarse point s, so a warp-level branch per query slot is skipped far more often than a shared one would be.
   const int stride = gridDim.x * blockDim.x;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += 2 * stride) {
     const int n2 = n + stride;
@@ -262,14 +279,9 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
     Top3 ta, tb;
     ta.init();
     tb.init();
-    // both queries against the same coarse point in packed fp32x2: identical IEEE operations to sqdist_expanded
-    // (fma(z, fma(y, x*x')), then (-2*dot + |q|^2) + |p|^2), two results per instruction
     const float2 qx2 = make_float2(ax, bx), qy2 = make_float2(ay, by), qz2 = make_float2(az, bz), qn2 = make_float2(a2, b2);
-    const float2 m2 = make_float2(-2.0f, -2.0f);
     for (int s = 0; s < S; ++s) {
-      const float4 v = sp[s];
-      float2 dot = __ffma2_rn(qz2, make_float2(v.z, v.z), __ffma2_rn(qy2, make_float2(v.y, v.y), __fmul2_rn(qx2, make_float2(v.x, v.x))));
-      float2 d = __fadd2_rn(__fadd2_rn(__fmul2_rn(m2, dot), qn2), make_float2(v.w, v.w));
+      const float2 d = sqdist2(qx2, qy2, qz2, qn2, sp[2 * s], sp[2 * s + 1]);
       ta.push(d.x, s);
       tb.push(d.y, s);
     }
@@ -289,11 +301,9 @@ int launch_fps4(const float* xyz0, const int64_t* start, int n_clouds, int* idx1
 int launch_ball_query(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group,
                       cudaStream_t st) {
   float r2 = (float)(radius * radius);  // python double r**2 compared in fp32 (torch scalar promotion)
-  int warps = 8;
-  int gx = (S + warps - 1) / warps;
-  if (gx > 16) gx = 16;
-  dim3 grid(gx, n_clouds);
-  ball_query_kernel<<<grid, warps * 32, N * sizeof(float4), st>>>(xyz, new_xyz, n_clouds, N, S, r2, group);
+  if (N & 15) return -1;  // the scan is unrolled over 8 point pairs
+  dim3 grid((S + BQ_T - 1) / BQ_T, n_clouds);
+  ball_query_kernel<<<grid, BQ_T, N * sizeof(float4) /* N/2 pairs x 2 float4 */, st>>>(xyz, new_xyz, n_clouds, N, S, r2, group);
   return 1;
 }
 
@@ -301,7 +311,7 @@ int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, i
                     cudaStream_t st) {
   int threads = N >= 512 ? 256 : 64;
   dim3 grid((N + 2 * threads - 1) / (2 * threads), n_clouds);  // two fine points per thread
-  three_nn_kernel<<<grid, threads, S * sizeof(float4), st>>>(xyz1, xyz2, n_clouds, N, S, nn_idx, nn_w);
+  three_nn_kernel<<<grid, threads, 2 * S * sizeof(float4), st>>>(xyz1, xyz2, n_clouds, N, S, nn_idx, nn_w);
   return 1;
 }
 

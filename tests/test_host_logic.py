@@ -155,3 +155,23 @@ def test_two_rank_sharding_plan_gloo():
         assert p.exitcode == 0
     g = golden("shard_wellcond")
     assert rel_l2(got, g["x0"]) < 2e-5
+
+
+def test_fps_kernel_has_no_contracted_fma():
+    """The FPS distance is (dx^2 + dy^2) + dz^2 with separately rounded products (reference pointnet2_utils.py:60-83).
+    ptxas contracts packed mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the rounding modifiers
+    (tools/probe/packed_fma_probe.cu), which silently changes 21 % of the distances; the kernel therefore adds in scalar.
+    Guard: the compiled FPS kernel must not contain any fused multiply-add."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lsdm_b200", "liblsdm_b200.so")
+    if not os.path.exists(cuobjdump) or not os.path.exists(lib):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    blocks = re.split(r"\n\s*Function : ", sass)
+    fps = [b for b in blocks if "fps4_kernel" in b.split("\n", 1)[0]]
+    assert fps, "fps4_kernel not found in the library"
+    for b in fps:
+        assert not re.search(r"\bFFMA2?\b", b), "FPS kernel contains a fused multiply-add (contracted mul+add)"
