@@ -100,6 +100,7 @@ struct lsdm_handle {
   void* allreduce_ctx = nullptr;  // running statistics changed (train-mode forward): re-fold before the next eval-mode encode
   float *head_w, *head_b;
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
+  std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
   int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
   int fp_fused = 0;              // 1: fused fp2 level (fine GEMM + interpolation + second conv in one kernel)
   std::vector<float> host_wx[2], host_wf[2], host_b1[2], host_b2[2];  // host copies for the v2 fused SA kernels (kernel params)
@@ -470,6 +471,16 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       coarse_feat = outs[l];
       continue;
     }
+    if (l == 3 && h->precision >= 1 && h->fp_tail && h->fp_fused) {  // fp1 + head: interpolation gathered inside the fused kernel
+      const double fl = 2.0 * C * N * 3.0 * 128 * 128;
+      int r = prof_launch(h, st, K_GEMM, [&] {
+        return launch_fp1_fused(w.tB, q.nn_idx[l], q.nn_w[l], h->host_fp1_b1.data(), h->fp_w[l][1], h->fp_w[l][2], h->head_w,
+                                h->host_tail.data(), C, N, S, w.backbone, st);
+      }, "fp1_fused", fl);
+      if (r < 0) return fail(LSDM_EINVAL, "fused fp1 kernel unavailable");
+      if (h->profiling) h->gemm_flops += fl;
+      continue;
+    }
     prof_launch(h, st, K_FPCOMB, [&] { return launch_fp_combine(Pa, h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l], C, N, S, C1, w.tP, h->precision == 1, st); });
     if (l < 3) {
       GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
@@ -769,6 +780,8 @@ LSDM_API int lsdm_finalize_weights(lsdm_handle* h, void* stream) {
     CK(cudaMemcpyAsync(h->host_b1[l].data(), h->sa_b[l][0], sizeof(float) * C1, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->host_b2[l].data(), h->sa_b[l][1], sizeof(float) * C2, cudaMemcpyDeviceToHost, st));
   }
+  h->host_fp1_b1.resize(128);
+  CK(cudaMemcpyAsync(h->host_fp1_b1.data(), h->fp_b[3][0], sizeof(float) * 128, cudaMemcpyDeviceToHost, st));
   h->host_tail.resize(771);
   CK(cudaMemcpyAsync(h->host_tail.data(), h->fp_b[3][1], sizeof(float) * 128, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h->host_tail.data() + 128, h->fp_b[3][2], sizeof(float) * 128, cudaMemcpyDeviceToHost, st));

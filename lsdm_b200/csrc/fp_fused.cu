@@ -250,6 +250,225 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused LAST level + head (reference pointnet2_utils.py:290-311, pointnet2.py:71-79): fp1 has no fine-level features, so
+//   h0 = ReLU(b1 + sum_k w_k . Pb[nn_k])  ->  W2 -> ReLU -> W3 -> ReLU -> Wh (conv1 + bn1) -> ReLU -> conv2 (128 -> 3)
+// for 128 rows per tile; only the [rows, 3] result leaves the SM.  Same thread roles as fp_fused_kernel (coalesced
+// 3-neighbour gather by all warps -> swizzled shared tile -> row threads), then three A-from-TMEM MMAs ping-ponging between
+// two 128-column TMEM regions with in-place epilogues; the three 128x128 weight matrices stay resident in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+struct Fp1Const {
+  float b1[128], b2[128], b3[128], bh[128];
+  float wc[3 * 128];
+  float bc[3];
+};
+template <int V>
+struct IntK { static constexpr int value = V; };
+
+__global__ void __launch_bounds__(256, 1) fp1_fused_kernel(const float* __restrict__ Pb, const int* __restrict__ nn_idx,
+                                                           const float* __restrict__ nn_w, const float* __restrict__ W2,
+                                                           const float* __restrict__ W3, const float* __restrict__ Wh,
+                                                           float* __restrict__ out, int n_tiles, int S, int n_shift,
+                                                           const __grid_constant__ Fp1Const k) {
+  constexpr int WB = 128 * 128 * 4;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rit = tid & 127, wq = warp & 3, half = tid >> 7;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW[3] = {base, base + WB, base + 2 * WB};
+  float* stage = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + 3 * WB);  // 2 x [128][32] floats
+  const uint32_t bar = smem_u32(&s_bar);
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 256);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  const float* Ws[3] = {W2, W3, Wh};
+  for (int m = 0; m < 3; ++m)
+    for (int q = tid; q < 128 * 128 / 4; q += 256) {
+      int n = q >> 5, k4 = q & 31;
+      float4 v = *reinterpret_cast<const float4*>(Ws[m] + (int64_t)n * 128 + k4 * 4);
+      st_shared_v4(sW[m] + (k4 >> 3) * (128 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+    }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+  constexpr uint32_t idesc = umma_idesc_tf32(128, 128);
+
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = (t0 + per < n_tiles) ? t0 + per : n_tiles;
+  const int lr0 = tid >> 3, lc4 = tid & 7;
+
+  auto run = [&](auto HC) {
+    constexpr int H = decltype(HC)::value;  // this thread's column half, a compile-time constant of the code path so that
+                                            // the per-channel vectors stay constant-bank operands
+    uint32_t phase = 0;
+    auto mma_layer = [&](int m, uint32_t col_a, uint32_t col_d) {
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t db = umma_desc_sw128(sW[m] + kb * (128 * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32_ts(tmem + col_d, tmem + col_a + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    };
+    // loader state: neighbour row pointers / weights of tile rows lr0 + 32 i, and the gathered float4s of one step
+    const float* gp[4][3];
+    float gw[4][3];
+    float4 nb[2][4][3];
+    auto load_nbrs = [&](int tile) {
+      if (tile < t1) {
+        const int64_t cbase = (((int64_t)tile * 128) >> n_shift) * S;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t r = (int64_t)tile * 128 + lr0 + 32 * i;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            gp[i][j] = Pb + (cbase + nn_idx[r * 3 + j]) * 128 + lc4 * 4;
+            gw[i][j] = nn_w[r * 3 + j];
+          }
+        }
+      }
+    };
+    auto gather = [&](int s) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) nb[hh][i][j] = *reinterpret_cast<const float4*>(gp[i][j] + (hh * 2 + s) * 32);
+    };
+    load_nbrs(t0);
+    if (t0 < t1) gather(0);
+    for (int tile = t0; tile < t1; ++tile) {
+      const int64_t row = (int64_t)tile * 128 + rit;
+      // ---- h0 = ReLU(b1 + interpolation) -> TF32 -> TMEM columns [0,128): two steps of 32 columns per column half ----
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 x0 = nb[hh][i][0], x1 = nb[hh][i][1], x2 = nb[hh][i][2];
+            const float w0 = gw[i][0], w1 = gw[i][1], w2 = gw[i][2];
+            float4 o;
+            o.x = fmaf(x2.x, w2, fmaf(x1.x, w1, x0.x * w0));
+            o.y = fmaf(x2.y, w2, fmaf(x1.y, w1, x0.y * w0));
+            o.z = fmaf(x2.z, w2, fmaf(x1.z, w1, x0.z * w0));
+            o.w = fmaf(x2.w, w2, fmaf(x1.w, w1, x0.w * w0));
+            const int r = lr0 + 32 * i;
+            *reinterpret_cast<float4*>(stage + hh * (128 * 32) + r * 32 + ((lc4 ^ (r & 7)) << 2)) = o;
+          }
+        __syncthreads();
+        if (s == 0) {
+          gather(1);
+        } else {
+          load_nbrs(tile + 1);               // the next tile's first step travels during this tile's three MMAs
+          if (tile + 1 < t1) gather(0);
+        }
+        uint32_t v[32];
+        const float* srow = stage + H * (128 * 32) + rit * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 it = *reinterpret_cast<const float4*>(srow + ((q ^ (rit & 7)) << 2));
+          const int c = (H * 2 + s) * 32 + q * 4;
+          v[q * 4 + 0] = rna_tf32_mma(fmaxf(k.b1[c + 0] + it.x, 0.0f));
+          v[q * 4 + 1] = rna_tf32_mma(fmaxf(k.b1[c + 1] + it.y, 0.0f));
+          v[q * 4 + 2] = rna_tf32_mma(fmaxf(k.b1[c + 2] + it.z, 0.0f));
+          v[q * 4 + 3] = rna_tf32_mma(fmaxf(k.b1[c + 3] + it.w, 0.0f));
+        }
+        tmem_st32(tlane + (H * 2 + s) * 32, v);
+        if (s == 0) __syncthreads();  // the staging tiles are rewritten by step 1 (the barrier below covers step 1)
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncthreads();
+      mma_layer(0, 0, 128);  // Y = h0 . W2^T
+#pragma unroll
+      for (int kl = 0; kl < 2; ++kl) {
+        constexpr int KB0 = H * 2;
+        const int kb = KB0 + kl;
+        uint32_t v[32];
+        tmem_ld32(tlane + 128 + kb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = rna_tf32_mma(fmaxf(__uint_as_float(v[e]) + k.b2[kb * 32 + e], 0.0f));
+        tmem_st32(tlane + 128 + kb * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncthreads();
+      mma_layer(1, 128, 0);  // X = Y . W3^T
+#pragma unroll
+      for (int kl = 0; kl < 2; ++kl) {
+        constexpr int KB0 = H * 2;
+        const int kb = KB0 + kl;
+        uint32_t v[32];
+        tmem_ld32(tlane + kb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = rna_tf32_mma(fmaxf(__uint_as_float(v[e]) + k.b3[kb * 32 + e], 0.0f));
+        tmem_st32(tlane + kb * 32, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncthreads();
+      mma_layer(2, 0, 128);  // Y = X . Wh^T   (conv1 with bn1 folded)
+      // ---- head: relu(Y + bh) . conv2^T + bc (128 -> 3), fp32 CUDA cores; the two column halves meet in shared memory ----
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+      for (int kl = 0; kl < 2; ++kl) {
+        constexpr int KB0 = H * 2;
+        const int kb = KB0 + kl;
+        uint32_t v[32];
+        tmem_ld32(tlane + 128 + kb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int ch = kb * 32 + e;
+          const float x = fmaxf(__uint_as_float(v[e]) + k.bh[ch], 0.0f);
+          o0 = fmaf(k.wc[ch], x, o0);
+          o1 = fmaf(k.wc[128 + ch], x, o1);
+          o2 = fmaf(k.wc[256 + ch], x, o2);
+        }
+      }
+      if (H == 1) {
+        stage[rit * 4 + 0] = o0;
+        stage[rit * 4 + 1] = o1;
+        stage[rit * 4 + 2] = o2;
+      }
+      tc_fence_before();
+      __syncthreads();
+      if (H == 0) {
+        out[row * 3 + 0] = (o0 + stage[rit * 4 + 0]) + k.bc[0];
+        out[row * 3 + 1] = (o1 + stage[rit * 4 + 1]) + k.bc[1];
+        out[row * 3 + 2] = (o2 + stage[rit * 4 + 2]) + k.bc[2];
+      }
+      __syncthreads();  // the next tile's loaders rewrite the staging tiles
+    }
+  };
+  if (half == 0) {
+    run(IntK<0>{});
+  } else {
+    run(IntK<1>{});
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace
 
 // fp2 of the reference backbone: CA = 64 (l1 features), C1 = 256, C2 = 128; N (fine points per cloud) must be a power of
@@ -270,6 +489,39 @@ int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, co
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = sms < a.n_tiles ? sms : a.n_tiles;
   fp_fused_kernel<64, 256, 128><<<grid, 256, smem, st>>>(a);
+  return 1;
+}
+
+}  // namespace lsdm
+
+namespace lsdm {
+
+// fp1 + head.  h_consts: host copy of [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)] (as launch_fp1_tail);
+// h_b1: host copy of the first conv's folded bias [128].  N (points per cloud) must be a power of two and a multiple of 128.
+int launch_fp1_fused(const float* Pb, const int* nn_idx, const float* nn_w, const float* h_b1, const float* W2, const float* W3,
+                     const float* Wh, const float* h_consts, int n_clouds, int N, int S, float* out, cudaStream_t st) {
+  if (N < 128 || (N & (N - 1)) != 0) return -1;
+  Fp1Const k;
+  for (int i = 0; i < 128; ++i) {
+    k.b1[i] = h_b1[i];
+    k.b2[i] = h_consts[i];
+    k.b3[i] = h_consts[128 + i];
+    k.bh[i] = h_consts[256 + i];
+  }
+  for (int i = 0; i < 384; ++i) k.wc[i] = h_consts[384 + i];
+  for (int i = 0; i < 3; ++i) k.bc[i] = h_consts[768 + i];
+  constexpr int smem = 3 * 128 * 128 * 4 + 2 * 128 * 32 * 4 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(fp1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_tiles = n_clouds * (N / 128);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  fp1_fused_kernel<<<grid, 256, smem, st>>>(Pb, nn_idx, nn_w, W2, W3, Wh, out, n_tiles, S, __builtin_ctz(N), k);
   return 1;
 }
 

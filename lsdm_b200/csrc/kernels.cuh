@@ -46,6 +46,10 @@ int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, co
                     const float* W1, const float* b1, int n_clouds, int N, int S, int C1, int C2, float* out, int round_out,
                     cudaStream_t st);
 
+// fused last level + head: fp1 (interpolation gathered in-kernel, 3 x 128x128 convs) + conv2; h_b1 / h_consts are HOST arrays
+int launch_fp1_fused(const float* Pb, const int* nn_idx, const float* nn_w, const float* h_b1, const float* W2, const float* W3,
+                     const float* Wh, const float* h_consts, int n_clouds, int N, int S, float* out, cudaStream_t st);
+
 // fused tail of the backbone: fp1 layers 2-3 + conv1/bn1 head + conv2, TF32 tensor cores; h_consts is a HOST array
 // [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]
 int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const float* Wh, const float* h_consts, int64_t rows,

@@ -270,6 +270,42 @@ def test_full_batch_sharding_and_determinism():
     assert rel_l2(hoisted.cpu(), strict_same.cpu()) < 1e-6            # (iii)
 
 
+def test_full_batch_selections_bit_exact_vs_oracle():
+    """B=64 (576 clouds): every FPS index of all four levels, and the ball-query groups / 3-NN indices of a bounded sample of
+    clouds, against the oracle's selection functions.  One-ulp changes in the distance arithmetic (e.g. a contracted
+    multiply-add) flip an argmax only on near-ties, about once per 10^6 rounds -- too rare for the 27-cloud stage tests,
+    but 576 clouds x 1360 rounds see it."""
+    B = 64
+    C = B * 9
+    m, _ = _model("wellcond")
+    inp = syn.make_inputs(31, B)
+    fps, _ = syn.make_step_randoms(32, B, 1)
+    g = _cuda(inp)
+    x = g["x_T"].clone()
+    with injected_rng(fps_starts=list(fps[0])):
+        m(x, g["mask"], torch.full((B,), 500, device="cuda"), g["given_objs"], g["given_cats"], g["text_emb"])
+    eng = m._engine
+    xyz = inp["given_objs"].reshape(C, 1024, 3)
+    sub = torch.cat([torch.arange(0, 24), torch.arange(C - 24, C)])      # clouds checked for ball query / 3-NN
+    present = (xyz.abs().sum((1, 2)) > 0)
+    xyzs = [xyz]
+    for lvl, (npnt, radius) in enumerate(((1024, 0.1), (256, 0.2), (64, 0.4), (16, 0.8))):
+        ref_idx = O.farthest_point_sample(xyzs[-1], npnt, fps[0][lvl])
+        got = eng.debug_tensor(f"fps_idx{lvl}", torch.int32).view(C, npnt).cpu().long()
+        assert torch.equal(got, ref_idx), f"fps level {lvl}: {(got != ref_idx).sum().item()} of {got.numel()} indices differ"
+        new_xyz = O._gather(xyzs[-1], ref_idx)
+        ref_grp = O.ball_query(radius, 32, xyzs[-1][sub], new_xyz[sub])
+        got = eng.debug_tensor(f"ball_idx{lvl}", torch.int32).view(C, npnt, 32).cpu().long()[sub]
+        assert torch.equal(got, ref_grp), f"ball query level {lvl}"
+        xyzs.append(new_xyz)
+    for name, fine, coarse, n in (("nn_idx0", 3, 4, 64), ("nn_idx3", 0, 1, 1024)):
+        d = O.square_distance(xyzs[fine][sub], xyzs[coarse][sub])
+        ref_nn = torch.topk(d, 3, dim=-1, largest=False, sorted=True)[1]
+        got = eng.debug_tensor(name, torch.int32).view(C, n, 3).cpu().long()[sub]
+        ok = present[sub]
+        assert torch.equal(got[ok], ref_nn[ok]), name
+
+
 def test_config3_ddim100_respaced_vs_oracle():
     """BASELINE config 3 schedule ('ddim100' respacing, ancestral sampler -- the only respaced sampler alive in the reference),
     last 3 of the 100 steps, batch 2, against the oracle."""
