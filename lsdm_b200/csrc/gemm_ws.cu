@@ -238,7 +238,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
         tmem_ld32(tl + (uint32_t)c0, v);
         tmem_ld_wait();
         float f[32];
-        epi_chunk(f, v, rbias, g.bias_mode == 1 ? &s_bias[n0 + c0] : nullptr, g.act, g.round_out);
+        // group max: ReLU (and the TF32 rounding) commute with the max, so they are applied to the 1 pooled value per lane
+        // instead of the 32 accumulator values
+        epi_chunk(f, v, rbias, g.bias_mode == 1 ? &s_bias[n0 + c0] : nullptr, g.group_max ? (int)ACT_NONE : g.act,
+                  g.group_max ? 0 : g.round_out);
         if (SPLIT && g.C_lo != nullptr) {
           // the consumer is another 3xTF32 GEMM: store x as its hi and lo planes (two passes through the staging tile)
           float* __restrict__ Cl = g.C_lo + (int64_t)z * g.strideC;
@@ -266,14 +269,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
             __syncwarp();
           }
         } else if (g.group_max) {
-          uint32_t res = 0;
+          // max of the biased values as SIGNED integers: exact whenever the true maximum is >= 0, some negative value
+          // otherwise -- which the ReLU maps to the same 0
+          int res = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(f[j]));
+            const int mx = __reduce_max_sync(0xffffffffu, __float_as_int(f[j]));
             if (lane == j) res = mx;
           }
+          float r = fmaxf(__int_as_float(res), 0.0f);
+          if (g.round_out) r = tf32_round_fin(r);
           const int gm = (m0 >> 5) + q4;
-          if (gm < (g.M >> 5)) C[(int64_t)gm * g.ldc + n0 + c0 + lane] = __uint_as_float(res);
+          if (gm < (g.M >> 5)) C[(int64_t)gm * g.ldc + n0 + c0 + lane] = r;
         } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q)

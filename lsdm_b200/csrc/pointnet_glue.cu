@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
                                                         const float* __restrict__ xyz, const float* __restrict__ new_xyz,
                                                         const int* __restrict__ group, int64_t rows, int N, int S, int C1,
                                                         float* __restrict__ h1, int round_out, int apply_relu) {
-  extern __shared__ float sw[];  // Wx[C1][3] (+ Wf3[C1][3] + bias[C1] when P == nullptr)
+  extern __shared__ __align__(16) float sw[];  // Wx[C1][3] (+ Wf3[C1][3] + bias[C1] when P == nullptr)
   for (int i = threadIdx.x; i < C1 * 3; i += blockDim.x) sw[i] = Wx[i];
   if (P == nullptr) {
     for (int i = threadIdx.x; i < C1 * 3; i += blockDim.x) sw[C1 * 3 + i] = Wf3[i];
@@ -37,14 +37,20 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
     float rx = jx - pc[0], ry = jy - pc[1], rz = jz - pc[2];
     float* out = h1 + row * C1;
     if (P != nullptr) {
+      // 128-bit accesses: a lane owns 4 consecutive channels per iteration (C1 is a multiple of 128 here)
       const float* prow = P + (c * N + j) * C1;
-      for (int ch = lane; ch < C1; ch += 32) {
-        float v = prow[ch];
-        v = fmaf(sw[ch * 3 + 0], rx, v);
-        v = fmaf(sw[ch * 3 + 1], ry, v);
-        v = fmaf(sw[ch * 3 + 2], rz, v);
-        if (apply_relu) v = fmaxf(v, 0.0f);
-        out[ch] = round_out ? tc::rna_tf32(v) : v;
+      for (int c4 = lane; c4 < (C1 >> 2); c4 += 32) {
+        const float4 p = *reinterpret_cast<const float4*>(prow + c4 * 4);
+        const float4 wa = *reinterpret_cast<const float4*>(sw + c4 * 12), wb = *reinterpret_cast<const float4*>(sw + c4 * 12 + 4),
+                     wc = *reinterpret_cast<const float4*>(sw + c4 * 12 + 8);  // Wx rows of channels 4 c4 .. 4 c4 + 3
+        float r[4] = {fmaf(wa.z, rz, fmaf(wa.y, ry, fmaf(wa.x, rx, p.x))), fmaf(wb.y, rz, fmaf(wb.x, ry, fmaf(wa.w, rx, p.y))),
+                      fmaf(wc.x, rz, fmaf(wb.w, ry, fmaf(wb.z, rx, p.z))), fmaf(wc.w, rz, fmaf(wc.z, ry, fmaf(wc.y, rx, p.w)))};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (apply_relu) r[e] = fmaxf(r[e], 0.0f);
+          if (round_out) r[e] = tc::rna_tf32(r[e]);
+        }
+        *reinterpret_cast<float4*>(out + c4 * 4) = make_float4(r[0], r[1], r[2], r[3]);
       }
     } else {
       for (int ch = lane; ch < C1; ch += 32) {
