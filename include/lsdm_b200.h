@@ -150,6 +150,31 @@ LSDM_API int lsdm_chamfer(lsdm_handle* h, const float* x, const float* y, int32_
  * sum_b CrossEntropy(probs[b,:] treated as logits, argmax(target_cat[b,:])) accumulated into *sum. */
 LSDM_API int lsdm_cat_loss(lsdm_handle* h, const float* probs, const float* target_cat, int32_t batch, float* sum, void* stream);
 
+/* ---- Evaluation metrics of the sampling path (reference run/test_sdm.py:186-207).  Handle-free. ----
+ *
+ * lsdm_eval_emd replaces util/evaluation.py:5-11 `emd(x, y)` = scipy cdist + linear_sum_assignment: for each of `batch`
+ * cloud pairs x[b,n,3], y[b,m,3] (n == m <= 1024) the mean Euclidean distance of the minimum-cost perfect matching, as a
+ * double in emd[batch].  Device algorithm: epsilon-scaled forward auction on integer-scaled distances (deterministic); the
+ * matching's cost is within 2^-26 x (cloud extent) per point of the optimum.  assignment[batch,n] (nullable) receives the
+ * matched y index of every x point, rounds[batch] (nullable) the number of bidding rounds.  A sample whose auction
+ * does not terminate within the round cap reports NaN. */
+LSDM_API int lsdm_eval_emd(const float* x, const float* y, int32_t batch, int32_t n, int32_t m, double* emd, int32_t* assignment,
+                           int32_t* rounds, void* stream);
+
+/* Replaces util/evaluation.py:28-52 `calculate_fscore(gt, pr, th)` (open3d nearest-neighbour distances both ways, double):
+ * out[batch,3] = {fscore, precision, recall}; counts[batch,2] is int32 scratch.  n, m <= 4096. */
+LSDM_API int lsdm_eval_fscore(const float* gt, const float* pr, int32_t batch, int32_t n, int32_t m, double th, int32_t* counts,
+                              double* out, void* stream);
+
+/* pytorch3d.loss.chamfer_distance as called per sample at run/test_sdm.py:187: per_sample[batch,2] = the two directed
+ * point-mean squared-NN terms of each pair (their sum is the reference's `loss` at batch 1). */
+LSDM_API int lsdm_eval_chamfer(const float* x, const float* y, int32_t batch, int32_t n, int32_t m, float* per_sample, void* stream);
+
+/* Replaces util/evaluation.py:13-26 `accuracy(output, target, topk)`: correct[k] = number of samples whose target class
+ * (int64) is among the ks[k] highest of scores[batch,n_classes] (ks: device int32[nk]; ties ordered by class index). */
+LSDM_API int lsdm_eval_topk(const float* scores, const int64_t* target, int32_t batch, int32_t n_classes, const int32_t* ks, int32_t nk,
+                            int32_t* correct, void* stream);
+
 /* Debug / parity taps: copy a named intermediate of the last encode/forward into `dst` (device).
  * Returns the element count, or a negative error.  Names: "backbone" [9Bl,1024,3], "hm" [Bl,1024,3],
  * "attn_w" [Bl,9], "tr" [Bl,9,12], "enc" [Bl,128], "pa" [Bl,9,12], "pw" [Bl,9,1024,3], "emb" [Bl,1024,128],

@@ -53,6 +53,10 @@ PROTOTYPES = {
     "lsdm_q_sample": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lsdm_chamfer": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lsdm_cat_loss": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
+    "lsdm_eval_emd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "lsdm_eval_fscore": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P]),
+    "lsdm_eval_chamfer": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "lsdm_eval_topk": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "lsdm_debug_tensor": (C.c_int64, [_P, C.c_char_p, _P, C.c_size_t, _P]),
     "lsdm_launch_count": (C.c_int64, [_P]),
     "lsdm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),

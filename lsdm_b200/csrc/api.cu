@@ -1079,6 +1079,45 @@ LSDM_API int lsdm_chamfer(lsdm_handle* h, const float* x, const float* y, int32_
   return LSDM_OK;
 }
 
+// ---- evaluation metrics (handle-free: they use no weights and no workspace beyond what the caller passes) ----
+LSDM_API int lsdm_eval_emd(const float* x, const float* y, int32_t batch, int32_t n, int32_t m, double* emd, int32_t* assignment,
+                           int32_t* rounds, void* stream) {
+  if (!x || !y || !emd || batch <= 0) return fail(LSDM_EINVAL, "bad argument");
+  if (n != m) return fail(LSDM_EINVAL, "lsdm_eval_emd: clouds must have the same number of points (perfect matching)");
+  if (n < 1 || n > 1024) return fail(LSDM_EINVAL, "lsdm_eval_emd: 1 <= n <= 1024");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (launch_emd(x, y, batch, n, emd, assignment, rounds, st) < 0) return fail(LSDM_ECUDA, "emd launch");
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_eval_fscore(const float* gt, const float* pr, int32_t batch, int32_t n, int32_t m, double th, int32_t* counts,
+                              double* out, void* stream) {
+  if (!gt || !pr || !counts || !out || batch <= 0 || n <= 0 || m <= 0 || n > 4096 || m > 4096) return fail(LSDM_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (launch_fscore(gt, pr, batch, n, m, th, counts, out, st) < 0) return fail(LSDM_EINVAL, "fscore launch");
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_eval_chamfer(const float* x, const float* y, int32_t batch, int32_t n, int32_t m, float* per_sample, void* stream) {
+  if (!x || !y || !per_sample || batch <= 0 || n <= 0 || m <= 0 || n > 4096 || m > 4096) return fail(LSDM_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(per_sample, 0, sizeof(float) * 2 * batch, st));
+  launch_chamfer(x, y, batch, n, m, per_sample, st, 2);
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_eval_topk(const float* scores, const int64_t* target, int32_t batch, int32_t n_classes, const int32_t* ks, int32_t nk,
+                            int32_t* correct, void* stream) {
+  if (!scores || !target || !ks || !correct || batch <= 0 || n_classes <= 0 || nk <= 0) return fail(LSDM_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_topk(scores, target, batch, n_classes, ks, nk, correct, st);
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
 LSDM_API int lsdm_cat_loss(lsdm_handle* h, const float* probs, const float* target_cat, int32_t batch, float* sum, void* stream) {
   if (!h || !probs || !target_cat || !sum || batch <= 0) return fail(LSDM_EINVAL, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;

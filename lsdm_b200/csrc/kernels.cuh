@@ -114,7 +114,16 @@ int launch_q_sample(const float* x0, const int64_t* t, const float* noise, const
                     float* xt, cudaStream_t st);
 
 // ---- loss.cu --------------------------------------------------------------------------------
-int launch_chamfer(const float* x, const float* y, int B, int n, int m, float* sums, cudaStream_t st);
+int launch_chamfer(const float* x, const float* y, int B, int n, int m, float* sums, cudaStream_t st, int sample_stride = 0);
 int launch_cat_loss(const float* probs, const float* target, int B, int C, float* sum, cudaStream_t st);
+
+// ---- eval_metrics.cu ------------------------------------------------------------------------
+// EMD (min-cost perfect matching, auction algorithm) of x[B,n,3] vs y[B,n,3], n <= 1024: out_emd[B] (double) = mean matched distance
+int launch_emd(const float* x, const float* y, int B, int n, double* out_emd, int* out_assign /*nullable [B,n]*/,
+               int* out_rounds /*nullable [B]*/, cudaStream_t st);
+// out[B,3] (double) = {fscore, precision, recall} at threshold th; counts[B,2] int scratch
+int launch_fscore(const float* gt, const float* pr, int B, int n, int m, double th, int* counts, double* out, cudaStream_t st);
+// correct[k] = number of samples whose target class is within the top ks[k] scores
+int launch_topk(const float* out, const int64_t* target, int B, int C, const int* ks, int nk, int* correct, cudaStream_t st);
 
 }  // namespace lsdm

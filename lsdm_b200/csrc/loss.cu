@@ -10,9 +10,9 @@ namespace lsdm {
 namespace {
 
 // grid (ceil(n/256), B, 2): z = 0 -> for each x_i min_j |x_i - y_j|^2 ; z = 1 -> roles swapped.
-// sums[z] += (1/n_z) * sum_i min  (atomic per CTA)
+// sums[b * sample_stride + z] += (1/n_z) * sum_i min  (atomic per CTA; sample_stride 0 = batch total, 2 = per sample)
 __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ x, const float* __restrict__ y, int n,
-                                                      int m, float* __restrict__ sums) {
+                                                      int m, float* __restrict__ sums, int sample_stride) {
   extern __shared__ float sm[];  // other cloud, xyz interleaved -> SoA
   const int dir = blockIdx.z, b = blockIdx.y;
   const float* a = dir == 0 ? x + (int64_t)b * n * 3 : y + (int64_t)b * m * 3;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_part[k];
-    atomicAdd(&sums[dir], tot / (float)na);
+    atomicAdd(&sums[b * sample_stride + dir], tot / (float)na);
   }
 }
 
@@ -70,10 +70,10 @@ __global__ void cat_loss_kernel(const float* __restrict__ probs, const float* __
 
 }  // namespace
 
-int launch_chamfer(const float* x, const float* y, int B, int n, int m, float* sums, cudaStream_t st) {
+int launch_chamfer(const float* x, const float* y, int B, int n, int m, float* sums, cudaStream_t st, int sample_stride) {
   int big = n > m ? n : m;
   dim3 grid((big + 255) / 256, B, 2);
-  chamfer_kernel<<<grid, 256, 3 * big * sizeof(float), st>>>(x, y, n, m, sums);
+  chamfer_kernel<<<grid, 256, 3 * big * sizeof(float), st>>>(x, y, n, m, sums, sample_stride);
   return 1;
 }
 
