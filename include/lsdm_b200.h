@@ -175,6 +175,34 @@ LSDM_API int lsdm_eval_chamfer(const float* x, const float* y, int32_t batch, in
 LSDM_API int lsdm_eval_topk(const float* scores, const int64_t* target, int32_t batch, int32_t n_classes, const int32_t* ks, int32_t nk,
                             int32_t* correct, void* stream);
 
+/* ---- CLIP text tower ------------------------------------------------------------------
+ * Replaces `clip_model.encode_text(tokens).float()` of model/sdm.py:245-259 (openai/CLIP `CLIP.encode_text`, ViT-B/32 text
+ * side: 12 pre-LN causal transformer blocks of width 512, 8 heads, QuickGELU MLP, ln_final, EOT-token feature times
+ * text_projection).  Tokenisation (clip.tokenize: BPE on the host) stays with the caller: `tokens` is its output.
+ *
+ * A separate handle: the tower is frozen and independent of the denoiser's weights.  Weight keys are the openai/CLIP
+ * state-dict names WITHOUT the reference's `clip_model.` prefix: token_embedding.weight [V,W], positional_embedding [ctx,W],
+ * transformer.resblocks.<l>.{ln_1,ln_2}.{weight,bias}, .attn.in_proj_{weight,bias}, .attn.out_proj.{weight,bias},
+ * .mlp.c_fc.{weight,bias}, .mlp.c_proj.{weight,bias}, ln_final.{weight,bias}, text_projection [W,E]; fp32, host or device
+ * pointers.  The configuration (width, layers, heads = W/64, context, vocabulary, embed dim) is inferred from the shapes at
+ * lsdm_clip_finalize, which fails if any tensor is missing.  The handle owns its weight copies (cudaMalloc). */
+typedef struct lsdm_clip lsdm_clip;
+LSDM_API int lsdm_clip_create(lsdm_clip** out, int32_t device);
+LSDM_API void lsdm_clip_destroy(lsdm_clip* h);
+LSDM_API int lsdm_clip_load_weight(lsdm_clip* h, const char* key, const float* data, const int64_t* shape, int32_t ndim, void* stream);
+LSDM_API int lsdm_clip_finalize(lsdm_clip* h);
+LSDM_API int lsdm_clip_dims(const lsdm_clip* h, int32_t* width, int32_t* layers, int32_t* heads, int32_t* ctx, int32_t* vocab, int32_t* embed);
+/* Dense-layer arithmetic: 0 fp32 CUDA cores, 1 TF32 tcgen05, 2 3xTF32 tcgen05 (default; fp32-grade accuracy). */
+LSDM_API int lsdm_clip_set_precision(lsdm_clip* h, int32_t precision);
+LSDM_API size_t lsdm_clip_workspace_bytes(const lsdm_clip* h, int32_t batch, int32_t seq_len);
+/* tokens: device int32 [batch, ctx] (zero-padded after the EOT token, which carries the largest id: clip.tokenize's layout);
+ * out: device fp32 [batch, embed].  Only positions [0, seq_len) are computed -- attention is causal, so this is bit-identical
+ * to the full context as long as every sample's EOT position is < seq_len (a sample that violates this gets NaN).
+ * Enqueues on `stream`, no synchronisation; workspace (256-byte aligned) of lsdm_clip_workspace_bytes(batch, seq_len). */
+LSDM_API int lsdm_clip_encode_text(lsdm_clip* h, const int32_t* tokens, int32_t batch, int32_t seq_len, void* workspace, size_t workspace_bytes,
+                                   float* out, void* stream);
+LSDM_API int64_t lsdm_clip_launch_count(const lsdm_clip* h);
+
 /* Debug / parity taps: copy a named intermediate of the last encode/forward into `dst` (device).
  * Returns the element count, or a negative error.  Names: "backbone" [9Bl,1024,3], "hm" [Bl,1024,3],
  * "attn_w" [Bl,9], "tr" [Bl,9,12], "enc" [Bl,128], "pa" [Bl,9,12], "pw" [Bl,9,1024,3], "emb" [Bl,1024,128],

@@ -57,6 +57,15 @@ PROTOTYPES = {
     "lsdm_eval_fscore": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P]),
     "lsdm_eval_chamfer": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lsdm_eval_topk": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
+    "lsdm_clip_create": (C.c_int, [C.POINTER(_P), C.c_int32]),
+    "lsdm_clip_destroy": (None, [_P]),
+    "lsdm_clip_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int32, _P]),
+    "lsdm_clip_finalize": (C.c_int, [_P]),
+    "lsdm_clip_dims": (C.c_int, [_P] + [C.POINTER(C.c_int32)] * 6),
+    "lsdm_clip_set_precision": (C.c_int, [_P, C.c_int32]),
+    "lsdm_clip_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
+    "lsdm_clip_encode_text": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_size_t, _P, _P]),
+    "lsdm_clip_launch_count": (C.c_int64, [_P]),
     "lsdm_debug_tensor": (C.c_int64, [_P, C.c_char_p, _P, C.c_size_t, _P]),
     "lsdm_launch_count": (C.c_int64, [_P]),
     "lsdm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),

@@ -25,6 +25,13 @@ int fail(int code, const std::string& msg) {
       return fail(LSDM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                      \
   } while (0)
 
+}  // namespace
+// error channel shared with the other translation units that export C ABI functions (clip_text.cu)
+namespace lsdm {
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace lsdm
+namespace {
+
 struct WEntry {
   std::string key;
   std::vector<int64_t> shape;

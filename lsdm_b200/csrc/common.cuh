@@ -14,7 +14,7 @@ constexpr int CATEMB = 32;
 constexpr int TRANS = 12;
 constexpr int NHEAD = 8;
 
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SILU = 4 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SILU = 4, ACT_QGELU = 5 /* x sigmoid(1.702 x), CLIP */ };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -25,6 +25,7 @@ __device__ __forceinline__ float apply_act(float x) {
   if (ACT == ACT_GELU) return gelu_erf(x);
   if (ACT == ACT_SIGMOID) return sigmoidf_(x);
   if (ACT == ACT_SILU) return x * sigmoidf_(x);
+  if (ACT == ACT_QGELU) return x * sigmoidf_(1.702f * x);
   return x;
 }
 
@@ -34,6 +35,7 @@ __device__ __forceinline__ float apply_act_rt(float x, int act) {
     case ACT_GELU: return gelu_erf(x);
     case ACT_SIGMOID: return sigmoidf_(x);
     case ACT_SILU: return x * sigmoidf_(x);
+    case ACT_QGELU: return x * sigmoidf_(1.702f * x);
     default: return x;
   }
 }
@@ -73,7 +75,9 @@ __device__ __forceinline__ void epi_chunk(float (&f)[32], const uint32_t (&v)[32
     case ACT_SIGMOID * 2: epi_chunk_t<ACT_SIGMOID, false>(f, v, rbias, cbias); break;
     case ACT_SIGMOID * 2 + 1: epi_chunk_t<ACT_SIGMOID, true>(f, v, rbias, cbias); break;
     case ACT_SILU * 2: epi_chunk_t<ACT_SILU, false>(f, v, rbias, cbias); break;
-    default: epi_chunk_t<ACT_SILU, true>(f, v, rbias, cbias); break;
+    case ACT_SILU * 2 + 1: epi_chunk_t<ACT_SILU, true>(f, v, rbias, cbias); break;
+    case ACT_QGELU * 2: epi_chunk_t<ACT_QGELU, false>(f, v, rbias, cbias); break;
+    default: epi_chunk_t<ACT_QGELU, true>(f, v, rbias, cbias); break;
   }
 }
 

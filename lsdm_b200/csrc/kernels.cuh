@@ -1,6 +1,7 @@
 // Launch prototypes of every non-GEMM kernel on the path.  Each launcher enqueues on `st` and
 // returns the number of kernels launched.
 #pragma once
+#include <string>
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -116,6 +117,9 @@ int launch_q_sample(const float* x0, const int64_t* t, const float* noise, const
 // ---- loss.cu --------------------------------------------------------------------------------
 int launch_chamfer(const float* x, const float* y, int B, int n, int m, float* sums, cudaStream_t st, int sample_stride = 0);
 int launch_cat_loss(const float* probs, const float* target, int B, int C, float* sum, cudaStream_t st);
+
+// ---- api.cu: thread-local error message behind lsdm_last_error(); returns `code` ----
+int set_error(int code, const std::string& msg);
 
 // ---- eval_metrics.cu ------------------------------------------------------------------------
 // EMD (min-cost perfect matching, auction algorithm) of x[B,n,3] vs y[B,n,3], n <= 1024: out_emd[B] (double) = mean matched distance

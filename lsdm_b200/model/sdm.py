@@ -185,14 +185,33 @@ class SceneDiffusionModel(nn.Module):
 
     # ------------------------------------------------------------------ reference-surface helpers
     def load_state_dict(self, state_dict, strict=True, **kw):
-        """Accepts an unmodified reference checkpoint: ``clip_model.*`` (external CLIP tower) is dropped."""
+        """Accepts an unmodified reference checkpoint.  ``clip_model.*`` entries (the frozen CLIP tower the reference keeps as
+        a sub-module, model/sdm.py:229-233) do not belong to this module's parameters: when a CUDA device is present they are
+        loaded into the device text tower (``self.clip_text``), otherwise they are dropped."""
         sd = {k: v for k, v in state_dict.items() if not k.startswith("clip_model.")}
         out = super().load_state_dict(sd, strict=strict, **kw)
         self._weights_sig = None
+        if any(k.startswith("clip_model.transformer.") for k in state_dict) and torch.cuda.is_available():
+            self.load_clip_state_dict(state_dict)
         return out
 
+    def load_clip_state_dict(self, state_dict, prefix="clip_model."):
+        """Installs the CLIP ViT-B/32 text tower (openai/CLIP state-dict names under ``prefix``) on the device."""
+        from .clip_text import ClipTextTower
+
+        dev = self.device if isinstance(self.device, torch.device) and self.device.type == "cuda" else None
+        tower = ClipTextTower(dev)
+        tower.load_state_dict(state_dict, prefix)
+        self.clip_text = tower
+        return tower
+
+    def set_tokenizer(self, fn):
+        """``fn(list[str], context_length=22, truncate=True) -> int [B, 22]``: stands in for ``clip.tokenize`` (host-side BPE;
+        its vocabulary file is not shipped here).  With it and a loaded text tower, ``y`` may be a list of strings."""
+        self._tokenizer = fn
+
     def set_text_encoder(self, fn):
-        """``fn(list[str]) -> [B,512]`` float tensor; stands in for the frozen CLIP text tower (out of scope)."""
+        """``fn(list[str]) -> [B,512]`` float tensor: an external replacement for the whole CLIP text path."""
         self._text_encoder = fn
 
     def set_shard(self, batch_global=None, batch_offset=0, sync_bn_group=None):
@@ -202,12 +221,28 @@ class SceneDiffusionModel(nn.Module):
         self._sync_bn_group = sync_bn_group  # torch.distributed group (or True for the default group) for train-mode SyncBN
 
     def _encode_text(self, y):
-        if torch.is_tensor(y):
+        """``enc_text`` of model/sdm.py:147-150.  float ``[B,512]`` -> already-encoded text (synthetic runs); integer
+        ``[B,77]`` -> ``clip.tokenize`` output, encoded by the device CLIP tower; list of strings -> tokenizer hook + tower
+        (model/sdm.py:245-259), or the external encoder hook."""
+        if torch.is_tensor(y) and y.is_floating_point():
             return y.float()
-        if self._text_encoder is None:
-            raise NotImplementedError("text strings need a CLIP ViT-B/32 text tower, which is outside the accelerated path; "
-                                      "pass the [B,512] text embedding as `y` or install one with set_text_encoder()")
-        return self._text_encoder(list(y)).float()
+        tower = getattr(self, "clip_text", None)
+        if torch.is_tensor(y):
+            if tower is None:
+                raise NotImplementedError("token ids need the CLIP text tower: load a checkpoint with clip_model.* entries or call "
+                                          "load_clip_state_dict()")
+            return tower.encode_text(y)
+        if self._text_encoder is not None:
+            return self._text_encoder(list(y)).float()
+        tok = getattr(self, "_tokenizer", None)
+        if tower is None or tok is None:
+            raise NotImplementedError("text strings need clip.tokenize (host-side BPE, vocabulary not shipped: set_tokenizer()) and the "
+                                      "CLIP text tower weights (load_clip_state_dict()); or pass the [B,512] embedding / [B,77] token ids "
+                                      "as `y`, or install an external encoder with set_text_encoder()")
+        # model/sdm.py:248-256: tokenise to 20 + 2 positions, zero-pad to the 77-token context
+        t = torch.as_tensor(tok(list(y), context_length=22, truncate=True))
+        t = torch.cat([t, torch.zeros(t.shape[0], tower.dims["ctx"] - t.shape[1], dtype=t.dtype)], dim=1)
+        return tower.encode_text(t)
 
     def _sig(self):
         return sum(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + 7919 * sum(

@@ -247,3 +247,43 @@ def make_dropout_mask(seed: int, batch: int):
     rs = np.random.RandomState(seed)
     keep = rs.rand(batch * N_OBJ, 128, N_POINTS) < 0.5
     return torch.from_numpy(keep.astype(np.float32) * 2.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CLIP text tower (model/sdm.py:245-277): seeded random weights under the openai/CLIP state-dict names and token batches in
+# clip.tokenize's layout (SOT, word ids, EOT = largest id, zero padding).  No checkpoint or BPE vocabulary exists offline.
+# ----------------------------------------------------------------------------------------------------------------------
+def make_clip_state_dict(seed=0, width=512, layers=12, vocab=49408, ctx=77, embed=512, prefix=""):
+    """Initialisation statistics of clip/model.py ``CLIP.initialize_parameters`` (+ randomised LayerNorm affine so that
+    every tensor matters); fp32 torch tensors keyed ``<prefix>token_embedding.weight`` ..."""
+    r = np.random.RandomState(seed)
+
+    def t(shape, std, mean=0.0):
+        return torch.from_numpy((r.standard_normal(shape) * std + mean).astype(np.float32))
+
+    proj_std, attn_std, fc_std = (width ** -0.5) * ((2 * layers) ** -0.5), width ** -0.5, (2 * width) ** -0.5
+    sd = {"token_embedding.weight": t((vocab, width), 0.02), "positional_embedding": t((ctx, width), 0.01),
+          "ln_final.weight": t((width,), 0.1, 1.0), "ln_final.bias": t((width,), 0.05),
+          "text_projection": t((width, embed), width ** -0.5)}
+    for l in range(layers):
+        p = f"transformer.resblocks.{l}."
+        sd[p + "ln_1.weight"], sd[p + "ln_1.bias"] = t((width,), 0.1, 1.0), t((width,), 0.05)
+        sd[p + "ln_2.weight"], sd[p + "ln_2.bias"] = t((width,), 0.1, 1.0), t((width,), 0.05)
+        sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"] = t((3 * width, width), attn_std), t((3 * width,), 0.02)
+        sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"] = t((width, width), proj_std), t((width,), 0.02)
+        sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"] = t((4 * width, width), fc_std), t((4 * width,), 0.02)
+        sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"] = t((width, 4 * width), proj_std), t((width,), 0.02)
+    return {prefix + k: v for k, v in sd.items()}
+
+
+def make_clip_tokens(seed, batch, vocab=49408, ctx=77, max_words=20):
+    """int32 [batch, ctx]: SOT (vocab-2), 0..max_words word ids, EOT (vocab-1), zeros -- what ``_encode_text_clip`` builds
+    (model/sdm.py:248-256: tokenised to max_words+2 positions, zero-padded to the 77-token context)."""
+    r = np.random.RandomState(seed)
+    tok = np.zeros((batch, ctx), dtype=np.int32)
+    for b in range(batch):
+        n = int(r.randint(0, max_words + 1)) if b else max_words  # sample 0 has the longest sentence
+        tok[b, 0] = vocab - 2
+        tok[b, 1:1 + n] = r.randint(1, vocab - 2, size=n)
+        tok[b, 1 + n] = vocab - 1
+    return torch.from_numpy(tok)
