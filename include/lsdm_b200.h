@@ -203,6 +203,37 @@ LSDM_API int lsdm_clip_encode_text(lsdm_clip* h, const int32_t* tokens, int32_t 
                                    float* out, void* stream);
 LSDM_API int64_t lsdm_clip_launch_count(const lsdm_clip* h);
 
+/* ---- ContactFormer temporal attention layer -------------------------------------------------------
+ * lsdm_cf_mha_forward replaces contact_former/transformer.py:72-103 `MultiHeadAttention.forward(x, mask)` in eval mode
+ * (both Dropouts off): x[bs, seg_len, n_verts, 64] -> LayerNorm(fc(softmax(q k^T / 8 [mask]) v) + x), attention along the
+ * seg_len axis independently per (head, vertex, sample); d_in = d_k = d_v = 64 (contact_former.py:271-275,318), seg_len <= 256,
+ * n_head * 64 in {64, 128, 192, k * 256}.  Weights are the module's tensors as stored (row-major [out, in]): w_q / w_k /
+ * w_v [n_head*64, 64] + biases, fc [64, n_head*64] + bias, layer_norm weight / bias [64].
+ * mask (nullable): uint8 [bs, seg_len, seg_len], entries equal to 0 are filled with -inf (transformer.py:87-89; a fully
+ * masked row yields NaN exactly as torch.softmax does); all_masked = the reference's `mask.sum() == 0` branch (:91-92),
+ * decided by the caller.  precision: 0 fp32 CUDA cores, 1 TF32 tcgen05, 2 3xTF32 tcgen05 for the four projections.
+ * Workspace: lsdm_cf_workspace_bytes(bs, seg_len, n_verts, n_head), 256-byte aligned.  `out` may not alias `x`.
+ * lsdm_cf_ffn_forward replaces transformer.py:167-177 `PositionwiseFeedForward.forward`: LayerNorm(w_2 relu(w_1 x) + x) on
+ * rows x 64 (the two 1x1 Conv1d weights as [d_hid, 64] and [64, d_hid]); workspace rows * (d_hid + 64) floats + 512 bytes. */
+typedef struct lsdm_cf_mha_weights {
+  const float *w_q, *b_q, *w_k, *b_k, *w_v, *b_v, *fc_w, *fc_b, *ln_w, *ln_b;
+} lsdm_cf_mha_weights;
+typedef struct lsdm_cf_ffn_weights {
+  const float *w1, *b1, *w2, *b2, *ln_w, *ln_b;
+  int32_t d_hid;
+  int32_t reserved;
+} lsdm_cf_ffn_weights;
+/* Process-wide knob: "attn_tc" = 1 (default) runs softmax(QK^T)V on the tensor cores (tcgen05 TF32, scores kept in tensor
+ * memory) when precision == 1 and seg_len is a multiple of 32; 0 forces the fp32 CUDA-core kernel that serves every other case
+ * (precision 0 / 2 always use it: their contract is fp32-grade accuracy). */
+LSDM_API int lsdm_cf_set_option(const char* name, int32_t value);
+LSDM_API size_t lsdm_cf_workspace_bytes(int32_t bs, int32_t seg_len, int32_t n_verts, int32_t n_head);
+LSDM_API int lsdm_cf_mha_forward(const lsdm_cf_mha_weights* w, const float* x, const uint8_t* mask, int32_t all_masked, int32_t bs, int32_t seg_len,
+                                 int32_t n_verts, int32_t n_head, int32_t precision, void* workspace, size_t workspace_bytes, float* out,
+                                 void* stream);
+LSDM_API int lsdm_cf_ffn_forward(const lsdm_cf_ffn_weights* w, const float* x, int64_t rows, int32_t precision, void* workspace, size_t workspace_bytes,
+                                 float* out, void* stream);
+
 /* Debug / parity taps: copy a named intermediate of the last encode/forward into `dst` (device).
  * Returns the element count, or a negative error.  Names: "backbone" [9Bl,1024,3], "hm" [Bl,1024,3],
  * "attn_w" [Bl,9], "tr" [Bl,9,12], "enc" [Bl,128], "pa" [Bl,9,12], "pw" [Bl,9,1024,3], "emb" [Bl,1024,128],

@@ -27,6 +27,16 @@ class Config(C.Structure):
 
 
 _P = C.c_void_p
+
+
+class CfMhaWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_q", "b_q", "w_k", "b_k", "w_v", "b_v", "fc_w", "fc_b", "ln_w", "ln_b")]
+
+
+class CfFfnWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "w2", "b2", "ln_w", "ln_b")] + [("d_hid", C.c_int32), ("reserved", C.c_int32)]
+
+
 # name -> (restype, argtypes); exactly the prototypes of include/lsdm_b200.h
 PROTOTYPES = {
     "lsdm_version": (C.c_char_p, []),
@@ -66,6 +76,11 @@ PROTOTYPES = {
     "lsdm_clip_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "lsdm_clip_encode_text": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_size_t, _P, _P]),
     "lsdm_clip_launch_count": (C.c_int64, [_P]),
+    "lsdm_cf_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
+    "lsdm_cf_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lsdm_cf_mha_forward": (C.c_int, [C.POINTER(CfMhaWeights), _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P,
+                                      C.c_size_t, _P, _P]),
+    "lsdm_cf_ffn_forward": (C.c_int, [C.POINTER(CfFfnWeights), _P, C.c_int64, C.c_int32, _P, C.c_size_t, _P, _P]),
     "lsdm_debug_tensor": (C.c_int64, [_P, C.c_char_p, _P, C.c_size_t, _P]),
     "lsdm_launch_count": (C.c_int64, [_P]),
     "lsdm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),

@@ -18,6 +18,7 @@
 
 #include "../../include/lsdm_b200.h"
 #include "kernels.cuh"
+#include "ln.cuh"
 
 using namespace lsdm;
 
@@ -35,30 +36,6 @@ struct lsdm_clip {
 namespace {
 
 constexpr int HEAD_DIM = 64;
-constexpr float LN_EPS = 1e-5f;
-
-// LayerNorm of one row held as `PER` values per lane (row width = 32 * PER): two-pass mean / biased variance, fp32
-template <int PER>
-__device__ __forceinline__ void layer_norm_row(float (&v)[PER], const float* __restrict__ g, const float* __restrict__ b, int lane,
-                                               float* __restrict__ dst) {
-  constexpr int WIDTH = 32 * PER;
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.0f / WIDTH);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const float d = v[i] - mean;
-    q += d * d;
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / WIDTH) + LN_EPS);
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int c = i * 32 + lane;
-    dst[c] = (v[i] - mean) * rstd * g[c] + b[c];
-  }
-}
 
 // warp per row r = (b, p), p < L:  x[r] = tok_emb[tokens[b, p]] + pos[p];  h[r] = LN(x[r])
 template <int PER>
@@ -76,23 +53,6 @@ __global__ void __launch_bounds__(256) clip_embed_ln_kernel(const int32_t* __res
   for (int i = 0; i < PER; ++i) {
     const int c = i * 32 + lane;
     v[i] = tok_emb[(int64_t)tok * WIDTH + c] + pos[(int64_t)p * WIDTH + c];
-    x[(int64_t)r * WIDTH + c] = v[i];
-  }
-  layer_norm_row<PER>(v, g, b, lane, h + (int64_t)r * WIDTH);
-}
-
-// warp per row:  x[r] += y[r] (+ bias already in y);  h[r] = LN(x[r])
-template <int PER>
-__global__ void __launch_bounds__(256) clip_add_ln_kernel(float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g,
-                                                          const float* __restrict__ b, int rows, float* __restrict__ h) {
-  constexpr int WIDTH = 32 * PER;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  float v[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int c = i * 32 + lane;
-    v[i] = x[(int64_t)r * WIDTH + c] + y[(int64_t)r * WIDTH + c];
     x[(int64_t)r * WIDTH + c] = v[i];
   }
   layer_norm_row<PER>(v, g, b, lane, h + (int64_t)r * WIDTH);
@@ -378,9 +338,9 @@ LSDM_API int lsdm_clip_encode_text(lsdm_clip* h, const int32_t* tokens, int32_t 
     ++h->launches;
   };
   auto add_ln = [&](const float* g, const float* b) {
-    if (W == 512) clip_add_ln_kernel<16><<<wblocks, 256, 0, st>>>(w.x, w.y, g, b, rows, w.hn);
-    else if (W == 768) clip_add_ln_kernel<24><<<wblocks, 256, 0, st>>>(w.x, w.y, g, b, rows, w.hn);
-    else clip_add_ln_kernel<32><<<wblocks, 256, 0, st>>>(w.x, w.y, g, b, rows, w.hn);
+    if (W == 512) add_ln_kernel<16><<<wblocks, 256, 0, st>>>(w.x, w.y, g, b, rows, w.hn);
+    else if (W == 768) add_ln_kernel<24><<<wblocks, 256, 0, st>>>(w.x, w.y, g, b, rows, w.hn);
+    else add_ln_kernel<32><<<wblocks, 256, 0, st>>>(w.x, w.y, g, b, rows, w.hn);
     ++h->launches;
   };
   const size_t attn_smem = sizeof(float) * ((size_t)L * (HEAD_DIM + 1) + (size_t)L * HEAD_DIM + 4 * HEAD_DIM + 4 * (size_t)L);
