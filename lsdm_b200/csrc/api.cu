@@ -1187,6 +1187,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
     h->fp_tail = value;
     return LSDM_OK;
   }
+  if (strcmp(name, "gemm_tma") == 0 && (value == 0 || value == 1)) {
+    g_gemm_tma = value;  // process-wide
+    return LSDM_OK;
+  }
   if (strcmp(name, "gemm_async") == 0 && (value == 0 || value == 1)) {
     g_gemm_async = value;  // process-wide
     return LSDM_OK;

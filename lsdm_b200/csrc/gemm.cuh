@@ -38,6 +38,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t stream);   // one CTA per tile (simple pipeline)
 int launch_gemm_ws(const GemmArgs& g, cudaStream_t stream);   // persistent, warp-specialised (default tensor path)
 extern int g_gemm_async;                                       // 1: pre-rounded operands take the cp.async-fed persistent kernel
+extern int g_gemm_tma;                                         // 1: un-batched pre-rounded operands are fed by TMA instead of cp.async
 extern int g_gemm_ws;                                          // 1: launch_gemm uses the warp-specialised kernel
 bool gemm_tc_eligible(const GemmArgs& g);
 

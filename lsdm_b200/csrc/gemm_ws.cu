@@ -2,12 +2,16 @@
 //   C[M,N] = act(A[M,K] . W[N,K]^T + bias),  TF32 (operands rounded to nearest) or 3xTF32, fp32 accumulate in TMEM.
 // One CTA per SM loops over 128 x BN output tiles.  Thirteen warps, three roles:
 //   warps 0-3  producers : ld.global (next k-block prefetched in registers) -> cvt.rna.tf32 [-> hi/lo split] ->
-//                          swizzled st.shared into an NSTAGE ring (K-major SWIZZLE_128B k-blocks) -> mbarrier "full"
+//                          swizzled st.shared into an NSTAGE ring (K-major SWIZZLE_128B k-blocks) -> mbarrier "full";
+//                          pre-rounded / pre-split operands skip the registers: TMA (cp.async.bulk.tensor, one thread,
+//                          SWIZZLE_128B boxes of 128 x 32 and BN x 32 floats, byte-counted mbarrier) or cp.async (batched GEMMs)
 //   warp  12   MMA issuer: one thread; waits "full", issues tcgen05.mma (M=128, N=BN, K=8), tcgen05.commit -> "empty";
 //                          after the last k-block commits the tile's accumulator -> "acc_full"
 //   warps 4-11 epilogue  : tcgen05.ld of the finished accumulator (two TMEM buffers alternate, so the epilogue of tile i
 //                          overlaps the loads + MMAs of tile i+1), bias / activation, then either a shared-memory
 //                          transpose for coalesced 128-bit stores or the 32-row group max (redux.sync) -> "acc_empty"
+#include <cuda.h>  // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no link against libcuda)
+
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 
@@ -31,8 +35,13 @@ __host__ __device__ constexpr int ws_nstage(int bn, bool split, bool async) {
   return split ? (async ? (bn <= 32 ? 4 : (bn <= 64 ? 3 : 2)) : 2) : ((async && bn < 256) ? 4 : 3);
 }
 
+struct TmaMaps {
+  CUtensorMap a, w, a_lo, w_lo;  // A / W (hi planes) and the 3xTF32 residual planes
+};
+
 template <int BN, bool SPLIT, bool ASYNC>
-__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int tiles_m, int tiles_n, int total_tiles) {
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int tiles_m, int tiles_n, int total_tiles, int use_tma,
+                                                                const __grid_constant__ TmaMaps maps) {
   constexpr int NSTAGE = ws_nstage(BN, SPLIT, ASYNC);
   constexpr int EPW = ws_epi_warps(BN, SPLIT);
   constexpr int W_STAGE = BN * 128;
@@ -54,7 +63,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
   if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 2 * TCOLS_PER);
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(smem_u32(&s_full[i]), NPROD);
+      mbar_init(smem_u32(&s_full[i]), (ASYNC && use_tma) ? 1 : NPROD);
       mbar_init(smem_u32(&s_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -78,7 +87,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
     n0 = (r % tiles_n) * BN;
   };
 
-  if (warp < PW && ASYNC) {
+  if (warp < PW && ASYNC && use_tma) {
+    // ============ producer, pre-rounded operands, TMA: one thread issues the bulk tensor copies of every stage ============
+    if (tid == 0) {
+      tma_prefetch_desc(&maps.a);
+      tma_prefetch_desc(&maps.w);
+      int t = blockIdx.x, kb = 0;
+      uint32_t it = 0;
+      while (t < total_tiles) {
+        const uint32_t s = it % NSTAGE;
+        if (it >= (uint32_t)NSTAGE) mbar_wait(smem_u32(&s_empty[s]), ((it / NSTAGE) & 1u) ^ 1u);
+        int m0, n0, z;
+        decode(t, m0, n0, z);
+        const uint32_t sA = base + s * STAGE, sW = sA + W_A_STAGE, full = smem_u32(&s_full[s]);
+        const int k0 = kb * WBK;
+        mbar_arrive_expect_tx(full, (uint32_t)STAGE);
+        tma_load_2d(sA, &maps.a, k0, m0, full);  // rows past M are zero-filled
+        tma_load_2d(sW, &maps.w, k0, n0, full);
+        if (SPLIT) {
+          tma_load_2d(sA + HALF, &maps.a_lo, k0, m0, full);
+          tma_load_2d(sW + HALF, &maps.w_lo, k0, n0, full);
+        }
+        if (++kb == nkb) {
+          kb = 0;
+          t += gridDim.x;
+        }
+        ++it;
+      }
+    }
+  } else if (warp < PW && ASYNC) {
     // ============ producers, pre-rounded operands: cp.async straight into the swizzled ring, NSTAGE k-blocks in flight ============
     int t = blockIdx.x, kb = 0;
     uint32_t it = 0;
@@ -305,6 +342,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
   if (warp == 0) tmem_dealloc(tmem, 2 * TCOLS_PER);
 }
 
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn tma_encoder() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+// [rows x K] fp32 row-major with leading dimension ld (floats) -> boxes of box_rows x 32 floats, SWIZZLE_128B, zero fill out of bounds
+bool tma_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int K, int64_t ld, int box_rows) {
+  EncodeFn enc = tma_encoder();
+  if (!enc || (reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 3) || rows <= 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, bool SPLIT, bool ASYNC>
 int launch_ws2(const GemmArgs& g, cudaStream_t st) {
   constexpr int nstage = ws_nstage(BN, SPLIT, ASYNC);
@@ -326,7 +389,13 @@ int launch_ws2(const GemmArgs& g, cudaStream_t st) {
   const int64_t total = (int64_t)tiles_m * tiles_n * batch;
   if (total > 0x7fffffff) return -1;
   const int grid = total < sms ? (int)total : sms;
-  gemm_ws_kernel<BN, SPLIT, ASYNC><<<grid, WS_THREADS, smem, st>>>(g, tiles_m, tiles_n, (int)total);
+  TmaMaps maps;
+  int use_tma = 0;
+  if (ASYNC && g_gemm_tma && batch == 1) {
+    use_tma = tma_map_2d(&maps.a, g.A, g.M, g.K, g.lda, WBM) && tma_map_2d(&maps.w, g.W, g.N, g.K, g.ldw, BN) &&
+              (!SPLIT || (tma_map_2d(&maps.a_lo, g.A_lo, g.M, g.K, g.lda, WBM) && tma_map_2d(&maps.w_lo, g.W_lo, g.N, g.K, g.ldw, BN)));
+  }
+  gemm_ws_kernel<BN, SPLIT, ASYNC><<<grid, WS_THREADS, smem, st>>>(g, tiles_m, tiles_n, (int)total, use_tma, maps);
   return 1;
 }
 template <int BN>
@@ -340,6 +409,8 @@ int launch_ws(const GemmArgs& g, cudaStream_t st) {
 }
 
 }  // namespace
+
+int g_gemm_tma = 1;  // 1: pre-rounded / pre-split operands of un-batched GEMMs are fed by TMA; 0: cp.async
 
 int launch_gemm_ws(const GemmArgs& g, cudaStream_t st) {
   if (!gemm_tc_eligible(g) || g.N > 1024) return -1;

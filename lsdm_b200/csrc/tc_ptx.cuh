@@ -42,6 +42,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// ---- TMA (cp.async.bulk.tensor): one thread moves a [box_rows x 128 B] k-block global -> shared, written in the
+// SWIZZLE_128B pattern the UMMA descriptors below describe; completion is counted in bytes on the mbarrier ----
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int c_inner, int c_outer, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(tmap), "r"(c_inner), "r"(c_outer), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---- proxies / fences ---------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -51,6 +51,7 @@ class Engine:
         self.set_option("sa_fused", int(os.environ.get("LSDM_SA_FUSED", "3")))
         self.set_option("gemm_ws", int(os.environ.get("LSDM_GEMM_WS", "0")))
         self.set_option("gemm_async", int(os.environ.get("LSDM_GEMM_ASYNC", "1")))
+        self.set_option("gemm_tma", int(os.environ.get("LSDM_GEMM_TMA", "1")))
         self.set_option("fp_tail", int(os.environ.get("LSDM_FP_TAIL", "1")))
         self.set_option("fp_fused", int(os.environ.get("LSDM_FP_FUSED", "1")))
 

@@ -42,13 +42,14 @@ for prec in ("3xtf32", "tf32", "fp32"):
     ms_mha, ms_ffn = e[0].elapsed_time(e[1]) / 5, e[1].elapsed_time(e[2]) / 5
     res[prec] = {"mha_ms": ms_mha, "mha_tflops": flops_mha / ms_mha / 1e9, "ffn_ms": ms_ffn,
                  "layer_io_gbs": 2 * rows * 64 * 4 * 2 / ((ms_mha + ms_ffn) * 1e-3) / 1e9}
-    if prec == "3xtf32":
-        got = z.cpu()
+    res[prec]["_out"] = z.cpu()
 torch.set_num_threads(os.cpu_count() or 1)
 with torch.no_grad():
     t0 = time.perf_counter()
     ref = FO.encoder_layer(sd, x)
     res["cpu_oracle_layer_ms"] = (time.perf_counter() - t0) * 1e3
 res["cpu_threads"] = os.cpu_count()
-res["rel_l2_3xtf32_vs_oracle"] = float((got - ref).norm() / ref.norm())
+for prec in ("3xtf32", "tf32", "fp32"):
+    got = res[prec].pop("_out")
+    res[prec]["rel_l2_vs_oracle"] = float((got - ref).norm() / ref.norm())
 print(json.dumps(res))
