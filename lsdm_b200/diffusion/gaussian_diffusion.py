@@ -263,17 +263,22 @@ class GaussianDiffusion:
         text = net._encode_text(y)
         n_total = self.num_timesteps - skip_timesteps
         with th.no_grad():
-            # first step through encode + denoise_step: the caller's tensor (when `noise` is given) only sees the
-            # first model call's in-place `x += pcd_out`, and the sample goes to a fresh tensor, as in the reference
             fps0 = net.draw_fps_starts(B)
-            nz0 = th.randn_like(img)
-            t0 = th.full((B,), n_total - 1, device=img.device, dtype=th.long)
-            net.encode(mask, given_objs, given_cats, text, fps0, device=img.device)
-            cur, x0, gd = eng.denoise_step(img, t0, nz0, clip_denoised=clip_denoised)
-            done = 1
+            if noise is not None or hoisted or n_total == 1:
+                # first step through encode + denoise_step: the caller's tensor (when `noise` is given) only sees the
+                # first model call's in-place `x += pcd_out`, and the sample goes to a fresh tensor, as in the reference
+                nz0 = th.randn_like(img)
+                t0 = th.full((B,), n_total - 1, device=img.device, dtype=th.long)
+                net.encode(mask, given_objs, given_cats, text, fps0, device=img.device)
+                cur, x0, gd = eng.denoise_step(img, t0, nz0, clip_denoised=clip_denoised)
+                done, fps0_used = 1, True
+            else:
+                # x_T is this function's own tensor: every step, the first included, runs inside the pipelined library loop
+                cur, done, fps0_used = img, 0, False
             while done < n_total:
                 n = min(chunk, n_total - done)
-                fps = th.stack([net.draw_fps_starts(B) for _ in range(n)])
+                fps = th.stack([fps0 if (k == 0 and not fps0_used) else net.draw_fps_starts(B) for k in range(n)])
+                fps0_used = True
                 nz = th.empty(n, *img.shape, device=img.device)
                 for k in range(n):
                     nz[k] = th.randn_like(img)

@@ -414,3 +414,25 @@ def test_odd_batch_sizes_vs_oracle(B, mode):
     assert rel_l2(out["sample"].cpu(), ref["sample"]) < TOL_E2E
     assert rel_l2(out["pred_xstart"].cpu(), ref["pred_xstart"]) < TOL_E2E
     assert rel_l2(x.cpu(), xo) < TOL_E2E
+
+
+def test_fused_loop_without_caller_noise_matches_stepwise_loop():
+    """noise=None: x_T is drawn inside, so every step (the first included) runs in the pipelined library loop; the RNG draws
+    (device generator: x_T then one noise per step; CPU generator: four FPS draws per step) and the result are those of the
+    step-by-step reference-shaped loop."""
+    from lsdm_b200.diffusion import gaussian_diffusion as gd
+    from lsdm_b200.diffusion.respace import SpacedDiffusion, space_timesteps
+
+    m, _ = _model("wellcond")
+    diff = SpacedDiffusion(use_timesteps=space_timesteps(1000, "6"), betas=gd.get_named_beta_schedule("cosine", 1000),
+                           model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
+    inp = _cuda(syn.make_inputs(8, 3))
+    outs = []
+    for fn, kw in ((diff.p_sample_loop, {}), (diff.p_sample_loop_fused, {"chunk": 4}), (diff.p_sample_loop_fused, {"chunk": 50})):
+        torch.manual_seed(123)
+        torch.cuda.manual_seed(123)
+        s = fn(m, (3, 1024, 3), inp["mask"], inp["given_objs"], inp["given_cats"], inp["text_emb"], clip_denoised=False, **kw)
+        outs.append((s.clone(), m.saved_guiding_points.clone(), m.saved_cat.clone()))
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert rel_l2(a.cpu(), b.cpu()) < 1e-6
