@@ -177,6 +177,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: keep it to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     clocks = ClockSampler(local_rank)
