@@ -47,6 +47,30 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = tf32_round_fin(x - hi);
 }
 
+// Tensor-core epilogue forms of the transcendental activations: MUFU ex2 / rcp instead of the ~25-instruction libm expf and
+// IEEE division (the epilogue warps, not the MMAs, bounded the sigmoid / GELU layers of the x0 network).  Relative error
+// <= ~4e-7 (ex2.approx 2^-22, rcp.approx 1 ulp; erf: Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7) -- far inside the 1e-3
+// bound of the path; the fp32 CUDA-core build (gemm_simt.cu) keeps the libm forms.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+template <int ACT>
+__device__ __forceinline__ float apply_act_fast(float x) {
+  if (ACT == ACT_GELU) return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752440f));
+  if (ACT == ACT_SIGMOID) return fast_sigmoid(x);
+  if (ACT == ACT_SILU) return x * fast_sigmoid(x);
+  if (ACT == ACT_QGELU) return x * fast_sigmoid(1.702f * x);
+  return apply_act<ACT>(x);
+}
+
 // Epilogue transform of one 32-column accumulator chunk: f = [round_tf32](act(v + row_bias + col_bias)).
 // The activation / rounding selectors are resolved ONCE per chunk (switch outside the unrolled element loop).
 template <int ACT, bool ROUND>
@@ -55,7 +79,7 @@ __device__ __forceinline__ void epi_chunk_t(float (&f)[32], const uint32_t (&v)[
   for (int j = 0; j < 32; ++j) {
     float x = __uint_as_float(v[j]) + rbias;
     if (cbias) x += cbias[j];
-    x = apply_act<ACT>(x);
+    x = apply_act_fast<ACT>(x);
     if (ROUND) {
       // == cvt.rna.tf32.f32 for finite x (two integer ops instead of the FSETP + IADD + LOP3 the cvt expands to)
       x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);

@@ -72,22 +72,31 @@ def test_layer_full_size_vs_oracle_and_masked_rows():
     from lsdm_b200.contact_former.transformer import EncoderLayer, MultiHeadAttention
 
     sd = cf_state_dict(9)
-    layer = EncoderLayer(8, 64, 64, 64)
+    layer = EncoderLayer(8, 64, 64, 64, precision="3xtf32")
     layer.load_state_dict(sd)
     layer = layer.cuda().eval()
+    fast = EncoderLayer(8, 64, 64, 64)  # default precision: TF32 projections + tensor-core attention
+    assert fast.self_attn.precision == "tf32"
+    fast.load_state_dict(sd)
+    fast = fast.cuda().eval()
     r = np.random.RandomState(1)
     x = torch.from_numpy(r.standard_normal((1, 256, 655, 64)).astype(np.float32))
     with torch.no_grad():
         got = layer(x.cuda()).cpu()
+        got_fast = fast(x.cuda()).cpu()
         # oracle on a vertex subset (attention is independent per vertex; LayerNorm / FFN are per row)
         vs = [0, 1, 100, 333, 654]
         ref = FO.encoder_layer(sd, x[:, :, vs])
-    assert torch.isfinite(got).all()
+    assert torch.isfinite(got).all() and torch.isfinite(got_fast).all()
     assert rel_l2(got[:, :, vs], ref) < 2e-5
+    assert rel_l2(got_fast[:, :, vs], ref) < 1e-3  # north_star's bound for what a path returns
     # a row whose keys are all masked is NaN in the reference (softmax over -inf); other rows are unaffected
     m = torch.ones(1, 256, 256)
     m[0, 7, :] = 0
     mha = layer.self_attn
+    with torch.no_grad():
+        gf = fast.self_attn(x[:, :, :4].cuda(), m).cpu()  # tensor-core kernel: same NaN row
+    assert torch.isnan(gf[0, 7]).all() and torch.isfinite(gf[0, 8]).all()
     with torch.no_grad():
         gm = mha(x[:, :, :4].cuda(), m).cpu()
         rm = FO.mha(sd, x[:, :, :4], m, "self_attn.")
