@@ -258,6 +258,9 @@ LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32
  *             fused tensor-core kernel.
  * "gemm_async" (process-wide): 1 = TF32 layers whose operands are pre-rounded by their producers use the cp.async-fed
  * persistent warp-specialised GEMM.
+ * "select_uniform" (process-wide): 1 (default) = a cloud whose points all coincide (an absent object, zero-padded by the
+ *             dataset) takes the closed-form FPS order {start, 0, 0, ...} and a 3-candidate 3-NN scan: the same integers as
+ *             the full scans, which 0 forces.
  * "gemm_tma" (process-wide): 1 (default) = those operands are moved by TMA (cp.async.bulk.tensor, SWIZZLE_128B boxes, one
  *             issuing thread, byte-counted mbarrier) for un-batched GEMMs; 0 = cp.async.
  * "gemm_ws" (process-wide): 1 = persistent warp-specialised tcgen05 GEMM (default), 0 = one-CTA-per-tile tcgen05 GEMM. */

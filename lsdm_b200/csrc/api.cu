@@ -1149,6 +1149,8 @@ LSDM_API int64_t lsdm_debug_tensor(lsdm_handle* h, const char* name, void* dst, 
       {"l2_feat", w.feat[2], C * 256 * 128, 4}, {"l3_feat", w.feat[3], C * 64 * 256, 4}, {"l4_feat", w.feat[4], C * 16 * 512, 4},
       {"fp4_feat", w.g3, C * 64 * 256, 4}, {"fp3_feat", w.g2, C * 256 * 256, 4}, {"fp2_feat", w.g1, C * 1024 * 128, 4},
       {"nn_idx3", q.nn_idx[3], C * 1024 * 3, 4}, {"nn_w3", q.nn_w[3], C * 1024 * 3, 4}, {"nn_idx0", q.nn_idx[0], C * 64 * 3, 4},
+      {"nn_w0", q.nn_w[0], C * 64 * 3, 4}, {"nn_idx1", q.nn_idx[1], C * 256 * 3, 4}, {"nn_w1", q.nn_w[1], C * 256 * 3, 4},
+      {"nn_idx2", q.nn_idx[2], C * 1024 * 3, 4}, {"nn_w2", q.nn_w[2], C * 1024 * 3, 4},
       {"x0", w.x0, B * NPTS * 3, 4}, {"guiding", w.guiding, B * NPTS * 3, 4}, {"s256", w.s256, B * 256, 4},
   };
   for (const Tap& t : taps) {
@@ -1185,6 +1187,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   }
   if (strcmp(name, "fp_tail") == 0 && (value == 0 || value == 1)) {
     h->fp_tail = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "select_uniform") == 0 && (value == 0 || value == 1)) {
+    g_select_uniform_shortcut = value;  // process-wide
     return LSDM_OK;
   }
   if (strcmp(name, "gemm_tma") == 0 && (value == 0 || value == 1)) {

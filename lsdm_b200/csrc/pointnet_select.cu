@@ -17,7 +17,7 @@ constexpr int FPS_T = 128;
 
 template <int N, int NP>
 __device__ __forceinline__ void fps_level(const float* sx, const float* sy, const float* sz, int start, int* s_idx,
-                                          unsigned long long* s_red, int tid) {
+                                          unsigned long long* s_red, int tid, bool uniform) {
   constexpr int PER = (N + FPS_T - 1) / FPS_T;
   constexpr bool PACKED = (N % FPS_T == 0) && (PER % 2 == 0);  // two points per instruction (fp32x2), every slot valid
   constexpr int PER2 = PACKED ? PER / 2 : 1;
@@ -43,6 +43,15 @@ __device__ __forceinline__ void fps_level(const float* sx, const float* sy, cons
   }
   int far = start;
   const int lane = tid & 31, warp = tid >> 5;
+  if (uniform) {
+    // Every point of the cloud has the same coordinates (an absent object: the dataset pads it with zeros, reference
+    // posa/dataset.py:456).  All squared distances are then (0 + 0) + 0 = 0 in every round, the running minimum is 0 after
+    // round 0 and the argmax of an all-equal array is its first index: the selection is {start, 0, 0, ...} -- exactly what
+    // the rounds below produce, without running them.
+    for (int it = tid; it < NP; it += FPS_T) s_idx[it] = it == 0 ? start : 0;
+    __syncthreads();
+    return;
+  }
   for (int it = 0; it < NP; ++it) {
     if (tid == 0) s_idx[it] = far;
     float cx = sx[far], cy = sy[far], cz = sz[far];
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
                                                      int n_clouds, int* __restrict__ idx1, int* __restrict__ idx2,
                                                      int* __restrict__ idx3, int* __restrict__ idx4,
                                                      float* __restrict__ xyz1, float* __restrict__ xyz2,
-                                                     float* __restrict__ xyz3, float* __restrict__ xyz4) {
+                                                     float* __restrict__ xyz3, float* __restrict__ xyz4, int g_fps_uniform_shortcut) {
   __shared__ float ax[1024], ay[1024], az[1024];
   __shared__ float bx[1024], by[1024], bz[1024];
   __shared__ int s_idx[1024];
@@ -117,9 +126,16 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
     ay[p] = src[p * 3 + 1];
     az[p] = src[p * 3 + 2];
   }
-  __syncthreads();
+  // all 1024 points equal (== compares values: +0 and -0 are the same point, a NaN never is)?  Then every level is uniform too.
+  bool same = true;
+  {
+    const float x0 = src[0], y0 = src[1], z0 = src[2];
+    same = fabsf(x0) < INFINITY && fabsf(y0) < INFINITY && fabsf(z0) < INFINITY;  // inf - inf is NaN, not 0: full rounds
+    for (int p = tid; p < 1024; p += FPS_T) same = same && src[p * 3] == x0 && src[p * 3 + 1] == y0 && src[p * 3 + 2] == z0;
+  }
+  const bool uniform = g_fps_uniform_shortcut && __syncthreads_and(same ? 1 : 0) != 0;
   // level 1: 1024 of 1024 (an FPS-ordered permutation)
-  fps_level<1024, 1024>(ax, ay, az, (int)start[0 * (int64_t)n_clouds + c], s_idx, s_red, tid);
+  fps_level<1024, 1024>(ax, ay, az, (int)start[0 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
   for (int p = tid; p < 1024; p += FPS_T) {
     int j = s_idx[p];
     idx1[(int64_t)c * 1024 + p] = j;
@@ -130,7 +146,7 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
   }
   __syncthreads();
   // level 2: 256 of 1024 over l1_xyz
-  fps_level<1024, 256>(bx, by, bz, (int)start[1 * (int64_t)n_clouds + c], s_idx, s_red, tid);
+  fps_level<1024, 256>(bx, by, bz, (int)start[1 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
   for (int p = tid; p < 256; p += FPS_T) {
     int j = s_idx[p];
     idx2[(int64_t)c * 256 + p] = j;
@@ -141,7 +157,7 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
   }
   __syncthreads();
   // level 3: 64 of 256
-  fps_level<256, 64>(ax, ay, az, (int)start[2 * (int64_t)n_clouds + c], s_idx, s_red, tid);
+  fps_level<256, 64>(ax, ay, az, (int)start[2 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
   for (int p = tid; p < 64; p += FPS_T) {
     int j = s_idx[p];
     idx3[(int64_t)c * 64 + p] = j;
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
   }
   __syncthreads();
   // level 4: 16 of 64
-  fps_level<64, 16>(bx, by, bz, (int)start[3 * (int64_t)n_clouds + c], s_idx, s_red, tid);
+  fps_level<64, 16>(bx, by, bz, (int)start[3 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
   for (int p = tid; p < 16; p += FPS_T) {
     int j = s_idx[p];
     idx4[(int64_t)c * 16 + p] = j;
@@ -256,15 +272,21 @@ struct Top3 {
 
 __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                                                        int n_clouds, int N, int S, int* __restrict__ nn_idx,
-                                                       float* __restrict__ nn_w) {
+                                                       float* __restrict__ nn_w, int uniform_shortcut) {
   extern __shared__ float4 sp[];  // per coarse point: (x, x, y, y) | (z, z, |p|^2, |p|^2)
   const int c = blockIdx.y;
   const float* src = xyz2 + (int64_t)c * S * 3;
+  bool same = true;
+  const float x0 = src[0], y0 = src[1], z0 = src[2];
   for (int p = threadIdx.x; p < S; p += blockDim.x) {
     const float x = src[p * 3], y = src[p * 3 + 1], z = src[p * 3 + 2], w = sqnorm3(x, y, z);
     sp[2 * p] = make_float4(x, x, y, y);
     sp[2 * p + 1] = make_float4(z, z, w, w);
+    same = same && x == x0 && y == y0 && z == z0;
   }
+  // All S coarse points equal (absent object, zero-padded): every candidate has the same distance, so the scan below keeps
+  // candidates 0, 1, 2 (insertion is strict '<', ties keep the lowest index) -- scanning only those three is the same result.
+  const int S_scan = (uniform_shortcut && __syncthreads_and(same ? 1 : 0) != 0 && S >= 3) ? 3 : S;
   __syncthreads();
   // two fine points per thread (one fp32x2 pair).  Each has its OWN insertion branch: an insertion happens ~3/s of the
   // time at coarse point s, so a warp-level branch per query slot is skipped far more often than a shared one would be.
@@ -280,7 +302,7 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
     ta.init();
     tb.init();
     const float2 qx2 = make_float2(ax, bx), qy2 = make_float2(ay, by), qz2 = make_float2(az, bz), qn2 = make_float2(a2, b2);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < S_scan; ++s) {
       const float2 d = sqdist2(qx2, qy2, qz2, qn2, sp[2 * s], sp[2 * s + 1]);
       ta.push(d.x, s);
       tb.push(d.y, s);
@@ -292,9 +314,13 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
 
 }  // namespace
 
+// 1 (default): clouds whose points all coincide (absent objects) take the closed-form FPS order / 3-candidate 3-NN scan -- the
+// same integers as the full scans (tests/test_gpu_parity.py::test_uniform_cloud_shortcuts_are_exact); 0: always the full scans.
+int g_select_uniform_shortcut = 1;
+
 int launch_fps4(const float* xyz0, const int64_t* start, int n_clouds, int* idx1, int* idx2, int* idx3, int* idx4,
                 float* xyz1, float* xyz2, float* xyz3, float* xyz4, cudaStream_t st) {
-  fps4_kernel<<<n_clouds, FPS_T, 0, st>>>(xyz0, start, n_clouds, idx1, idx2, idx3, idx4, xyz1, xyz2, xyz3, xyz4);
+  fps4_kernel<<<n_clouds, FPS_T, 0, st>>>(xyz0, start, n_clouds, idx1, idx2, idx3, idx4, xyz1, xyz2, xyz3, xyz4, g_select_uniform_shortcut);
   return 1;
 }
 
@@ -311,7 +337,7 @@ int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, i
                     cudaStream_t st) {
   int threads = N >= 512 ? 256 : 64;
   dim3 grid((N + 2 * threads - 1) / (2 * threads), n_clouds);  // two fine points per thread
-  three_nn_kernel<<<grid, threads, 2 * S * sizeof(float4), st>>>(xyz1, xyz2, n_clouds, N, S, nn_idx, nn_w);
+  three_nn_kernel<<<grid, threads, 2 * S * sizeof(float4), st>>>(xyz1, xyz2, n_clouds, N, S, nn_idx, nn_w, g_select_uniform_shortcut);
   return 1;
 }
 

@@ -436,3 +436,51 @@ def test_fused_loop_without_caller_noise_matches_stepwise_loop():
     for o in outs[1:]:
         for a, b in zip(o, outs[0]):
             assert rel_l2(a.cpu(), b.cpu()) < 1e-6
+
+
+def test_uniform_cloud_shortcuts_are_exact():
+    """Clouds whose points all coincide (absent objects are zero-padded by the dataset) take closed-form selections: FPS order
+    {start, 0, 0, ...} and a 3-candidate 3-NN scan.  Every integer and every interpolation weight must equal what the full
+    scans produce ("select_uniform" = 0), and the FPS order must equal the oracle's, for zero clouds, constant non-zero clouds,
+    mixed +0 / -0 clouds and almost-uniform clouds (one point differs -> no shortcut)."""
+    B = 4
+    C = B * 9
+    m, _ = _model("wellcond")
+    inp = syn.make_inputs(41, B)
+    objs = inp["given_objs"].clone()
+    objs[0, 1] = 0.0
+    objs[0, 2] = torch.tensor([0.3, -0.2, 0.7])
+    objs[0, 3] = 0.0
+    objs[0, 3, torch.arange(0, 1024, 3)] = -0.0                        # same point as +0
+    objs[1, 4] = torch.tensor([0.25, 0.25, -0.5])
+    objs[1, 4, 777] = torch.tensor([0.25, 0.25, -0.4999])             # almost uniform: must take the full scans
+    objs[2, 5] = 0.0
+    objs[2, 5, 0, 0] = 1e-30                                           # point 0 differs
+    inp["given_objs"] = objs
+    fps, _ = syn.make_step_randoms(42, B, 1)
+    g = _cuda(inp)
+    names = [f"fps_idx{l}" for l in range(4)] + [f"ball_idx{l}" for l in range(4)] + [f"nn_idx{l}" for l in range(4)]
+    out = {}
+    for flag in (1, 0):
+        eng = m.engine(B, torch.device("cuda", 0))
+        eng.set_option("select_uniform", flag)
+        try:
+            x = g["x_T"].clone()
+            with injected_rng(fps_starts=list(fps[0])):
+                oc, x0 = m(x, g["mask"], torch.full((B,), 500, device="cuda"), g["given_objs"], g["given_cats"], g["text_emb"])
+            out[flag] = {n: m._engine.debug_tensor(n, torch.int32).cpu().clone() for n in names}
+            for l in range(4):
+                out[flag][f"nn_w{l}"] = m._engine.debug_tensor(f"nn_w{l}", torch.float32).cpu().clone()
+            out[flag]["x0"] = x0.cpu().clone()
+        finally:
+            eng.set_option("select_uniform", 1)
+    for n in out[1]:
+        assert torch.equal(out[1][n], out[0][n]), n
+    xyz = objs.reshape(C, 1024, 3)
+    lvl_xyz = xyz
+    for lvl, npnt in enumerate((1024, 256, 64, 16)):
+        ref_idx = O.farthest_point_sample(lvl_xyz, npnt, fps[0][lvl])
+        assert torch.equal(out[1][f"fps_idx{lvl}"].view(C, npnt).long(), ref_idx), f"fps level {lvl}"
+        lvl_xyz = O._gather(lvl_xyz, ref_idx)
+    uni = out[1]["fps_idx0"].view(C, 1024)[[1, 2, 3]]
+    assert (uni[:, 1:] == 0).all()   # the closed form really is {start, 0, 0, ...}
