@@ -177,7 +177,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: keep it to the ONE JSON line
+        # NCCL writes its version banner / debug lines to stdout by default: send them to stderr so that stdout is the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     clocks = ClockSampler(local_rank)
@@ -338,6 +339,32 @@ def run_ours(args):
         hoisted_info = {"value": Bg * K / (hms * 1e-3), "unit": UNIT, "ms_per_step": hms / K,
                         "note": "conditions (incl. PointNet++) encoded once per K-step call instead of every step: NOT the reference's per-step work"}
 
+    # ---- transparency leg: the same K steps with the closed-form selections for uniform (zero-padded) clouds switched off ----
+    full_scans = None
+    if not hoisted:
+        eng.set_option("select_uniform", 0)
+        try:
+            xf = g["x_T"].clone()
+            run_steps(0, W, xf)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            run_steps(W, K, xf)
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1)
+            if world > 1:
+                tfm = torch.tensor([fms], device=dev)
+                dist.all_reduce(tfm, op=dist.ReduceOp.MAX)
+                fms = float(tfm.item())
+            full_scans = {"value": Bg * K / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms / K,
+                          "identical_output": bool(torch.equal(xf, x)),
+                          "note": "lsdm_set_option('select_uniform', 0): FPS / 3-NN run their full scans on clouds whose points all "
+                                  "coincide too; `value` uses the closed forms (bit-identical selections, DESIGN.md 5)"}
+        finally:
+            eng.set_option("select_uniform", 1)
     clk = clocks.stop(t_load0, time.perf_counter()) if rank == 0 else None
     if rank == 0:
         cpu_baseline = None
@@ -353,7 +380,7 @@ def run_ours(args):
                        "l2": "per-step working set (GBs of intermediates over 9*B clouds) is far larger than the 126 MB L2; no flush needed",
                        "weights": "seeded well-conditioned random init (lsdm_b200.synthetic)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernel_time_shares": shares,
-            "cpu_baseline": cpu_baseline, "hoisted": hoisted_info,
+            "cpu_baseline": cpu_baseline, "hoisted": hoisted_info, "uniform_cloud_full_scans": full_scans,
         }
         print(json.dumps(line))
     if world > 1:

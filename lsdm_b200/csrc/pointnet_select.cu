@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ x
     same = fabsf(x0) < INFINITY && fabsf(y0) < INFINITY && fabsf(z0) < INFINITY;  // inf - inf is NaN, not 0: full rounds
     for (int p = tid; p < 1024; p += FPS_T) same = same && src[p * 3] == x0 && src[p * 3 + 1] == y0 && src[p * 3 + 2] == z0;
   }
-  const bool uniform = g_fps_uniform_shortcut && __syncthreads_and(same ? 1 : 0) != 0;
+  // (this barrier also publishes the staged points: it must not sit behind the option's short-circuit)
+  const int all_same = __syncthreads_and(same ? 1 : 0);
+  const bool uniform = g_fps_uniform_shortcut != 0 && all_same != 0;
   // level 1: 1024 of 1024 (an FPS-ordered permutation)
   fps_level<1024, 1024>(ax, ay, az, (int)start[0 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
   for (int p = tid; p < 1024; p += FPS_T) {
@@ -286,8 +288,8 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
   }
   // All S coarse points equal (absent object, zero-padded): every candidate has the same distance, so the scan below keeps
   // candidates 0, 1, 2 (insertion is strict '<', ties keep the lowest index) -- scanning only those three is the same result.
-  const int S_scan = (uniform_shortcut && __syncthreads_and(same ? 1 : 0) != 0 && S >= 3) ? 3 : S;
-  __syncthreads();
+  const int all_same = __syncthreads_and(same ? 1 : 0);  // also the barrier that publishes the staged coarse points
+  const int S_scan = (uniform_shortcut != 0 && all_same != 0 && S >= 3) ? 3 : S;
   // two fine points per thread (one fp32x2 pair).  Each has its OWN insertion branch: an insertion happens ~3/s of the
   // time at coarse point s, so a warp-level branch per query slot is skipped far more often than a shared one would be.
   const int stride = gridDim.x * blockDim.x;
