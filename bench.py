@@ -30,6 +30,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def _claim_stdout():
+    """stdout must carry ONE JSON line, but native libraries print there too (NCCL's "NCCL version ..." banner at communicator
+    creation).  Keep a private duplicate of fd 1 for the result and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return keep
+
+
+def _emit(fd, line):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
 METRIC = "denoising-steps/sec (batch x timesteps)"
 UNIT = "sample-steps/s"
 WORKLOAD = "SDM 1000-step DDPM p_sample_loop, batch=64 per GPU, 9x1024-pt clouds (BASELINE configs[1])"
@@ -170,6 +183,7 @@ def run_ours(args):
     from lsdm_b200.model.sdm import SceneDiffusionModel
     from lsdm_b200.util.model_util import create_gaussian_diffusion, get_default_diffusion, get_default_model_proxd
 
+    out_fd = _claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -177,8 +191,6 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout by default: send them to stderr so that stdout is the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     clocks = ClockSampler(local_rank)
@@ -382,7 +394,7 @@ def run_ours(args):
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernel_time_shares": shares,
             "cpu_baseline": cpu_baseline, "hoisted": hoisted_info, "uniform_cloud_full_scans": full_scans,
         }
-        print(json.dumps(line))
+        _emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
 
