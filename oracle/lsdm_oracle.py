@@ -418,7 +418,7 @@ def encode_conditions(sd, mask_global, given_objs, given_cats, text, fps_starts,
     Returns dict(enc, out_cat, w, pcd_out) where pcd_out is the quantity added to x in place."""
     B = given_objs.shape[0]
     enc = text_embedding(sd, text)
-    out_cat = predict_category(sd, enc)
+    out_cat = predict_category(sd, enc.detach())  # model/sdm.py:156: predict_cat sees enc_text.clone().detach()
     emb_cat = _gelu(_lin(sd, "embed_cat.0", given_cats))
     hm = human_decoder(sd, given_objs[:, 0])
     Fb = pointnet2_backbone(sd, given_objs.reshape(B * N_OBJ, N_PTS, 3), fps_starts, trace, train, drop_mask).reshape(B, N_OBJ, N_PTS * 3)
@@ -514,3 +514,20 @@ def training_losses(sd, tables, x_start, mask, t, given_objs, given_cats, target
     cat_loss = F.cross_entropy(out_cat[:, 0], target_cat.argmax(dim=1)) * lambda_cat
     mse = chamfer_distance(x0.float(), x_start.float())
     return {"cat_loss": cat_loss, "mse": mse, "loss": mse + cat_loss, "model_output": x0}
+
+
+def training_grads(sd, tables, x_start, mask, t, given_objs, given_cats, target_cat, text, fps_starts, noise, drop_mask,
+                   lambda_cat=0.1):
+    """Gradient oracle for SURVEY 8(f) row 1 (run/train_sdm.py:78-84: ``loss.backward()`` in ``model.train()`` mode): autograd on
+    this file's functional forward.  Returns (loss, {parameter name: gradient or None}) for every floating-point entry of ``sd``
+    that is not a BatchNorm running statistic.  Pinned against the live reference by tests/golden/make_golden_grads.py."""
+    leaves = {}
+    for k, v in sd.items():
+        if torch.is_floating_point(v) and not k.endswith(("running_mean", "running_var")):
+            leaves[k] = v.detach().clone().requires_grad_(True)
+    sd2 = {k: leaves.get(k, v) for k, v in sd.items()}
+    terms = training_losses(sd2, tables, x_start, mask, t, given_objs, given_cats, target_cat, text, fps_starts, noise,
+                            lambda_cat=lambda_cat, train={}, drop_mask=drop_mask)
+    names = list(leaves)
+    grads = torch.autograd.grad(terms["loss"], [leaves[k] for k in names], allow_unused=True)
+    return terms["loss"].detach(), dict(zip(names, grads))

@@ -154,3 +154,36 @@ def test_train_mode_forward_and_bn_updates():
         elif k.endswith("num_batches_tracked"):
             assert int(tr["updates"][k]) == int(g[k])
     assert n == 14 and len([k for k in tr["updates"] if k.endswith("running_mean")]) == 22
+
+
+def test_training_gradients_match_reference():
+    """Groundwork for SURVEY 8(f) row 1: autograd on the oracle's functional forward reproduces the gradients the unmodified
+    reference computes with loss.backward() in model.train() mode (norm and sum of every parameter's gradient, full tensors for
+    13 parameters spread over the network, and the same set of dead parameters)."""
+    from golden.make_golden_grads import CASE, FULL
+
+    g = golden("train_grads_wellcond")
+    sd = syn.make_state_dict(0, "wellcond")
+    B = CASE["B"]
+    inp = syn.make_inputs(CASE["seed_in"], B, training=True)
+    fps, noise = syn.make_step_randoms(CASE["seed_rng"], B, 1)
+    drop = syn.make_dropout_mask(CASE["seed_drop"], B)
+    tables = O.diffusion_tables(O.cosine_betas(1000))
+    loss, grads = O.training_grads(sd, tables, inp["x_start"], inp["mask"], inp["t"], inp["given_objs"], inp["given_cats"],
+                                   inp["target_cat"], inp["text_emb"], list(fps[0]), noise[0], drop)
+    assert abs(float(loss) - float(g["loss"])) < 2e-5 * abs(float(g["loss"]))
+    names = [str(n) for n in g["names"]]
+    assert set(names) <= set(grads)
+    for n, norm, s in zip(names, g["norms"], g["sums"]):
+        gr = grads[n]
+        if np.isnan(norm):
+            assert gr is None or float(gr.abs().max()) == 0.0, n    # dead in the reference: no gradient reaches it
+            continue
+        assert gr is not None, n
+        # conv biases in front of a train-mode BatchNorm have a mathematically zero gradient (the batch mean absorbs them): both
+        # sides hold rounding noise there (<= 2e-5 against weight gradients of 1e-2 .. 1), hence the absolute term
+        assert abs(float(gr.double().norm()) - norm) <= 2e-3 * norm + 3e-5, (n, float(gr.double().norm()), norm)
+    for n in FULL:
+        if ".mlp_convs." in n and n.endswith(".bias"):
+            continue  # zero gradient up to rounding noise (see above)
+        assert rel_l2(grads[n], g["grad/" + n]) < 2e-3, n
