@@ -37,6 +37,30 @@ def test_cabi_argument_errors_without_gpu():
     assert lib.lsdm_launch_count(None) == 0
 
 
+def test_cabi_argument_errors_of_the_widened_rows_without_gpu():
+    """Evaluation metrics, CLIP tower and ContactFormer layer entry points validate their arguments before touching the device."""
+    import ctypes as C
+
+    from lsdm_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.lsdm_eval_emd(None, None, 1, 8, 8, None, None, None, None) == _lib.EINVAL
+    one = C.c_void_p(16)  # never dereferenced: the size checks come first
+    assert lib.lsdm_eval_emd(one, one, 1, 8, 9, one, None, None, None) == _lib.EINVAL and b"same number" in lib.lsdm_last_error()
+    assert lib.lsdm_eval_emd(one, one, 1, 2048, 2048, one, None, None, None) == _lib.EINVAL and b"1024" in lib.lsdm_last_error()
+    assert lib.lsdm_eval_fscore(one, one, 1, 5000, 8, C.c_double(0.1), one, one, None) == _lib.EINVAL
+    assert lib.lsdm_eval_topk(one, one, 0, 13, one, 1, one, None) == _lib.EINVAL
+    assert lib.lsdm_clip_create(None, 0) == _lib.EINVAL
+    assert lib.lsdm_clip_finalize(None) == _lib.EINVAL
+    assert lib.lsdm_clip_workspace_bytes(None, 4, 22) == 0 and lib.lsdm_clip_launch_count(None) == 0
+    assert lib.lsdm_clip_encode_text(None, None, 1, 22, None, 0, None, None) == _lib.EINVAL
+    assert lib.lsdm_cf_workspace_bytes(0, 16, 5, 8) == 0 and lib.lsdm_cf_workspace_bytes(1, 256, 655, 8) > 0
+    assert lib.lsdm_cf_mha_forward(None, None, None, 0, 1, 16, 5, 8, 1, None, 0, None, None) == _lib.EINVAL
+    assert lib.lsdm_cf_set_option(b"no_such_option", 1) == _lib.EINVAL
+    w = _lib.CfMhaWeights()
+    assert lib.lsdm_cf_mha_forward(C.byref(w), one, None, 0, 1, 16, 5, 8, 1, one, 0, one, None) == _lib.EINVAL  # null weights
+
+
 def test_state_dict_contract():
     from lsdm_b200.util.model_util import create_model_and_diffusion
 
