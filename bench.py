@@ -285,6 +285,27 @@ def run_ours(args):
                             for r in sorted(detail, key=lambda r: -r["ms"])],
                 "algorithmic_tflops_whole_step": (FLOP_HOISTED if hoisted else FLOP_STRICT) * Bg * K / (ms * 1e-3) / 1e12}
     shares = {k: (v / tot_ms if tot_ms else 0.0) for k, v in cls_ms.items()}
+    # The non-tensor kernel classes against the HBM roofline: ALGORITHMIC bytes per step (what the stage must read
+    # and write once, from the tensor shapes; C = 9 B clouds) / the class's measured time.  They are latency- / issue-bound
+    # exact-fp32 scans, not bandwidth-bound: the fractions say so.
+    Cc = 9 * B
+    lvl_n, lvl_s = (1024, 1024, 256, 64), (1024, 256, 64, 16)          # source points / centroids per SA level
+    sel_bytes = {
+        "fps": Cc * (1024 * 12 + sum(s * (4 + 12) for s in lvl_s) + 4 * 8),                     # xyz in; idx + xyz of 4 levels out
+        "ball_query": Cc * sum(n * 12 + s * 12 + s * 32 * 4 for n, s in zip(lvl_n, lvl_s)),      # points + centroids in; groups out
+        "three_nn": Cc * sum(f * 12 + c * 12 + f * 3 * 8 for f, c in ((64, 16), (256, 64), (1024, 256), (1024, 1024))),
+        "sa_gather": Cc * (64 * 256 * 4 + 16 * 32 * 4 + 16 * 32 * 256 * 4),                       # level 4: projected rows + groups in; rows out
+        "fp_combine": Cc * sum(c * ch * 4 + f * ch * 4 * 2 + f * 3 * 8 for f, c, ch in ((64, 16, 256), (256, 64, 256))),
+    }
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_classes = []
+    for name, nbytes in sel_bytes.items():
+        c_ms = cls_ms.get(name, 0.0) / prof_steps
+        if c_ms > 0:
+            gbs = nbytes / (c_ms * 1e-3) / 1e9
+            hbm_classes.append({"class": name, "ms_per_step": c_ms, "algorithmic_bytes_per_step": int(nbytes), "achieved_gbs": gbs,
+                                "frac_of_hbm_peak": gbs / hbm_peak})
+    roofline["hbm_bound_classes"] = {"peak_gbs": hbm_peak, "peak_source": f"{peak_src} hbm_gbs", "classes": hbm_classes}
 
     # ---- e2e through the public API with host buffers ----
     e2e = None
