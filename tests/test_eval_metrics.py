@@ -118,3 +118,59 @@ def test_fscore_accuracy_chamfer_vs_oracle():
     np.testing.assert_allclose(ch, EO.chamfer_per_sample(x, y), rtol=1e-5, atol=1e-9)
     loss, normals = E.chamfer_distance(torch.from_numpy(x), torch.from_numpy(y))
     assert normals is None and abs(float(loss) - EO.chamfer_per_sample(x, y).mean()) <= 1e-5 * float(loss)
+
+
+def _auction_model(x, y, eps0=1 << 27, eps_final=16, theta=8):
+    """numpy model of eval_metrics.cu::emd_auction_kernel: same integer scaling, epsilon schedule, Jacobi rounds and
+    (bid << 10 | 1023 - person) conflict resolution -- a CPU check of the ALGORITHM (the kernel itself is tested on the GPU)."""
+    n = len(x)
+    ext = max(np.abs(x).max(), np.abs(y).max())
+    _, e2 = np.frexp(np.float32(ext))
+    scale = np.float32(2.0 ** (28 - int(e2)))
+    d = np.sqrt(((x[:, None, :] - y[None, :, :]).astype(np.float32) ** 2).sum(-1, dtype=np.float32)).astype(np.float32)
+    c = np.rint((d * scale).astype(np.float64)).astype(np.int64)
+    assert c.max() < 2 ** 30
+    price = np.zeros(n, np.int64)
+    eps, rounds = eps0, 0
+    while True:
+        owner = -np.ones(n, np.int64)
+        assigned = -np.ones(n, np.int64)
+        while True:
+            L = np.nonzero(assigned < 0)[0]
+            if len(L) == 0:
+                break
+            rounds += 1
+            v = -c[L] - price[None, :]
+            j1 = np.argmax(v, 1)
+            v1 = v[np.arange(len(L)), j1]
+            v[np.arange(len(L)), j1] = np.iinfo(np.int64).min
+            v2 = v.max(1) if n > 1 else v1
+            bid = price[j1] + (v1 - v2 if n > 1 else 0) + eps
+            key = (bid << 10) | (1023 - L)
+            best = {}
+            for k, j in zip(key, j1):
+                best[j] = max(best.get(j, 0), int(k))
+            for j, k in best.items():
+                w = 1023 - (k & 1023)
+                if owner[j] >= 0:
+                    assigned[owner[j]] = -1
+                owner[j], assigned[w], price[j] = w, j, k >> 10
+        if eps <= eps_final:
+            break
+        eps = max(eps // theta, eps_final)
+    assert price.max() < 2 ** 53  # the 64-bit bid key has room
+    return np.sqrt(((x.astype(np.float64) - y[assigned].astype(np.float64)) ** 2).sum(-1)).sum() / n, rounds
+
+
+@pytest.mark.parametrize("n", [1, 2, 17, 96])
+def test_auction_algorithm_model_matches_hungarian(n):
+    r = np.random.RandomState(n)
+    for x, y in (((r.rand(n, 3) - 0.5), (r.rand(n, 3) - 0.5)),                       # uniform vs uniform
+                 ((r.randn(n, 3) * 0.01), (r.rand(n, 3) - 0.5)),                      # collapsed vs spread
+                 (np.round((r.rand(n, 3) - 0.5) * 4) / 4, np.round((r.rand(n, 3) - 0.5) * 4) / 4),   # duplicates / ties
+                 (np.zeros((n, 3)), (r.rand(n, 3) - 0.5) * 100.0)):                   # identical persons, large extent
+        x, y = x.astype(np.float32), y.astype(np.float32)
+        got, rounds = _auction_model(x, y)
+        ref = EO.emd(x, y)
+        assert abs(got - ref) <= 1e-6 * max(ref, 1e-12) + 1e-9, (n, got, ref)
+        assert rounds < (1 << 20)
