@@ -11,9 +11,12 @@ condition encode incl. PointNet++ on 9B clouds, x0 network, posterior + ancestra
 per-step work of the reference; ``--mode hoisted`` encodes once (an algorithmic optimisation, reported separately).
 
 value : device-timed (CUDA events on the launching stream), all inputs already resident in HBM.
-e2e   : same metric through the reference-shaped public API (p_sample_loop over the same K timesteps) with HOST
-        (pinned) condition buffers: host->device copies of conditions and per-step FPS starts and the final
-        device->host read of the samples are inside the timed region.
+e2e   : same metric through the reference's own entry point, ``diffusion.p_sample_loop(...)`` with exactly the keyword
+        arguments of run/test_sdm.py:166-182 (skip_timesteps leaves the same K timesteps), with HOST (pinned) condition
+        buffers: host->device copies of conditions and per-step FPS starts and the final device->host read of the
+        samples are inside the timed region.
+extra_configs : BASELINE configs 3, 4, 5 measured in the same run (each with its own device-timed value and e2e), a
+        full 1000-step B=64 loop (wall seconds), the fp32 / 3xTF32-everywhere builds, and a PyTorch-eager-on-GPU baseline.
 N > 1 : weak scaling, B samples per GPU, samples sharded across ranks (global mask replicated), one NCCL all-gather of
         the outputs at the end of the timed region.
 """
@@ -61,6 +64,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra_configs (BASELINE configs 3-5, full loop, precision variants, eager baseline)")
     return ap.parse_args()
 
 
@@ -123,7 +127,7 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's p_sample, "as written" (materialised point attention), all host threads
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(steps, warmup, micro_batch=4):
+def cpu_port_rate(steps, warmup, micro_batch=8):
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -154,11 +158,52 @@ def cpu_port_rate(steps, warmup, micro_batch=4):
             "sec_per_step": sec / len(timed)}
 
 
+def gpu_eager_rate(steps, warmup, micro_batch=8):
+    """Second baseline: the same port of the reference's p_sample executed eagerly by PyTorch on this GPU
+    (stock ATen / cuBLAS kernels, TF32 off, as written incl. the materialised 1024x1024 point attention), micro-batched."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lsdm_oracle as O
+    from lsdm_b200 import synthetic as syn
+
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        sd = {k: v.cuda() for k, v in syn.make_state_dict(0, "wellcond").items()}
+        tables = O.diffusion_tables(O.cosine_betas(1000))
+        inp = {k: v.cuda() for k, v in syn.make_inputs(1234, micro_batch).items()}
+        fps, noise = syn.make_step_randoms(4321, micro_batch, steps + warmup)
+        fps, noise = fps.cuda(), noise.cuda()
+        x = inp["x_T"].clone()
+        times = []
+        torch.set_default_device("cuda")
+        try:
+            with torch.no_grad():
+                for k in range(steps + warmup):
+                    t = torch.full((micro_batch,), 999 - k, dtype=torch.long)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    out = O.p_sample(sd, tables, x, inp["mask"], t, inp["given_objs"], inp["given_cats"], inp["text_emb"], list(fps[k]),
+                                     noise[k], as_written=True)
+                    x = out["sample"]
+                    torch.cuda.synchronize()
+                    times.append(time.perf_counter() - t0)
+        finally:
+            torch.set_default_device("cpu")
+        timed = times[warmup:]
+        return {"value": micro_batch * len(timed) / sum(timed), "unit": UNIT, "kind": "port, torch eager on cuda",
+                "sample": f"oracle port of the reference p_sample run by PyTorch eager on the GPU (as written, fp32, TF32 off): micro-batch "
+                          f"{micro_batch} x {len(timed)} timed steps after {warmup} warm-up", "finite": bool(torch.isfinite(x).all().item())}
+    except Exception as e:  # a baseline leg must never take the benchmark down
+        return {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 5))   # BASELINE.md section 3: micro-batch 8, K=5 timed steps after 1 warm-up
     warm = max(1, min(args.warmup, 1))
     cb = cpu_port_rate(steps, warm)
     line = {
@@ -307,49 +352,59 @@ def run_ours(args):
                                 "frac_of_hbm_peak": gbs / hbm_peak})
     roofline["hbm_bound_classes"] = {"peak_gbs": hbm_peak, "peak_source": f"{peak_src} hbm_gbs", "classes": hbm_classes}
 
-    # ---- e2e through the public API with host buffers ----
-    e2e = None
-    if not args.no_e2e:
-        from lsdm_b200.diffusion import gaussian_diffusion as gdm
+    # ---- e2e through the reference's own entry point with host buffers ----
+    def ref_call(dd, batch, hostd, skip):
+        """diffusion.p_sample_loop with exactly the keyword arguments of reference run/test_sdm.py:166-182."""
+        return dd.p_sample_loop(model, [batch, 1024, 3], hostd["mask"], hostd["given_objs"], hostd["given_cats"], y=hostd["text_emb"],
+                                clip_denoised=False, model_kwargs=None, skip_timesteps=skip, init_image=None, progress=False,
+                                dump_steps=None, noise=None, const_noise=False)
 
+    def time_e2e(dd, batch, hostd, n_steps, warm_steps, repeats=3):
         torch.manual_seed(7)
-        # W untimed warm-up steps through the SAME public call (first-use costs of the API path: device RNG initialisation,
-        # lazy module loads of torch's own kernels, pinned staging buffers)
-        # (same call shape as the timed one, so that the caching allocator and the pinned staging buffers are warm: max(W, K) steps)
-        diff.p_sample_loop_fused(model, (B, 1024, 3), host["mask"], host["given_objs"], host["given_cats"], host["text_emb"],
-                                 noise=None, clip_denoised=False, device=dev, skip_timesteps=T - max(W, K), hoisted=hoisted,
-                                 chunk=K).cpu()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        # the reference's call: diffusion.p_sample_loop(model, shape, mask, given_objs, given_cats, y, clip_denoised=False);
-        # skip_timesteps leaves K timesteps; host tensors are uploaded inside (Engine._f32), result read back.
-        # Three back-to-back calls, each timed on its own with a synchronize on both sides; the best one is reported (a host
-        # hiccup of tens of ms -- scheduler, nvidia-smi polling -- otherwise lands in a 50-100 ms region) and all three are listed.
-        e2e_runs = []
-        for _ in range(3):
+        with torch.no_grad():
+            ref_call(dd, batch, hostd, dd.num_timesteps - warm_steps).cpu()   # untimed: first-use costs of the API path
+        runs, out_host = [], None
+        for _ in range(repeats):
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            out = diff.p_sample_loop_fused(model, (B, 1024, 3), host["mask"], host["given_objs"], host["given_cats"], host["text_emb"],
-                                           noise=None, clip_denoised=False, device=dev, skip_timesteps=T - K, hoisted=hoisted, chunk=K)
-            out_host = out.cpu()
+            with torch.no_grad():
+                out_host = ref_call(dd, batch, hostd, dd.num_timesteps - n_steps).cpu()
             torch.cuda.synchronize()
-            e2e_runs.append(time.perf_counter() - t0)
+            runs.append(time.perf_counter() - t0)
         if world > 1:
-            tdt = torch.tensor(e2e_runs, device=dev, dtype=torch.float64)
+            tdt = torch.tensor(runs, device=dev, dtype=torch.float64)
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)  # per call: the slowest rank
-            e2e_runs = [float(v) for v in tdt.tolist()]
-        dt = min(e2e_runs)
+            runs = [float(v) for v in tdt.tolist()]
+        cond_bytes = sum(hostd[k].numel() * 4 for k in ("mask", "given_objs", "given_cats", "text_emb"))
+        return {"value": batch * world * n_steps / min(runs), "unit": UNIT, "h2d_bytes_per_step": int(cond_bytes / n_steps + 4 * 9 * batch * 8),
+                "d2h_bytes_per_step": int(out_host.numel() * 4 / n_steps), "runs_sample_steps_per_s": [batch * world * n_steps / v for v in runs]}
+
+    e2e = None
+    if not args.no_e2e and not hoisted:
+        # Three back-to-back calls, each timed on its own with a synchronize on both sides; the best one is reported (a host
+        # hiccup of tens of ms -- scheduler, nvidia-smi polling -- otherwise lands in a 50-100 ms region) and all three are listed.
+        e2e = time_e2e(diff, B, host, K, max(W, K))
+        e2e["note"] = ("diffusion.p_sample_loop(model, shape, mask, given_objs, given_cats, y=..., clip_denoised=False, model_kwargs=None, "
+                       "skip_timesteps=T-K, init_image=None, progress=False, dump_steps=None, noise=None, const_noise=False) -- the call of "
+                       "reference run/test_sdm.py:166-182 -- over the same K timesteps; conditions (pinned host) uploaded once per call, FPS "
+                       "starts drawn on the CPU generator and uploaded per chunk, noise drawn on the device generator (as the reference "
+                       "does), final samples read back; best of 3 calls")
+    elif not args.no_e2e:
+        torch.manual_seed(7)
+        runs = []
+        for i in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out_host = diff.p_sample_loop_fused(model, (B, 1024, 3), host["mask"], host["given_objs"], host["given_cats"], host["text_emb"],
+                                                clip_denoised=False, device=dev, skip_timesteps=T - K, hoisted=True).cpu()
+            torch.cuda.synchronize()
+            if i:
+                runs.append(time.perf_counter() - t0)
         cond_bytes = sum(host[k].numel() * 4 for k in ("mask", "given_objs", "given_cats", "text_emb"))
-        fps_bytes = 4 * 9 * B * 8
-        e2e = {"value": Bg * K / dt, "unit": UNIT, "h2d_bytes_per_step": int(cond_bytes / K + fps_bytes),
-               "d2h_bytes_per_step": int(out_host.numel() * 4 / K),
-               "note": "p_sample_loop_fused over the same K timesteps via the reference-shaped API; conditions (pinned host) uploaded once per "
-                       "call, FPS starts drawn on the CPU generator and uploaded per chunk, noise drawn on the device generator "
-                       "(as the reference does), final samples read back; best of 3 calls",
-               "runs_sample_steps_per_s": [Bg * K / v for v in e2e_runs]}
+        e2e = {"value": Bg * K / min(runs), "unit": UNIT, "h2d_bytes_per_step": int(cond_bytes / K), "d2h_bytes_per_step": int(out_host.numel() * 4 / K),
+               "note": "p_sample_loop_fused(hoisted=True) with host buffers; best of 3"}
 
     # ---- hoisted variant (conditions encoded once per loop; an algorithmic optimisation, reported separately) ----
     hoisted_info = None
@@ -398,11 +453,234 @@ def run_ours(args):
                                   "coincide too; `value` uses the closed forms (bit-identical selections, DESIGN.md 5)"}
         finally:
             eng.set_option("select_uniform", 1)
+    def dev_timed(fn):
+        """CUDA-event time of fn() on the current stream, barrier + synchronize on both sides, max over ranks (ms)."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        fn()
+        a1.record()
+        torch.cuda.synchronize()
+        t_ms = a0.elapsed_time(a1)
+        if world > 1:
+            tt = torch.tensor([t_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt.item())
+        return t_ms
+
+    # ---- N > 1: driver-side proof that the sharded results are right: rank 0 recomputes rank 1's shard of the timed leg ----
+    gather_check = None
+    if world > 1 and not hoisted:
+        if rank == 0:
+            sl1 = slice(B, 2 * B)
+            model.set_shard(Bg, B)
+            eng1 = diff._engine(model, B, dev)
+            g1 = {k: (inp[k] if k == "mask" else inp[k][sl1].contiguous()).to(dev) for k in ("mask", "given_objs", "given_cats", "text_emb", "x_T")}
+            fps1 = fps_all.view(W + K, 4, Bg, 9)[:, :, sl1].reshape(W + K, 4, B * 9).contiguous().to(dev)
+            nz1 = noise_all[:, sl1].contiguous().to(dev)
+            x1 = g1["x_T"].clone()
+            for first, n in ((0, W), (W, K)):
+                eng1.sample_loop(x1, g1["text_emb"], g1["given_objs"], g1["given_cats"], g1["mask"], fps1[first:first + n], nz1[first:first + n],
+                                 T - 1 - first, False)
+            torch.cuda.synchronize()
+            gather_check = {"max_abs": float((x1 - gather_buf[1]).abs().max().item()), "own_shard_max_abs": float((x - gather_buf[0]).abs().max().item()),
+                            "note": f"rank 0 recomputed rank 1's shard (samples {B}..{2 * B - 1} of the global batch, {W}+{K} steps, global mask / "
+                                    "offsets) and compared it with what the all-gather delivered; must be 0.0"}
+            model.set_shard(Bg, off)
+            diff._engine(model, B, dev)
+        dist.barrier()
+
+    extra = None
+    if not args.no_extras and not hoisted:
+        extra = {}
+        sd0 = syn.make_state_dict(0, "wellcond")
+
+        def shard_inputs(seed, per_rank, total, training=False):
+            gi = syn.make_inputs(seed, total, training=training)
+            lo = rank * per_rank
+            hostd = {k: (v if k == "mask" else v[lo:lo + per_rank].contiguous()).pin_memory() for k, v in gi.items()}
+            return gi, hostd, {k: v.to(dev) for k, v in hostd.items()}
+
+        def loop_leg(dd, per_rank, total, n_steps, warm, seed, gather=True, e2e_repeats=2):
+            """n_steps consecutive steps of dd's loop at per_rank samples per GPU (global batch `total`): device-timed + e2e."""
+            model.set_shard(total, rank * per_rank)
+            en = dd._engine(model, per_rank, dev)
+            _, hostd, gd_ = shard_inputs(seed, per_rank, total)
+            fa, na = syn.make_step_randoms(seed + 1, total, warm + n_steps)
+            lo = rank * per_rank
+            fl = fa.view(warm + n_steps, 4, total, 9)[:, :, lo:lo + per_rank].reshape(warm + n_steps, 4, per_rank * 9).contiguous().to(dev)
+            nl = na[:, lo:lo + per_rank].contiguous().to(dev)
+            xx = gd_["x_T"].clone()
+            gb = torch.empty(world, per_rank, 1024, 3, device=dev) if (world > 1 and gather) else None
+            t_hi = dd.num_timesteps - 1
+
+            def run(first, n):
+                en.sample_loop(xx, gd_["text_emb"], gd_["given_objs"], gd_["given_cats"], gd_["mask"], fl[first:first + n], nl[first:first + n],
+                               t_hi - first, False)
+
+            run(0, warm)
+
+            def timed():
+                run(warm, n_steps)
+                if gb is not None:
+                    dist.all_gather_into_tensor(gb.view(-1), xx.view(-1))
+
+            t_ms = dev_timed(timed)
+            leg = {"value": total * n_steps / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / n_steps, "steps": n_steps, "warmup": warm,
+                   "global_batch": total, "per_gpu_batch": per_rank, "finite": bool(torch.isfinite(xx).all().item())}
+            if not args.no_e2e:
+                leg["e2e"] = time_e2e(dd, per_rank, hostd, n_steps, max(warm, min(n_steps, 10)), repeats=e2e_repeats)
+            del fl, nl, xx, gd_
+            return leg
+
+        # ---- BASELINE config 3: 100-step respaced ('ddim100') ancestral loop, B=256, one GPU: the WHOLE loop is timed ----
+        if world == 1:
+            diff3 = create_gaussian_diffusion(get_default_diffusion(), timestep_respacing="ddim100")
+            leg = loop_leg(diff3, 256, 256, diff3.num_timesteps - 3, 3, 5150, gather=False)
+            leg["workload"] = ("BASELINE configs[2]: SpacedDiffusion(space_timesteps(1000,'ddim100')), ancestral p_sample_loop (the only respaced sampler "
+                               "alive in the reference), batch 256, 1 GPU; device leg = steps 96..0 after 3 warm-up steps, e2e = the full 100-step call")
+            if not args.no_e2e:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    _, h3, _ = shard_inputs(5150, 256, 256)
+                    ref_call(diff3, 256, h3, 0).cpu()
+                torch.cuda.synchronize()
+                dt3 = time.perf_counter() - t0
+                leg["full_loop_wall_s"] = dt3
+                leg["full_loop_sample_steps_per_s"] = 256 * 100 / dt3
+            extra["config3_respaced100_b256"] = leg
+
+        # ---- BASELINE config 4: training_losses forward, 64 samples per GPU, eval-BN and train-BN (+SyncBN over ranks) ----
+        B4, K4, W4 = 64, 5, 2
+        if world > 1:
+            model.set_shard(B4 * world, rank * B4, sync_bn_group=True)
+        else:
+            model.set_shard(None)
+        _, host4, g4 = shard_inputs(7700, B4, B4 * world, training=True)
+        cfg4 = {}
+        for mode_name in ("eval_bn", "train_bn"):
+            model.train(mode_name == "train_bn")
+
+            def one(src, read_back):
+                terms = diff.training_losses(model, src["x_start"], src["mask"], src["t"], src["given_objs"], src["given_cats"], src["target_cat"],
+                                             y=src["text_emb"])
+                vec = torch.stack([terms["loss"].detach(), terms["mse"].detach(), terms["cat_loss"].detach()])
+                if world > 1:
+                    dist.all_reduce(vec)   # the path's one exchange step: three scalars
+                    vec = vec / world
+                return vec.cpu() if read_back else vec
+
+            torch.manual_seed(11)
+            with torch.no_grad():
+                for _ in range(W4):
+                    one(g4, False)
+                t_ms = dev_timed(lambda: [one(g4, False) for _ in range(K4)])
+                runs4 = []
+                last = None
+                for _ in range(K4 + 1):
+                    torch.cuda.synchronize()
+                    if world > 1:
+                        dist.barrier()
+                    t0 = time.perf_counter()
+                    last = one(host4, True)   # host inputs in, three scalars read back
+                    runs4.append(time.perf_counter() - t0)
+            dt4 = sum(runs4[1:]) / K4
+            if world > 1:
+                tt = torch.tensor([dt4], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt4 = float(tt.item())
+            h2d4 = sum(host4[k].numel() * host4[k].element_size() for k in ("x_start", "mask", "t", "given_objs", "given_cats", "target_cat", "text_emb"))
+            cfg4[mode_name] = {"value": B4 * world * K4 / (t_ms * 1e-3), "unit": "samples/s", "ms_per_forward": t_ms / K4, "steps": K4, "warmup": W4,
+                               "loss": float(last[0]), "mse": float(last[1]), "cat_loss": float(last[2]),
+                               "e2e": {"value": B4 * world / dt4, "unit": "samples/s", "h2d_bytes_per_step": int(h2d4), "d2h_bytes_per_step": 12}}
+        model.eval()
+        model.load_state_dict(sd0)   # train-mode forwards moved the BatchNorm running statistics
+        cfg4["workload"] = (f"BASELINE configs[3]: diffusion.training_losses forward (q_sample + SDM forward + chamfer + category CE), {B4} samples per GPU, "
+                            f"global batch {B4 * world}; eval_bn = model.eval() (folded BatchNorm), train_bn = model.train() (batch statistics over all "
+                            "9B clouds, running-stat updates, Dropout; SyncBN all-reduce of the statistics when N > 1); one all-reduce of the three loss scalars")
+        extra["config4_training_forward_b64_per_gpu"] = cfg4
+
+        # ---- BASELINE config 5: 1000-step sampling at batch 1024 over 8 GPUs: 128 per GPU (weak) and 1024 in total (strong) ----
+        K5 = min(K, 10)
+        leg = loop_leg(diff, 128, 128 * world, K5, 3, 5500)
+        leg["workload"] = "BASELINE configs[4], weak scaling: 128 samples per GPU (1024 at N=8), first K timesteps of the 1000-step loop + one all-gather"
+        extra["config5_weak_b128_per_gpu"] = leg
+        per_rank = 1024 // world
+        mb = min(per_rank, 256)
+        n_mb = per_rank // mb
+        gi5 = syn.make_inputs(5600, 1024)
+        fa5, na5 = syn.make_step_randoms(5601, 1024, 2 + K5)
+        sets = []
+        for j in range(n_mb):
+            lo = rank * per_rank + j * mb
+            sets.append({"lo": lo, "g": {k: (v if k == "mask" else v[lo:lo + mb].contiguous()).to(dev) for k, v in gi5.items()},
+                         "fps": fa5.view(2 + K5, 4, 1024, 9)[:, :, lo:lo + mb].reshape(2 + K5, 4, mb * 9).contiguous().to(dev),
+                         "nz": na5[:, lo:lo + mb].contiguous().to(dev)})
+        xs = torch.cat([s_["g"]["x_T"] for s_ in sets]).clone()
+        gb5 = torch.empty(world, per_rank, 1024, 3, device=dev) if world > 1 else None
+
+        def strong(first, n):
+            for j, s_ in enumerate(sets):
+                model.set_shard(1024, s_["lo"])
+                en = diff._engine(model, mb, dev)
+                gg = s_["g"]
+                en.sample_loop(xs[j * mb:(j + 1) * mb], gg["text_emb"], gg["given_objs"], gg["given_cats"], gg["mask"], s_["fps"][first:first + n],
+                               s_["nz"][first:first + n], T - 1 - first, False)
+            if gb5 is not None and first > 0:
+                dist.all_gather_into_tensor(gb5.view(-1), xs.view(-1))
+
+        strong(0, 2)
+        t_ms = dev_timed(lambda: strong(2, K5))
+        extra["config5_strong_b1024_total"] = {
+            "value": 1024 * K5 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / K5, "steps": K5, "warmup": 2, "global_batch": 1024,
+            "per_gpu_batch": per_rank, "micro_batch": mb, "finite": bool(torch.isfinite(xs).all().item()),
+            "workload": f"BASELINE configs[4], strong scaling: 1024 samples in total, {per_rank} per GPU processed as {n_mb} shard(s) of {mb} with the "
+                        "global mask / offsets (bit-identical to one 1024-sample batch), first K timesteps + one all-gather"}
+        del sets, xs, gi5, fa5, na5
+
+        if world == 1:
+            # ---- the named workload run in full: 1000 steps x 64 samples through the reference's call (anchors the K-step rate) ----
+            model.set_shard(Bg, off)
+            if not args.no_e2e:
+                torch.manual_seed(7)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    full = ref_call(diff, B, host, 0).cpu()
+                torch.cuda.synchronize()
+                dtf = time.perf_counter() - t0
+                extra["full_loop_1000_steps_b64"] = {"wall_s": dtf, "value": B * T / dtf, "unit": UNIT, "finite": bool(torch.isfinite(full).all().item()),
+                                                    "note": "diffusion.p_sample_loop(...) exactly as run/test_sdm.py:166-182 calls it (skip_timesteps=0): "
+                                                            "64 000 sample-steps, host condition buffers in, samples read back, wall clock"}
+            # ---- the other builds of the dense layers beside the `tf32` headline ----
+            eng = diff._engine(model, B, dev)
+            variants = {}
+            for pname, kp in (("fp32", 4), ("3xtf32", 8), ("tf32-all", 8)):
+                try:
+                    eng.set_precision(pname)
+                    xv = g["x_T"].clone()
+                    run_steps(0, 2, xv)
+                    t_ms = dev_timed(lambda: run_steps(2, kp, xv))
+                    variants[pname] = {"value": B * kp / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / kp, "steps": kp}
+                except Exception as e:
+                    variants[pname] = {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
+            eng.set_precision("tf32")
+            variants["note"] = ("same K-step leg with every dense layer in fp32 on the CUDA cores ('fp32'), split-TF32 everywhere ('3xtf32', fp32-grade) "
+                                "and single-pass TF32 everywhere ('tf32-all'); the headline build is 'tf32' (TF32 encoder, 3xTF32 x0 network)")
+            extra["precision_variants"] = variants
+            # ---- second baseline: the same port run eagerly by PyTorch on this GPU ----
+            if not args.no_cpu_baseline:
+                extra["gpu_eager_baseline"] = gpu_eager_rate(3, 1)
+        model.set_shard(Bg, off)
+
     clk = clocks.stop(t_load0, time.perf_counter()) if rank == 0 else None
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_port_rate(4, 1)
+            cb = cpu_port_rate(5, 1)  # BASELINE.md section 3: micro-batch 8 x 5 timed steps after 1 warm-up
             cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -414,6 +692,7 @@ def run_ours(args):
                        "weights": "seeded well-conditioned random init (lsdm_b200.synthetic)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernel_time_shares": shares,
             "cpu_baseline": cpu_baseline, "hoisted": hoisted_info, "uniform_cloud_full_scans": full_scans,
+            "gather_check": gather_check, "extra_configs": extra,
         }
         _emit(out_fd, line)
     if world > 1:

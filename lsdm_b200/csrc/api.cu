@@ -612,7 +612,11 @@ __global__ void fill_t_kernel(int64_t* t, int n, int64_t v) {
 
 extern "C" {
 
-LSDM_API const char* lsdm_version(void) { return "lsdm_b200 0.1 sm_100a"; }
+#ifndef LSDM_SRC_HASH
+#define LSDM_SRC_HASH "unknown"
+#endif
+// "... src:<first 16 hex digits of sha256(cat of csrc/*.cu, *.cuh and include/lsdm_b200.h in Makefile order)>"
+LSDM_API const char* lsdm_version(void) { return "lsdm_b200 0.2 sm_100a src:" LSDM_SRC_HASH; }
 LSDM_API const char* lsdm_last_error(void) { return g_err.c_str(); }
 
 LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
@@ -621,7 +625,10 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
       cfg->batch_offset + cfg->batch_local > cfg->batch_global)
     return fail(LSDM_EINVAL, "bad batch configuration");
   if (cfg->n_cats <= 0 || cfg->n_cats > 32) return fail(LSDM_EINVAL, "n_cats must be in 1..32");
+  int prev_dev = 0;
+  CK(cudaGetDevice(&prev_dev));
   CK(cudaSetDevice(cfg->device));
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev_dev};  // the caller's current device is left as it was
   lsdm_handle* h = new lsdm_handle();
   h->cfg = *cfg;
   build_registry(h);
@@ -649,7 +656,10 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
 
 LSDM_API void lsdm_destroy(lsdm_handle* h) {
   if (!h) return;
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
   cudaSetDevice(h->cfg.device);
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev_dev};
   if (h->arena) cudaFree(h->arena);
   if (h->sched) cudaFree(h->sched);
   if (h->side) cudaStreamDestroy(h->side);

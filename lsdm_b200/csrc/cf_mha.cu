@@ -401,21 +401,13 @@ LSDM_API int lsdm_cf_mha_forward(const lsdm_cf_mha_weights* w, const float* x, c
   if ((seg_len & 31) == 0 && g_cf_attn_tc && precision == 1) {  // single-pass TF32 operands: only where the caller asked for TF32
     // tensor-core attention: K + V^T + one Q tile as swizzled TF32 operands (+1 KB alignment slack)
     const size_t smem = (size_t)seg_len * 512 + 32 * 1024 + 1024;
-    static bool attr_tc = false;
-    if (!attr_tc) {
-      if (cudaFuncSetAttribute(cf_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 512 + 33 * 1024) != cudaSuccess)
-        return set_error(LSDM_ECUDA, "cudaFuncSetAttribute(cf_attn_tc_kernel)");
-      attr_tc = true;
-    }
+    static PerDeviceOnce attr_tc;
+  if (smem_opt_in(attr_tc, cf_attn_tc_kernel, 256 * 512 + 33 * 1024) != cudaSuccess) return set_error(LSDM_ECUDA, "cudaFuncSetAttribute(cf_attn_tc_kernel)");
     cf_attn_tc_kernel<<<dim3(H, n_verts, bs), 256, smem, st>>>(ws.qkv, mask, all_masked, seg_len, n_verts, H, ws.att);
   } else {
     const size_t smem = sizeof(float) * ((((size_t)seg_len * (CF_D + 1) + 3) & ~size_t(3)) + (size_t)seg_len * CF_D + CF_WARPS * CF_D + (size_t)CF_WARPS * seg_len);
-    static bool attr_done = false;
-    if (!attr_done) {
-      if (cudaFuncSetAttribute(cf_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
-        return set_error(LSDM_ECUDA, "cudaFuncSetAttribute(cf_attn_kernel)");
-      attr_done = true;
-    }
+    static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, cf_attn_kernel, 160 * 1024) != cudaSuccess) return set_error(LSDM_ECUDA, "cudaFuncSetAttribute(cf_attn_kernel)");
     cf_attn_kernel<<<dim3(H, n_verts, bs), CF_WARPS * 32, smem, st>>>(ws.qkv, mask, all_masked, seg_len, n_verts, H, 1.0f / sqrtf((float)CF_D), ws.att);
   }
   if (cf_gemm(ws.att, HD, w->fc_w, HD, w->fc_b, ws.y, CF_D, rows, CF_D, HD, ACT_NONE, precision, st) < 0)

@@ -344,11 +344,8 @@ LSDM_API int lsdm_clip_encode_text(lsdm_clip* h, const int32_t* tokens, int32_t 
     ++h->launches;
   };
   const size_t attn_smem = sizeof(float) * ((size_t)L * (HEAD_DIM + 1) + (size_t)L * HEAD_DIM + 4 * HEAD_DIM + 4 * (size_t)L);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CCK(cudaFuncSetAttribute(clip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  CCK(smem_opt_in(attr_done, clip_attn_kernel, 64 * 1024));
   embed_ln(h->W(blk(0, "ln_1.weight")), h->W(blk(0, "ln_1.bias")));
   for (int l = 0; l < h->layers; ++l) {
     if (clip_gemm(h, w.hn, W, h->W(blk(l, "attn.in_proj_weight")), h->W(blk(l, "attn.in_proj_bias")), w.qkv, rows, 3 * W, W, ACT_NONE, st) < 0)

@@ -4,7 +4,32 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace lsdm {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: every launcher opts in once per
+// (kernel, device), not once per process (a second GPU driven from the same process needs its own opt-in).
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const uint64_t bit = 1ull << (d & 63);
+    return !(mask.fetch_or(bit) & bit);
+  }
+};
+template <typename Kernel>
+inline cudaError_t smem_opt_in(PerDeviceOnce& once, Kernel kernel, int bytes) {
+  if (!once.first()) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+inline int device_sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
 
 constexpr int NPTS = 1024;  // points per cloud
 constexpr int NOBJ = 9;     // object slots per scene

@@ -271,12 +271,8 @@ size_t emd_smem_bytes(int n) {
 int launch_emd(const float* x, const float* y, int B, int n, double* out_emd, int* out_assign, int* out_rounds, cudaStream_t st) {
   if (n < 1 || n > EMD_MAXN) return -1;
   const size_t smem = emd_smem_bytes(n);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emd_smem_bytes(EMD_MAXN)) != cudaSuccess)
-      return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, emd_auction_kernel, (int)emd_smem_bytes(EMD_MAXN)) != cudaSuccess) return -1;
   emd_auction_kernel<<<B, EMD_THREADS, smem, st>>>(x, y, n, out_emd, out_assign, out_rounds);
   return 1;
 }

@@ -479,11 +479,8 @@ int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, co
   if (CA != 64 || C1 != 256 || C2 != 128 || N < 128 || (N & (N - 1)) != 0) return -1;
   FpArgs a{X, Wa, ba, Pb, nn_idx, nn_w, W1, b1, out, n_clouds * (N / 128), S, __builtin_ctz(N), round_out};
   constexpr int smem = 256 * 64 * 4 + 128 * 256 * 4 + 2 * 128 * 32 * 4 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(fp_fused_kernel<64, 256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, fp_fused_kernel<64, 256, 128>, smem) != cudaSuccess) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -511,11 +508,8 @@ int launch_fp1_fused(const float* Pb, const int* nn_idx, const float* nn_w, cons
   for (int i = 0; i < 384; ++i) k.wc[i] = h_consts[384 + i];
   for (int i = 0; i < 3; ++i) k.bc[i] = h_consts[768 + i];
   constexpr int smem = 3 * 128 * 128 * 4 + 2 * 128 * 32 * 4 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(fp1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, fp1_fused_kernel, smem) != cudaSuccess) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

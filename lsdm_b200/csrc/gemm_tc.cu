@@ -176,11 +176,8 @@ __global__ void __launch_bounds__(TNT) gemm_tc_kernel(GemmArgs g) {
 template <int BN, bool SPLIT>
 int launch_bn2(const GemmArgs& g, cudaStream_t st) {
   constexpr int smem = 2 * (A_STAGE + BN * 128) * (SPLIT ? 2 : 1) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, gemm_tc_kernel<BN, SPLIT>, smem) != cudaSuccess) return -1;
   int batch = g.batch > 0 ? g.batch : 1;
   dim3 grid((g.M + TBM - 1) / TBM, g.N / BN, batch);
   gemm_tc_kernel<BN, SPLIT><<<grid, TNT, smem, st>>>(g);

@@ -373,17 +373,9 @@ int launch_ws2(const GemmArgs& g, cudaStream_t st) {
   constexpr int nstage = ws_nstage(BN, SPLIT, ASYNC);
   constexpr int smem = nstage * (W_A_STAGE + BN * 128) * (SPLIT ? 2 : 1) + ws_epi_warps(BN, SPLIT) * 32 * WSTG * 4 + 1024;
   static_assert(smem <= 227 * 1024 - 8 * 1024, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_ws_kernel<BN, SPLIT, ASYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr_done = true;
-  }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, gemm_ws_kernel<BN, SPLIT, ASYNC>, smem) != cudaSuccess) return -1;
+  const int sms = device_sm_count();
   const int batch = g.batch > 0 ? g.batch : 1;
   const int tiles_m = (g.M + WBM - 1) / WBM, tiles_n = g.N / BN;
   const int64_t total = (int64_t)tiles_m * tiles_n * batch;

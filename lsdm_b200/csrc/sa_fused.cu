@@ -284,13 +284,8 @@ int launch_t(const SaArgs& a, cudaStream_t st) {
   static_assert(per_sm >= 1, "does not fit");
   constexpr int floor_smem = (227 * 1024) / (per_sm + 1) + 1;  // > 1/(per_sm+1) of the SM => at most per_sm CTAs
   constexpr int smem = need > floor_smem ? need : floor_smem;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-        cudaSuccess)
-      return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, sa_fused_kernel<C1, C2, C3, FIRST, A_TMEM, NT>, smem) != cudaSuccess) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -555,12 +550,8 @@ int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float
   constexpr int per_sm = by_smem < want ? by_smem : want;
   constexpr int floor_smem = (227 * 1024) / (per_sm + 1) + 1;
   constexpr int smem = need > floor_smem ? need : floor_smem;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(sa_fused_v2_kernel<C1, C2, C3, FIRST, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, sa_fused_v2_kernel<C1, C2, C3, FIRST, NT>, smem) != cudaSuccess) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -757,11 +748,8 @@ int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const flo
   for (int i = 0; i < 384; ++i) k.wc[i] = h_consts[384 + i];
   for (int i = 0; i < 3; ++i) k.bc[i] = h_consts[768 + i];
   constexpr int smem = 3 * 128 * 128 * 4 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(fp1_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, fp1_tail_kernel, smem) != cudaSuccess) return -1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

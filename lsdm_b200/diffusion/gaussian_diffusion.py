@@ -206,7 +206,16 @@ class GaussianDiffusion:
     def p_sample_loop(self, model, shape, mask, given_objs, given_cats, y, noise=None, clip_denoised=True, denoised_fn=None,
                       cond_fn=None, model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
                       randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False):
-        """Reference gaussian_diffusion.py:611-682."""
+        """Reference gaussian_diffusion.py:611-682.  The call every reference driver makes (run/test_sdm.py:166-182,
+        run/train_sdm.py:132-148, run/scene_edit.py:296-313) -- ``dump_steps=None``, no progress bar -- runs the whole loop
+        inside the library (``lsdm_sample_loop``: three-stream pipeline, no per-step Python); intermediate dumps and the
+        tqdm bar need the per-step generator and take :meth:`p_sample_loop_progressive`.  Both give the same tensors for the
+        same RNG state (tests/test_gpu_parity.py)."""
+        if dump_steps is None and not progress and not const_noise:
+            if denoised_fn is not None or cond_fn is not None or cond_fn_with_grad or randomize_class:
+                raise NotImplementedError("denoised_fn / cond_fn guidance / randomize_class are not used by any SDM caller")
+            return self._sample_loop_library(model, shape, mask, given_objs, given_cats, y, noise=noise, clip_denoised=clip_denoised,
+                                             device=device, skip_timesteps=skip_timesteps, init_image=init_image)
         final = None
         dump = [] if dump_steps is not None else None
         for i, sample in enumerate(self.p_sample_loop_progressive(
@@ -247,29 +256,43 @@ class GaussianDiffusion:
                 yield out
                 img = out["sample"]
 
-    def p_sample_loop_fused(self, model, shape, mask, given_objs, given_cats, y, noise=None, clip_denoised=True, device=None,
-                            skip_timesteps=0, hoisted=False, chunk=50):
-        """Same result as :meth:`p_sample_loop`, with the loop body inside ``lsdm_sample_loop`` (no per-step Python):
-        per chunk of ``chunk`` steps the FPS starts and noises are drawn in the reference's order and uploaded once.
-        ``hoisted=True`` encodes the conditions once with the first step's FPS starts (an algorithmic optimisation that
-        changes the random draw the backbone sees, SURVEY.md 7.0 -- not the reference's per-step behaviour)."""
+    def _sample_loop_library(self, model, shape, mask, given_objs, given_cats, y, noise=None, clip_denoised=True, device=None,
+                             skip_timesteps=0, init_image=None, hoisted=False, chunk=100):
+        """The T-step ancestral loop of reference gaussian_diffusion.py:684-759 with the loop body inside ``lsdm_sample_loop``.
+        RNG is consumed as the reference does: ``th.randn(*shape)`` for x_T, then per step four CPU-generator FPS-start draws and
+        one device-generator ``randn_like``; per chunk of ``chunk`` steps they are drawn up front (the two generators are
+        independent streams, so the per-generator order is the reference's) and uploaded once.  ``skip_timesteps`` /
+        ``init_image`` follow :716-731: x_T = q_sample(init_image or zeros, t_first, noise)."""
         net = self._unwrap(model)
         if device is None:
             device = next(net.parameters()).device
+        device = th.device(device)
         B = shape[0]
+        assert isinstance(shape, (tuple, list))
         img = noise if noise is not None else th.randn(*shape, device=device)
-        self._check_x(img)
-        eng = self._engine(model, B, img.device)
-        text = net._encode_text(y)
+        caller_owns_img = noise is not None
         n_total = self.num_timesteps - skip_timesteps
+        if n_total <= 0:
+            raise ValueError("skip_timesteps leaves no timestep to run")
+        if skip_timesteps and init_image is None:
+            init_image = th.zeros_like(img)
+        eng = self._engine(model, B, device)
         with th.no_grad():
+            if init_image is not None:
+                my_t = th.ones([B], device=device, dtype=th.long) * (n_total - 1)
+                img = self.q_sample(init_image, my_t, img, model=model)  # a fresh tensor: the caller's noise is not touched
+                caller_owns_img = False
+            self._check_x(img)
+            # conditions go to the device once per loop (the reference's callers move them before the call)
+            text = eng._f32(net._encode_text(y))
+            mask_d, objs_d, cats_d = eng._f32(mask), eng._f32(given_objs), eng._f32(given_cats)
             fps0 = net.draw_fps_starts(B)
-            if noise is not None or hoisted or n_total == 1:
+            if caller_owns_img or hoisted or n_total == 1:
                 # first step through encode + denoise_step: the caller's tensor (when `noise` is given) only sees the
                 # first model call's in-place `x += pcd_out`, and the sample goes to a fresh tensor, as in the reference
                 nz0 = th.randn_like(img)
                 t0 = th.full((B,), n_total - 1, device=img.device, dtype=th.long)
-                net.encode(mask, given_objs, given_cats, text, fps0, device=img.device)
+                net.encode(mask_d, objs_d, cats_d, text, fps0, device=img.device)
                 cur, x0, gd = eng.denoise_step(img, t0, nz0, clip_denoised=clip_denoised)
                 done, fps0_used = 1, True
             else:
@@ -277,19 +300,28 @@ class GaussianDiffusion:
                 cur, done, fps0_used = img, 0, False
             while done < n_total:
                 n = min(chunk, n_total - done)
-                fps = th.stack([fps0 if (k == 0 and not fps0_used) else net.draw_fps_starts(B) for k in range(n)])
+                if hoisted:
+                    fps = fps0[None]
+                else:
+                    fps = th.stack([fps0 if (k == 0 and not fps0_used) else net.draw_fps_starts(B) for k in range(n)])
                 fps0_used = True
                 nz = th.empty(n, *img.shape, device=img.device)
                 for k in range(n):
                     nz[k] = th.randn_like(img)
-                if hoisted:
-                    fps = fps0[None]
-                x0, gd = eng.sample_loop(cur, text, given_objs, given_cats, mask, fps, nz, n_total - 1 - done, hoisted,
-                                         clip_denoised)
+                x0, gd = eng.sample_loop(cur, text, objs_d, cats_d, mask_d, fps, nz, n_total - 1 - done, hoisted, clip_denoised)
                 done += n
         net.saved_cat = eng.out_cat().unsqueeze(1)
         net.saved_guiding_points = gd
         return cur
+
+    def p_sample_loop_fused(self, model, shape, mask, given_objs, given_cats, y, noise=None, clip_denoised=True, device=None,
+                            skip_timesteps=0, init_image=None, hoisted=False, chunk=100):
+        """:meth:`p_sample_loop`'s library loop with its two extra knobs exposed: ``hoisted=True`` encodes the conditions once
+        with the first step's FPS starts (an algorithmic optimisation that changes the random draw the backbone sees,
+        SURVEY.md 7.0 -- not the reference's per-step behaviour) and ``chunk`` (steps per library call)."""
+        return self._sample_loop_library(model, shape, mask, given_objs, given_cats, y, noise=noise, clip_denoised=clip_denoised,
+                                         device=device, skip_timesteps=skip_timesteps, init_image=init_image, hoisted=hoisted,
+                                         chunk=chunk)
 
     def ddim_sample_loop(self, *args, **kwargs):
         """Referenced but never called by the reference (run/test_sdm.py:160-164); its own implementation raises

@@ -25,6 +25,18 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _on_device(fn):
+    """Engine methods launch kernels on the handle's device: make it current for the call (the C ABI launches on the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+
+    return wrapped
+
+
 class Engine:
     def __init__(self, batch_local, n_cats=13, device=None, batch_global=None, batch_offset=0):
         if not torch.cuda.is_available():
@@ -56,6 +68,7 @@ class Engine:
         self.set_option("fp_fused", int(os.environ.get("LSDM_FP_FUSED", "1")))
 
     # ------------------------------------------------------------------ lifecycle
+    @_on_device
     def _alloc_workspace(self):
         n = self.lib.lsdm_workspace_bytes(self.h)
         self._ws = torch.empty(n + 256, dtype=torch.uint8, device=self.device)
@@ -64,6 +77,7 @@ class Engine:
         _lib.check(self.lib.lsdm_set_workspace(self.h, C.c_void_p(aligned), C.c_size_t(n)))
         self.workspace_bytes = n
 
+    @_on_device
     def close(self):
         if getattr(self, "h", None):
             torch.cuda.synchronize(self.device)
@@ -88,6 +102,7 @@ class Engine:
     def expected_keys(self):
         return [self.lib.lsdm_weight_key(self.h, i).decode() for i in range(self.lib.lsdm_num_weights(self.h))]
 
+    @_on_device
     def load_state_dict(self, sd):
         """Uploads a reference ``model_state_dict`` (SURVEY.md Appendix B keys); clip_model.* is skipped."""
         st = _stream(self.device)
@@ -107,6 +122,7 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         self._keep.clear()
 
+    @_on_device
     def set_schedule(self, tables):
         """tables: dict of float64 numpy arrays (GaussianDiffusion attributes); cast to fp32 here, once."""
         names = ("posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped",
@@ -131,6 +147,7 @@ class Engine:
             t = t.to(torch.int64).contiguous()
         return t  # host or device: the C side copies with cudaMemcpyDefault
 
+    @_on_device
     def encode_conditions(self, text_emb, given_objs, given_cats, mask_global, fps_start):
         B = self.batch_local
         text_emb, given_objs, given_cats, mask_global = map(self._f32, (text_emb, given_objs, given_cats, mask_global))
@@ -146,6 +163,7 @@ class Engine:
         if not fps_start.is_cuda:
             torch.cuda.current_stream(self.device).synchronize()  # pageable host source must outlive the copy
 
+    @_on_device
     def encode_conditions_train(self, text_emb, given_objs, given_cats, mask_global, fps_start, drop_mask):
         """model.train() condition encoder: BatchNorm batch statistics (+ running-stat update inside the handle) and the Dropout mask
         ``drop_mask[9B,128,1024]`` (0 or 2) of the backbone head."""
@@ -183,12 +201,14 @@ class Engine:
         self._allreduce_cb = _lib.ALLREDUCE_FN(hook)  # keep alive
         _lib.check(self.lib.lsdm_set_allreduce(self.h, C.cast(self._allreduce_cb, C.c_void_p), None))
 
+    @_on_device
     def read_weight(self, key, like):
         """Current value of a state-dict entry inside the handle (BatchNorm running statistics after a train-mode forward)."""
         out = torch.empty(like.shape, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.lsdm_read_weight(self.h, key.encode(), _ptr(out), out.numel(), _stream(self.device)))
         return out
 
+    @_on_device
     def denoise_step(self, x, t, noise, sample_out=None, want_x0=True, want_guiding=True, clip_denoised=False):
         """x is mutated in place (x += pcd_out).  Returns (sample, x0, guiding)."""
         B = self.batch_local
@@ -204,6 +224,7 @@ class Engine:
             torch.cuda.current_stream(self.device).synchronize()
         return sample, x0, gd
 
+    @_on_device
     def forward(self, x, t):
         """x is mutated in place.  Returns (out_cat[B,C], x0, guiding)."""
         B = self.batch_local
@@ -217,6 +238,7 @@ class Engine:
             torch.cuda.current_stream(self.device).synchronize()
         return out_cat, x0, gd
 
+    @_on_device
     def sample_loop(self, x, text_emb, given_objs, given_cats, mask_global, fps_start_all, noise_all, t_first, hoisted=False,
                     clip_denoised=False):
         """Runs len(noise_all) consecutive steps t_first, t_first-1, ... in place on x.  Returns (x0, guiding) of the last."""
@@ -236,16 +258,19 @@ class Engine:
                                              _stream(self.device)))
         return x0, gd
 
+    @_on_device
     def out_cat(self):
         o = torch.empty(self.batch_local, self.n_cats, device=self.device)
         _lib.check(self.lib.lsdm_get_out_cat(self.h, _ptr(o), _stream(self.device)))
         return o
 
+    @_on_device
     def pcd_out(self):
         o = torch.empty(self.batch_local, N_POINTS, 3, device=self.device)
         _lib.check(self.lib.lsdm_get_pcd_out(self.h, _ptr(o), _stream(self.device)))
         return o
 
+    @_on_device
     def q_sample(self, x_start, t, noise):
         x_start, noise = self._f32(x_start), self._f32(noise)
         t = self._i64(t)
@@ -255,6 +280,7 @@ class Engine:
             torch.cuda.current_stream(self.device).synchronize()
         return out
 
+    @_on_device
     def chamfer(self, x, y):
         """pytorch3d.loss.chamfer_distance(x, y)[0] with default arguments (scalar tensor)."""
         x, y = self._f32(x), self._f32(y)
@@ -264,6 +290,7 @@ class Engine:
         _lib.check(self.lib.lsdm_chamfer(self.h, _ptr(x), _ptr(y), B, n, m, _ptr(sums), _stream(self.device)))
         return sums.sum() / B
 
+    @_on_device
     def cat_loss(self, probs, target_cat):
         probs, target_cat = self._f32(probs), self._f32(target_cat)
         B = probs.shape[0]
@@ -271,6 +298,7 @@ class Engine:
         _lib.check(self.lib.lsdm_cat_loss(self.h, _ptr(probs), _ptr(target_cat), B, _ptr(s), _stream(self.device)))
         return s[0] / B
 
+    @_on_device
     def debug_tensor(self, name, dtype=torch.float32):
         n = self.lib.lsdm_debug_tensor(self.h, name.encode(), None, 0, None)
         if n < 0:
@@ -289,6 +317,7 @@ class Engine:
     def profile_begin(self):
         _lib.check(self.lib.lsdm_profile_begin(self.h))
 
+    @_on_device
     def profile_end(self):
         """Returns ({class: ms}, {class: launches}, gemm_flops) measured with CUDA events inside the library."""
         n = len(self.KCLASSES)
@@ -318,6 +347,7 @@ class Engine:
     def set_option(self, name, value):
         _lib.check(self.lib.lsdm_set_option(self.h, name.encode(), int(value)))
 
+    @_on_device
     def debug_gemm(self, A, W, bias=None, act=0, group_max=False, tf32=False, bias_mode=1, precision=None):
         """One linear layer through the library's GEMM (test hook)."""
         M, K = A.shape

@@ -199,8 +199,8 @@ class SceneDiffusionModel(nn.Module):
         """Installs the CLIP ViT-B/32 text tower (openai/CLIP state-dict names under ``prefix``) on the device."""
         from .clip_text import ClipTextTower
 
-        dev = self.device if isinstance(self.device, torch.device) and self.device.type == "cuda" else None
-        tower = ClipTextTower(dev)
+        dev = torch.device(self.device)
+        tower = ClipTextTower(dev if dev.type == "cuda" else None)
         tower.load_state_dict(state_dict, prefix)
         self.clip_text = tower
         return tower
@@ -245,8 +245,15 @@ class SceneDiffusionModel(nn.Module):
         return tower.encode_text(t)
 
     def _sig(self):
-        return sum(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + 7919 * sum(
-            t.data_ptr() % 1000003 for t in self.parameters())
+        """Per-tensor (version, storage pointer) of every parameter / buffer.  In-place updates through ``.data`` (EMA,
+        ``p.data.copy_``) do not bump a tensor's version: call :meth:`invalidate_weights` after those."""
+        return tuple((int(t._version), t.data_ptr()) for t in list(self.parameters()) + list(self.buffers()))
+
+    def invalidate_weights(self):
+        """Forces the next call to re-upload this module's weights into the device handle."""
+        self._weights_sig = None
+
+    sync_weights = invalidate_weights
 
     def engine(self, batch_local, device):
         """The ``lsdm_handle`` owner for this batch size / shard; (re)uploads weights when they changed."""

@@ -114,7 +114,7 @@ def diffusion_tables(betas: np.ndarray) -> dict:
 
 def _extract(arr: np.ndarray, t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
     """diffusion/gaussian_diffusion.py:1585-1598: gather in float64, THEN cast to fp32."""
-    v = torch.from_numpy(arr)[t].float().to(like.dtype)
+    v = torch.from_numpy(arr).to(t.device)[t].float().to(like.dtype)
     return v.view(-1, *([1] * (like.dim() - 1)))
 
 

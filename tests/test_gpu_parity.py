@@ -141,9 +141,19 @@ def test_p_sample_config1_vs_golden(kind, mode):
     assert rel_l2(m.saved_guiding_points.cpu(), g["guiding"]) < TOL_E2E
 
 
-@pytest.mark.parametrize("fused", [False, True])
+def _stepwise_loop(diff, *a, **k):
+    """The per-step generator of the reference (p_sample_loop_progressive), last sample -- p_sample_loop itself runs in the library."""
+    final = None
+    for out in diff.p_sample_loop_progressive(*a, **k):
+        final = out
+    return final["sample"]
+
+
+@pytest.mark.parametrize("fused", ["stepwise", "p_sample_loop", "fused_chunk3"])
 def test_respaced_loop_vs_golden(fused, mode):
-    """8-step respaced ancestral loop (SpacedDiffusion), reference-shaped API and the fused C loop."""
+    """8-step respaced ancestral loop (SpacedDiffusion): the per-step generator, the reference's own entry point p_sample_loop
+    (library loop) and the library loop in chunks of 3."""
+    import functools
     from lsdm_b200.diffusion import gaussian_diffusion as gd
     from lsdm_b200.diffusion.respace import SpacedDiffusion, space_timesteps
 
@@ -157,7 +167,8 @@ def test_respaced_loop_vs_golden(fused, mode):
     inp = _cuda(syn.make_inputs(5, 2))
     fps, noise = syn.make_step_randoms(6, 2, T)
     x_T = inp["x_T"].clone()
-    fn = diff.p_sample_loop_fused if fused else diff.p_sample_loop
+    fn = {"stepwise": functools.partial(_stepwise_loop, diff), "p_sample_loop": diff.p_sample_loop,
+          "fused_chunk3": functools.partial(diff.p_sample_loop_fused, chunk=3)}[fused]
     with injected_rng(fps_starts=[v for s in fps for v in s], noises=list(noise)):
         sample = fn(m, (2, 1024, 3), inp["mask"], inp["given_objs"], inp["given_cats"], inp["text_emb"], noise=x_T, clip_denoised=False)
     assert rel_l2(sample.cpu(), g["sample"]) < TOL_E2E
@@ -428,7 +439,8 @@ def test_fused_loop_without_caller_noise_matches_stepwise_loop():
                            model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
     inp = _cuda(syn.make_inputs(8, 3))
     outs = []
-    for fn, kw in ((diff.p_sample_loop, {}), (diff.p_sample_loop_fused, {"chunk": 4}), (diff.p_sample_loop_fused, {"chunk": 50})):
+    import functools
+    for fn, kw in ((functools.partial(_stepwise_loop, diff), {}), (diff.p_sample_loop, {}), (diff.p_sample_loop_fused, {"chunk": 4})):
         torch.manual_seed(123)
         torch.cuda.manual_seed(123)
         s = fn(m, (3, 1024, 3), inp["mask"], inp["given_objs"], inp["given_cats"], inp["text_emb"], clip_denoised=False, **kw)
@@ -436,6 +448,39 @@ def test_fused_loop_without_caller_noise_matches_stepwise_loop():
     for o in outs[1:]:
         for a, b in zip(o, outs[0]):
             assert rel_l2(a.cpu(), b.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("with_init", [False, True])
+def test_library_loop_skip_timesteps_and_init_image_match_stepwise(with_init):
+    """skip_timesteps > 0 (and init_image): the library loop starts from q_sample(init_image or zeros, t_first, noise) exactly as
+    reference gaussian_diffusion.py:716-731 and the per-step generator do; the caller's `noise` tensor is left untouched in
+    that case (q_sample returns a fresh tensor)."""
+    import functools
+
+    from lsdm_b200.diffusion import gaussian_diffusion as gd
+    from lsdm_b200.diffusion.respace import SpacedDiffusion, space_timesteps
+
+    m, _ = _model("wellcond")
+    diff = SpacedDiffusion(use_timesteps=space_timesteps(1000, "10"), betas=gd.get_named_beta_schedule("cosine", 1000),
+                           model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
+    B = 2
+    inp = _cuda(syn.make_inputs(18, B))
+    init = (0.3 * inp["x_T"].flip(0)).contiguous() if with_init else None
+    outs = []
+    for fn in (functools.partial(_stepwise_loop, diff), diff.p_sample_loop):
+        for give_noise in (False, True):
+            torch.manual_seed(321)
+            torch.cuda.manual_seed(321)
+            nz = inp["x_T"].clone() if give_noise else None
+            s = fn(m, (B, 1024, 3), inp["mask"], inp["given_objs"], inp["given_cats"], inp["text_emb"], noise=nz, clip_denoised=False,
+                   skip_timesteps=6, init_image=init)
+            if give_noise:
+                assert torch.equal(nz, inp["x_T"])
+            outs.append((give_noise, s.clone(), m.saved_guiding_points.clone()))
+    for give_noise, s, gdp in outs[2:]:
+        ref = [o for o in outs[:2] if o[0] == give_noise][0]
+        assert rel_l2(s.cpu(), ref[1].cpu()) < 1e-6
+        assert rel_l2(gdp.cpu(), ref[2].cpu()) < 1e-6
 
 
 def test_uniform_cloud_shortcuts_are_exact():
