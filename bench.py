@@ -298,6 +298,8 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     value = Bg * K / (ms * 1e-3)
+    if rank == 0:
+        print(f"[bench] device-timed: {value:.1f} {UNIT}, {ms / K:.3f} ms/step, {launches} launches", file=sys.stderr, flush=True)
 
     # ---- per-kernel-class shares + roofline numerator: separate profiled pass (CUDA events around every launch) ----
     xp = g["x_T"].clone()
@@ -391,6 +393,8 @@ def run_ours(args):
                        "reference run/test_sdm.py:166-182 -- over the same K timesteps; conditions (pinned host) uploaded once per call, FPS "
                        "starts drawn on the CPU generator and uploaded per chunk, noise drawn on the device generator (as the reference "
                        "does), final samples read back; best of 3 calls")
+        if rank == 0:
+            print(f"[bench] e2e via p_sample_loop: {e2e['value']:.1f} {UNIT} ({e2e['value'] / value:.3f} of device-timed)", file=sys.stderr, flush=True)
     elif not args.no_e2e:
         torch.manual_seed(7)
         runs = []
@@ -535,17 +539,31 @@ def run_ours(args):
             del fl, nl, xx, gd_
             return leg
 
+        def log(msg):
+            if rank == 0:
+                print("[bench] " + msg, file=sys.stderr, flush=True)
+
+        def guard(name, fn):
+            """A failing extra leg is reported in the JSON line instead of taking the benchmark down."""
+            try:
+                fn()
+                log(f"{name}: " + json.dumps(extra.get(name), default=str)[:600])
+            except Exception as e:
+                import traceback
+                traceback.print_exc()
+                extra[name] = {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
+
         # ---- BASELINE config 3: 100-step respaced ('ddim100') ancestral loop, B=256, one GPU: the WHOLE loop is timed ----
-        if world == 1:
+        def leg_config3():
             diff3 = create_gaussian_diffusion(get_default_diffusion(), timestep_respacing="ddim100")
             leg = loop_leg(diff3, 256, 256, diff3.num_timesteps - 3, 3, 5150, gather=False)
             leg["workload"] = ("BASELINE configs[2]: SpacedDiffusion(space_timesteps(1000,'ddim100')), ancestral p_sample_loop (the only respaced sampler "
                                "alive in the reference), batch 256, 1 GPU; device leg = steps 96..0 after 3 warm-up steps, e2e = the full 100-step call")
             if not args.no_e2e:
+                _, h3, _ = shard_inputs(5150, 256, 256)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 with torch.no_grad():
-                    _, h3, _ = shard_inputs(5150, 256, 256)
                     ref_call(diff3, 256, h3, 0).cpu()
                 torch.cuda.synchronize()
                 dt3 = time.perf_counter() - t0
@@ -553,127 +571,150 @@ def run_ours(args):
                 leg["full_loop_sample_steps_per_s"] = 256 * 100 / dt3
             extra["config3_respaced100_b256"] = leg
 
+        if world == 1:
+            guard("config3_respaced100_b256", leg_config3)
+
         # ---- BASELINE config 4: training_losses forward, 64 samples per GPU, eval-BN and train-BN (+SyncBN over ranks) ----
-        B4, K4, W4 = 64, 5, 2
-        if world > 1:
-            model.set_shard(B4 * world, rank * B4, sync_bn_group=True)
-        else:
-            model.set_shard(None)
-        _, host4, g4 = shard_inputs(7700, B4, B4 * world, training=True)
-        cfg4 = {}
-        for mode_name in ("eval_bn", "train_bn"):
-            model.train(mode_name == "train_bn")
-
-            def one(src, read_back):
-                terms = diff.training_losses(model, src["x_start"], src["mask"], src["t"], src["given_objs"], src["given_cats"], src["target_cat"],
-                                             y=src["text_emb"])
-                vec = torch.stack([terms["loss"].detach(), terms["mse"].detach(), terms["cat_loss"].detach()])
-                if world > 1:
-                    dist.all_reduce(vec)   # the path's one exchange step: three scalars
-                    vec = vec / world
-                return vec.cpu() if read_back else vec
-
-            torch.manual_seed(11)
-            with torch.no_grad():
-                for _ in range(W4):
-                    one(g4, False)
-                t_ms = dev_timed(lambda: [one(g4, False) for _ in range(K4)])
-                runs4 = []
-                last = None
-                for _ in range(K4 + 1):
-                    torch.cuda.synchronize()
-                    if world > 1:
-                        dist.barrier()
-                    t0 = time.perf_counter()
-                    last = one(host4, True)   # host inputs in, three scalars read back
-                    runs4.append(time.perf_counter() - t0)
-            dt4 = sum(runs4[1:]) / K4
+        def leg_config4():
+            B4, K4, W4 = 64, 5, 2
             if world > 1:
-                tt = torch.tensor([dt4], device=dev, dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt4 = float(tt.item())
-            h2d4 = sum(host4[k].numel() * host4[k].element_size() for k in ("x_start", "mask", "t", "given_objs", "given_cats", "target_cat", "text_emb"))
-            cfg4[mode_name] = {"value": B4 * world * K4 / (t_ms * 1e-3), "unit": "samples/s", "ms_per_forward": t_ms / K4, "steps": K4, "warmup": W4,
-                               "loss": float(last[0]), "mse": float(last[1]), "cat_loss": float(last[2]),
-                               "e2e": {"value": B4 * world / dt4, "unit": "samples/s", "h2d_bytes_per_step": int(h2d4), "d2h_bytes_per_step": 12}}
-        model.eval()
-        model.load_state_dict(sd0)   # train-mode forwards moved the BatchNorm running statistics
-        cfg4["workload"] = (f"BASELINE configs[3]: diffusion.training_losses forward (q_sample + SDM forward + chamfer + category CE), {B4} samples per GPU, "
-                            f"global batch {B4 * world}; eval_bn = model.eval() (folded BatchNorm), train_bn = model.train() (batch statistics over all "
-                            "9B clouds, running-stat updates, Dropout; SyncBN all-reduce of the statistics when N > 1); one all-reduce of the three loss scalars")
-        extra["config4_training_forward_b64_per_gpu"] = cfg4
+                model.set_shard(B4 * world, rank * B4, sync_bn_group=True)
+            else:
+                model.set_shard(None)
+            _, host4, g4 = shard_inputs(7700, B4, B4 * world, training=True)
+            cfg4 = {}
+            for mode_name in ("eval_bn", "train_bn"):
+                model.train(mode_name == "train_bn")
+
+                def one(src, read_back):
+                    terms = diff.training_losses(model, src["x_start"], src["mask"], src["t"], src["given_objs"], src["given_cats"], src["target_cat"],
+                                                 y=src["text_emb"])
+                    vec = torch.stack([terms["loss"].detach(), terms["mse"].detach(), terms["cat_loss"].detach()])
+                    if world > 1:
+                        dist.all_reduce(vec)   # the path's one exchange step: three scalars
+                        vec = vec / world
+                    return vec.cpu() if read_back else vec
+
+                torch.manual_seed(11)
+                with torch.no_grad():
+                    for _ in range(W4):
+                        one(g4, False)
+                    t_ms = dev_timed(lambda: [one(g4, False) for _ in range(K4)])
+                    runs4 = []
+                    last = None
+                    for _ in range(K4 + 1):
+                        torch.cuda.synchronize()
+                        if world > 1:
+                            dist.barrier()
+                        t0 = time.perf_counter()
+                        last = one(host4, True)   # host inputs in, three scalars read back
+                        runs4.append(time.perf_counter() - t0)
+                dt4 = sum(runs4[1:]) / K4
+                if world > 1:
+                    tt = torch.tensor([dt4], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    dt4 = float(tt.item())
+                h2d4 = sum(host4[k].numel() * host4[k].element_size() for k in ("x_start", "mask", "t", "given_objs", "given_cats", "target_cat", "text_emb"))
+                cfg4[mode_name] = {"value": B4 * world * K4 / (t_ms * 1e-3), "unit": "samples/s", "ms_per_forward": t_ms / K4, "steps": K4, "warmup": W4,
+                                   "loss": float(last[0]), "mse": float(last[1]), "cat_loss": float(last[2]),
+                                   "e2e": {"value": B4 * world / dt4, "unit": "samples/s", "h2d_bytes_per_step": int(h2d4), "d2h_bytes_per_step": 12}}
+            model.eval()
+            model.load_state_dict(sd0)   # train-mode forwards moved the BatchNorm running statistics
+            cfg4["workload"] = (f"BASELINE configs[3]: diffusion.training_losses forward (q_sample + SDM forward + chamfer + category CE), {B4} samples per GPU, "
+                                f"global batch {B4 * world}; eval_bn = model.eval() (folded BatchNorm), train_bn = model.train() (batch statistics over all "
+                                "9B clouds, running-stat updates, Dropout; SyncBN all-reduce of the statistics when N > 1); one all-reduce of the three loss scalars")
+            extra["config4_training_forward_b64_per_gpu"] = cfg4
+
+        guard("config4_training_forward_b64_per_gpu", leg_config4)
 
         # ---- BASELINE config 5: 1000-step sampling at batch 1024 over 8 GPUs: 128 per GPU (weak) and 1024 in total (strong) ----
         K5 = min(K, 10)
-        leg = loop_leg(diff, 128, 128 * world, K5, 3, 5500)
-        leg["workload"] = "BASELINE configs[4], weak scaling: 128 samples per GPU (1024 at N=8), first K timesteps of the 1000-step loop + one all-gather"
-        extra["config5_weak_b128_per_gpu"] = leg
-        per_rank = 1024 // world
-        mb = min(per_rank, 256)
-        n_mb = per_rank // mb
-        gi5 = syn.make_inputs(5600, 1024)
-        fa5, na5 = syn.make_step_randoms(5601, 1024, 2 + K5)
-        sets = []
-        for j in range(n_mb):
-            lo = rank * per_rank + j * mb
-            sets.append({"lo": lo, "g": {k: (v if k == "mask" else v[lo:lo + mb].contiguous()).to(dev) for k, v in gi5.items()},
-                         "fps": fa5.view(2 + K5, 4, 1024, 9)[:, :, lo:lo + mb].reshape(2 + K5, 4, mb * 9).contiguous().to(dev),
-                         "nz": na5[:, lo:lo + mb].contiguous().to(dev)})
-        xs = torch.cat([s_["g"]["x_T"] for s_ in sets]).clone()
-        gb5 = torch.empty(world, per_rank, 1024, 3, device=dev) if world > 1 else None
 
-        def strong(first, n):
-            for j, s_ in enumerate(sets):
-                model.set_shard(1024, s_["lo"])
-                en = diff._engine(model, mb, dev)
-                gg = s_["g"]
-                en.sample_loop(xs[j * mb:(j + 1) * mb], gg["text_emb"], gg["given_objs"], gg["given_cats"], gg["mask"], s_["fps"][first:first + n],
-                               s_["nz"][first:first + n], T - 1 - first, False)
-            if gb5 is not None and first > 0:
-                dist.all_gather_into_tensor(gb5.view(-1), xs.view(-1))
+        def leg_config5_weak():
+            leg = loop_leg(diff, 128, 128 * world, K5, 3, 5500)
+            leg["workload"] = "BASELINE configs[4], weak scaling: 128 samples per GPU (1024 at N=8), first K timesteps of the 1000-step loop + one all-gather"
+            extra["config5_weak_b128_per_gpu"] = leg
 
-        strong(0, 2)
-        t_ms = dev_timed(lambda: strong(2, K5))
-        extra["config5_strong_b1024_total"] = {
-            "value": 1024 * K5 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / K5, "steps": K5, "warmup": 2, "global_batch": 1024,
-            "per_gpu_batch": per_rank, "micro_batch": mb, "finite": bool(torch.isfinite(xs).all().item()),
-            "workload": f"BASELINE configs[4], strong scaling: 1024 samples in total, {per_rank} per GPU processed as {n_mb} shard(s) of {mb} with the "
-                        "global mask / offsets (bit-identical to one 1024-sample batch), first K timesteps + one all-gather"}
-        del sets, xs, gi5, fa5, na5
+        def leg_config5_strong():
+            per_rank = 1024 // world
+            mb = min(per_rank, 256)
+            n_mb = per_rank // mb
+            gi5 = syn.make_inputs(5600, 1024)
+            fa5, na5 = syn.make_step_randoms(5601, 1024, 2 + K5)
+            sets = []
+            for j in range(n_mb):
+                lo = rank * per_rank + j * mb
+                sets.append({"lo": lo, "g": {k: (v if k == "mask" else v[lo:lo + mb].contiguous()).to(dev) for k, v in gi5.items()},
+                             "fps": fa5.view(2 + K5, 4, 1024, 9)[:, :, lo:lo + mb].reshape(2 + K5, 4, mb * 9).contiguous().to(dev),
+                             "nz": na5[:, lo:lo + mb].contiguous().to(dev)})
+            xs = torch.cat([s_["g"]["x_T"] for s_ in sets]).clone()
+            gb5 = torch.empty(world, per_rank, 1024, 3, device=dev) if world > 1 else None
 
-        if world == 1:
-            # ---- the named workload run in full: 1000 steps x 64 samples through the reference's call (anchors the K-step rate) ----
+            def strong(first, n):
+                for j, s_ in enumerate(sets):
+                    model.set_shard(1024, s_["lo"])
+                    en = diff._engine(model, mb, dev)
+                    gg = s_["g"]
+                    en.sample_loop(xs[j * mb:(j + 1) * mb], gg["text_emb"], gg["given_objs"], gg["given_cats"], gg["mask"], s_["fps"][first:first + n],
+                                   s_["nz"][first:first + n], T - 1 - first, False)
+                if gb5 is not None and first > 0:
+                    dist.all_gather_into_tensor(gb5.view(-1), xs.view(-1))
+
+            strong(0, 2)
+            t_ms = dev_timed(lambda: strong(2, K5))
+            extra["config5_strong_b1024_total"] = {
+                "value": 1024 * K5 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / K5, "steps": K5, "warmup": 2, "global_batch": 1024,
+                "per_gpu_batch": per_rank, "micro_batch": mb, "finite": bool(torch.isfinite(xs).all().item()),
+                "workload": f"BASELINE configs[4], strong scaling: 1024 samples in total, {per_rank} per GPU processed as {n_mb} shard(s) of {mb} with the "
+                            "global mask / offsets (bit-identical to one 1024-sample batch), first K timesteps + one all-gather"}
+            del sets, xs, gi5, fa5, na5
+
+        guard("config5_weak_b128_per_gpu", leg_config5_weak)
+        guard("config5_strong_b1024_total", leg_config5_strong)
+
+        # ---- the named workload run in full: 1000 steps x 64 samples through the reference's call (anchors the K-step rate) ----
+        def leg_full_loop():
             model.set_shard(Bg, off)
-            if not args.no_e2e:
-                torch.manual_seed(7)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                with torch.no_grad():
-                    full = ref_call(diff, B, host, 0).cpu()
-                torch.cuda.synchronize()
-                dtf = time.perf_counter() - t0
-                extra["full_loop_1000_steps_b64"] = {"wall_s": dtf, "value": B * T / dtf, "unit": UNIT, "finite": bool(torch.isfinite(full).all().item()),
-                                                    "note": "diffusion.p_sample_loop(...) exactly as run/test_sdm.py:166-182 calls it (skip_timesteps=0): "
-                                                            "64 000 sample-steps, host condition buffers in, samples read back, wall clock"}
-            # ---- the other builds of the dense layers beside the `tf32` headline ----
-            eng = diff._engine(model, B, dev)
+            torch.manual_seed(7)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                full = ref_call(diff, B, host, 0).cpu()
+            torch.cuda.synchronize()
+            dtf = time.perf_counter() - t0
+            extra["full_loop_1000_steps_b64"] = {"wall_s": dtf, "value": B * T / dtf, "unit": UNIT, "finite": bool(torch.isfinite(full).all().item()),
+                                                "note": "diffusion.p_sample_loop(...) exactly as run/test_sdm.py:166-182 calls it (skip_timesteps=0): "
+                                                        "64 000 sample-steps, host condition buffers in, samples read back, wall clock"}
+
+        # ---- the other builds of the dense layers beside the `tf32` headline ----
+        def leg_precisions():
+            model.set_shard(Bg, off)
+            en = diff._engine(model, B, dev)
             variants = {}
-            for pname, kp in (("fp32", 4), ("3xtf32", 8), ("tf32-all", 8)):
-                try:
-                    eng.set_precision(pname)
-                    xv = g["x_T"].clone()
-                    run_steps(0, 2, xv)
-                    t_ms = dev_timed(lambda: run_steps(2, kp, xv))
-                    variants[pname] = {"value": B * kp / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / kp, "steps": kp}
-                except Exception as e:
-                    variants[pname] = {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
-            eng.set_precision("tf32")
+            try:
+                for pname, kp in (("fp32", 4), ("3xtf32", 8), ("tf32-all", 8)):
+                    try:
+                        en.set_precision(pname)
+                        xv = g["x_T"].clone()
+                        run_steps(0, 2, xv)
+                        t_ms = dev_timed(lambda: run_steps(2, kp, xv))
+                        variants[pname] = {"value": B * kp / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / kp, "steps": kp}
+                    except Exception as e:
+                        variants[pname] = {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
+            finally:
+                en.set_precision("tf32")
             variants["note"] = ("same K-step leg with every dense layer in fp32 on the CUDA cores ('fp32'), split-TF32 everywhere ('3xtf32', fp32-grade) "
                                 "and single-pass TF32 everywhere ('tf32-all'); the headline build is 'tf32' (TF32 encoder, 3xTF32 x0 network)")
             extra["precision_variants"] = variants
+
+        if world == 1:
+            if not args.no_e2e:
+                guard("full_loop_1000_steps_b64", leg_full_loop)
+            guard("precision_variants", leg_precisions)
             # ---- second baseline: the same port run eagerly by PyTorch on this GPU ----
             if not args.no_cpu_baseline:
                 extra["gpu_eager_baseline"] = gpu_eager_rate(3, 1)
+                log("gpu_eager_baseline: " + json.dumps(extra["gpu_eager_baseline"])[:400])
         model.set_shard(Bg, off)
 
     clk = clocks.stop(t_load0, time.perf_counter()) if rank == 0 else None

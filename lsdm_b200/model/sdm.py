@@ -259,6 +259,13 @@ class SceneDiffusionModel(nn.Module):
         """The ``lsdm_handle`` owner for this batch size / shard; (re)uploads weights when they changed."""
         from ..engine import Engine
 
+        device = torch.device(device)
+        if device.type != "cuda":  # host tensors in: the handle lives where the parameters live
+            device = next(self.parameters()).device
+            if device.type != "cuda":
+                device = torch.device(self.device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         bg, off = self._shard if self._shard is not None else (batch_local, 0)
         sig = (int(batch_local), bg, off, str(device))
         if self._engine is None or self._engine_sig[3] != sig[3]:
