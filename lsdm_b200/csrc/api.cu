@@ -1,6 +1,7 @@
 // C ABI of lsdm_b200 (include/lsdm_b200.h): handle, weight registry, workspace carving and the
 // orchestration of the kernels for encode_conditions / denoise_step / forward / sample_loop.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -79,6 +80,9 @@ struct Workspace {
   } sel[2];
   int cur;  // set used by the last encode (debug taps)
   float* feat[5];
+  // absent-cloud de-duplication (lsdm_sample_loop): compacted clouds, cloud -> compact position, compact -> cloud
+  float* clouds_c;
+  int *remap, *active, *n_active;
   float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out[2];  // pcd_out: one per selection set (the step of k reads it while dense(k+1) writes the other)
   // step
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
@@ -110,6 +114,9 @@ struct lsdm_handle {
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
   int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
   int fp_fused = 0;              // 1: fused fp2 level (fine GEMM + interpolation + second conv in one kernel)
+  int dedup_absent = 1;          // 1: lsdm_sample_loop encodes ONE all-zero (absent, zero-padded) cloud per step and shares its
+                                 //    backbone output with every other absent cloud (bit-identical: eval-mode clouds are independent)
+  int n_active = 0;              // clouds the encoder runs on in the current lsdm_sample_loop call
   std::vector<float> host_wx[2], host_wf[2], host_b1[2], host_b2[2];  // host copies for the v2 fused SA kernels (kernel params)
   // schedule
   float* sched = nullptr;  // 5 x T
@@ -267,6 +274,10 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
       s.nn_w[l] = a.take<float>(C * fn[l] * 3);
     }
   }
+  w->clouds_c = a.take<float>(C * NPTS * 3);
+  w->remap = a.take<int>(C);
+  w->active = a.take<int>(C);
+  w->n_active = a.take<int>(4);
   w->tA = a.take<float>(C * 2097152);  // 2M floats/cloud: the train-mode path materialises sa1's [32768,64] pre-pool layer
   w->bn_stats = a.take<double>(2 * 1024);
   w->tB = a.take<float>(C * 1048576);
@@ -379,12 +390,21 @@ int check_ready(lsdm_handle* h, bool need_cond) {
 
 // FPS (4 levels), ball queries (4 levels), 3-NN weights (4 levels): everything that depends only on coordinates.
 // Also the small per-sample condition MLPs and the POSA human decoder, which are equally independent of x / t.
-int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const float* clouds, const float* cats,
-                 const float* mask_global, const int64_t* fps_start, cudaStream_t st) {
-  const int B = h->cfg.batch_local, C = B * NOBJ;
+__global__ void gather_fps_start_kernel(const int64_t* __restrict__ src, const int* __restrict__ active, int n_src, int n_dst,
+                                        int64_t* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * n_dst) dst[i] = src[(int64_t)(i / n_dst) * n_src + active[i % n_dst]];
+}
+
+// `objs` are the caller's [B,9,1024,3] clouds (human decoder input); `clouds` / `C` are what the PointNet++ selection chain
+// runs on: the same tensor, or the de-duplicated copy (Workspace::clouds_c, `active` = compact -> original cloud index).
+int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const float* objs, const float* cats,
+                 const float* mask_global, const int64_t* fps_start, cudaStream_t st, const float* clouds = nullptr, int C = -1,
+                 const int* active = nullptr) {
+  const int B = h->cfg.batch_local;
+  if (!clouds) clouds = objs, C = B * NOBJ;
   Workspace& w = h->ws;
   {
-    const float* objs = clouds;
     CondWeights cw{h->W("embed_text.0.weight"), h->W("embed_text.0.bias"), h->W("embed_text.2.weight"), h->W("embed_text.2.bias"),
                    h->W("embed_text.4.weight"), h->W("embed_text.4.bias"), h->W("predict_cat.0.weight"), h->W("predict_cat.0.bias"),
                    h->W("predict_cat.2.weight"), h->W("predict_cat.2.bias"), h->W("predict_cat.4.weight"), h->W("predict_cat.4.bias"),
@@ -404,7 +424,11 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
     hw.w3 = h->W("human_backbone.de_spiral.3.layer.weight"); hw.b3 = h->W("human_backbone.de_spiral.3.layer.bias");
     prof_launch(h, st, K_COND, [&] { return launch_human(hw, objs, B, w.human_scratch, q.hm, st); });
   }
-  if (fps_start != q.fps_start) CK(cudaMemcpyAsync(q.fps_start, fps_start, sizeof(int64_t) * 4 * C, cudaMemcpyDefault, st));
+  if (active) {
+    gather_fps_start_kernel<<<(4 * C + 255) / 256, 256, 0, st>>>(fps_start, active, B * NOBJ, C, q.fps_start);
+  } else if (fps_start != q.fps_start) {
+    CK(cudaMemcpyAsync(q.fps_start, fps_start, sizeof(int64_t) * 4 * C, cudaMemcpyDefault, st));
+  }
   prof_launch(h, st, K_FPS, [&] { return launch_fps4(clouds, q.fps_start, C, q.idx[0], q.idx[1], q.idx[2], q.idx[3], q.xyz[1], q.xyz[2],
                                                      q.xyz[3], q.xyz[4], st); });
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
@@ -419,9 +443,8 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
 }
 
 // Dense layers of PointNet++ given the selection results.
-int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cudaStream_t st) {
+int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cudaStream_t st, int C) {
   Workspace& w = h->ws;
-  const int C = h->cfg.batch_local * NOBJ;
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   const float* feat[5] = {clouds, w.feat[1], w.feat[2], w.feat[3], w.feat[4]};
   for (int l = 0; l < 4; ++l) {
@@ -603,6 +626,46 @@ __global__ void add_planes_kernel(const float* __restrict__ hi, const float* __r
   if (i < n) dst[i] = hi[i] + lo[i];
 }
 
+// Absent objects are zero-padded by the dataset (reference posa/dataset.py:456): a cloud whose 3072 floats are all +0.0f.
+// In eval mode every cloud goes through PointNet++ independently and the output for such a cloud does not depend on its
+// FPS start draws (every point, hence every gathered row, is the same), so all absent clouds of a batch share ONE result.
+__global__ void classify_clouds_kernel(const float* __restrict__ clouds, int* __restrict__ absent) {
+  const uint4* p = reinterpret_cast<const uint4*>(clouds + (int64_t)blockIdx.x * NPTS * 3);
+  unsigned acc = 0;
+  for (int i = threadIdx.x; i < NPTS * 3 / 4; i += blockDim.x) {
+    const uint4 v = p[i];
+    acc |= v.x | v.y | v.z | v.w;
+  }
+  const int any = __syncthreads_or(acc != 0);
+  if (threadIdx.x == 0) absent[blockIdx.x] = any ? 0 : 1;
+}
+// active = [every present cloud in order, then the first absent cloud]; remap[c] = position of c's result in that list.
+// `remap` holds the absent flags on entry.  One thread: C <= 9216, once per lsdm_sample_loop call.
+__global__ void compact_clouds_kernel(int* __restrict__ remap, int* __restrict__ active, int* __restrict__ n_active, int C) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int n = 0, first_absent = -1;
+  for (int c = 0; c < C; ++c) {
+    if (remap[c]) {
+      if (first_absent < 0) first_absent = c;
+    } else {
+      active[n++] = c;
+    }
+  }
+  const int rep = n;
+  if (first_absent >= 0) active[n++] = first_absent;
+  int k = 0;
+  for (int c = 0; c < C; ++c) {
+    if (remap[c]) remap[c] = rep;
+    else remap[c] = k++;
+  }
+  *n_active = n;
+}
+__global__ void gather_clouds_kernel(const float* __restrict__ clouds, const int* __restrict__ active, float* __restrict__ out) {
+  const float4* src = reinterpret_cast<const float4*>(clouds + (int64_t)active[blockIdx.x] * NPTS * 3);
+  float4* dst = reinterpret_cast<float4*>(out + (int64_t)blockIdx.x * NPTS * 3);
+  for (int i = threadIdx.x; i < NPTS * 3 / 4; i += blockDim.x) dst[i] = src[i];
+}
+
 __global__ void fill_t_kernel(int64_t* t, int n, int64_t v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) t[i] = v;
@@ -642,8 +705,14 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
     return fail(LSDM_ENOMEM, std::string("cudaMalloc weights: ") + cudaGetErrorString(e));
   }
   h->derived = h->arena + h->arena_floats;
-  cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&h->dense_st, cudaStreamNonBlocking);
+  // The selection chain (side stream) is a long dependent chain of small kernels (1360 FPS rounds per cloud): it gets the
+  // greatest stream priority so that its CTAs are scheduled ahead of the persistent dense kernels' (LSDM_SIDE_PRIO=0: off).
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const char* pe = getenv("LSDM_SIDE_PRIO");
+  const int pmode = pe ? atoi(pe) : 1;
+  cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, pmode >= 1 ? prio_hi : prio_lo);
+  cudaStreamCreateWithPriority(&h->dense_st, cudaStreamNonBlocking, pmode >= 2 ? prio_hi : prio_lo);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&h->ev_sel[i], cudaEventDisableTiming);
@@ -927,19 +996,21 @@ int dense_phase_train(lsdm_handle* h, const Workspace::Sel& q, const float* clou
 
 // Everything of the condition encoder except the selection chain (which the caller has already enqueued for set `si`).
 static int encode_dense(lsdm_handle* h, const float* text, const float* objs, const float* cats, const float* mask_global, int si,
-                        cudaStream_t st, const float* train_drop_mask = nullptr) {
+                        cudaStream_t st, const float* train_drop_mask = nullptr, const float* clouds = nullptr, int n_clouds = -1,
+                        const int* remap = nullptr) {
   Workspace& w = h->ws;
   const int B = h->cfg.batch_local;
+  if (!clouds) clouds = objs, n_clouds = B * NOBJ;
   if (train_drop_mask) {
     GE(dense_phase_train(h, w.sel[si], objs, train_drop_mask, st));
   } else {
     if (h->fold_dirty) GE(lsdm_finalize_weights(h, st));  // running statistics moved since the last fold
-    GE(dense_phase(h, w.sel[si], objs, st));
+    GE(dense_phase(h, w.sel[si], clouds, st, n_clouds));
   }
   SceneWeights sw{h->W("pcd_attention.k_proj_weight"), h->W("pcd_attention.v_proj_weight"), h->W("pcd_attention.in_proj_bias"),
                   h->W("pcd_attention.out_proj.weight"), h->W("pcd_attention.out_proj.bias"),
                   h->W("point_wise_trans_layer.0.weight"), h->W("point_wise_trans_layer.0.bias")};
-  prof_launch(h, st, K_SCENE, [&] { return launch_point_attention(sw, w.backbone, w.sel[si].attn_w, w.sel[si].qq, B, w.pa, w.pw, st); });
+  prof_launch(h, st, K_SCENE, [&] { return launch_point_attention(sw, w.backbone, w.sel[si].attn_w, w.sel[si].qq, B, w.pa, w.pw, st, remap); });
   prof_launch(h, st, K_SCENE, [&] { return launch_scene_mix(w.pw, w.sel[si].hm, mask_global, B, h->cfg.batch_global, h->cfg.batch_offset, w.pcd_out[si], st); });
   CK(cudaPeekAtLastError());
   w.cur = si;
@@ -1018,6 +1089,31 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
   //   dense stream : PointNet++ dense layers + scene branch of step k               -> pcd_out[k&1]
   //   caller stream: x0 network + posterior of step k-... (the only part that is serial in x)
   // Two buffer sets; events order producer -> consumer and consumer -> reuse.
+  // absent-cloud de-duplication: classify once per call (the clouds are constant over the loop), run the encoder on the
+  // compacted list, read the shared result through `remap` in the scene branch
+  const float* clouds = nullptr;
+  const int *remap = nullptr, *active = nullptr;
+  int nc = -1;
+  if (h->dedup_absent) {
+    Workspace& w = h->ws;
+    classify_clouds_kernel<<<C, 256, 0, st>>>(objs, w.remap);
+    compact_clouds_kernel<<<1, 32, 0, st>>>(w.remap, w.active, w.n_active, C);
+    int n_act = 0;
+    CK(cudaMemcpyAsync(&n_act, w.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));  // once per call: grid sizes of the encoder depend on the count
+    h->launches += 2;
+    if (n_act < C) {
+      gather_clouds_kernel<<<n_act, 256, 0, st>>>(objs, w.active, w.clouds_c);
+      h->launches += 1;
+      clouds = w.clouds_c;
+      remap = w.remap;
+      active = w.active;
+      nc = n_act;
+    }
+    h->n_active = n_act;
+  } else {
+    h->n_active = C;
+  }
   const bool pipelined = !hoisted && n_steps > 1 && !h->profiling;
   cudaStream_t side = pipelined ? h->side : st;
   cudaStream_t dst = pipelined ? h->dense_st : st;
@@ -1026,7 +1122,7 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     CK(cudaStreamWaitEvent(side, h->ev_fork, 0));
     CK(cudaStreamWaitEvent(dst, h->ev_fork, 0));
   }
-  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side));
+  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side, clouds, nc, active));
   if (pipelined) CK(cudaEventRecord(h->ev_sel[0], side));
   for (int k = 0; k < n_steps; ++k) {
     const int si = hoisted ? 0 : (k & 1);
@@ -1036,16 +1132,17 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
         CK(cudaStreamWaitEvent(side, h->ev_dense[sn], 0));
         CK(cudaStreamWaitEvent(side, h->ev_step[sn], 0));
       }
-      GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side));
+      GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active));
       CK(cudaEventRecord(h->ev_sel[sn], side));
     }
-    if (!pipelined && !hoisted && k >= 1) GE(select_phase(h, h->ws.sel[si], text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, st));
+    if (!pipelined && !hoisted && k >= 1)
+      GE(select_phase(h, h->ws.sel[si], text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, st, clouds, nc, active));
     if (!hoisted || k == 0) {
       if (pipelined) {
         CK(cudaStreamWaitEvent(dst, h->ev_sel[si], 0));
         if (k >= 2) CK(cudaStreamWaitEvent(dst, h->ev_step[si], 0));  // pcd_out[si] was last read by step(k-2)
       }
-      GE(encode_dense(h, text, objs, cats, mask_global, si, dst));
+      GE(encode_dense(h, text, objs, cats, mask_global, si, dst, nullptr, clouds, nc, remap));
       if (pipelined) {
         CK(cudaEventRecord(h->ev_dense[si], dst));
         CK(cudaStreamWaitEvent(st, h->ev_dense[si], 0));
@@ -1193,6 +1290,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   }
   if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 3) {
     h->sa_fused = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "dedup_absent") == 0 && (value == 0 || value == 1)) {
+    h->dedup_absent = value;
     return LSDM_OK;
   }
   if (strcmp(name, "fp_tail") == 0 && (value == 0 || value == 1)) {

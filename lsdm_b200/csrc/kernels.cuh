@@ -97,7 +97,7 @@ struct SceneWeights {
 };
 // per (b,o'): scramble #1, collapsed 12-head attention, pointwise 15->3 GELU -> pw[B,9,1024,3], pa[B,9,12]
 int launch_point_attention(const SceneWeights& w, const float* backbone /*[9B,1024,3]*/, const float* attn_w,
-                           const float* qq, int B, float* pa, float* pw, cudaStream_t st);
+                           const float* qq, int B, float* pa, float* pw, cudaStream_t st, const int* remap = nullptr);
 // scramble #2 (global mask), sum over objects, average with human feature -> pcd_out[B,1024,3]
 int launch_scene_mix(const float* pw, const float* hm, const float* mask_global, int B, int Bg, int b_off, float* pcd_out,
                      cudaStream_t st);

@@ -15,11 +15,12 @@ constexpr int PA_T = 256;
 __global__ void __launch_bounds__(PA_T) point_attention_kernel(SceneWeights w, const float* __restrict__ backbone,
                                                                const float* __restrict__ attn_w,
                                                                const float* __restrict__ qq, float* __restrict__ pa_out,
-                                                               float* __restrict__ pw) {
+                                                               float* __restrict__ pw, const int* __restrict__ remap) {
   __shared__ float s_p1[NPTS * 3];
   __shared__ float s_red[PA_T / 32][TRANS][3];
   __shared__ float s_max[TRANS], s_ctx[TRANS], s_pa[TRANS];
   __shared__ float s_wk[TRANS * 3], s_wv[TRANS * 3], s_bk[TRANS], s_bv[TRANS], s_qq[TRANS], s_aw[NOBJ];
+  __shared__ int s_src[NOBJ];  // where cloud (b, o) sits in `backbone` (identity, or the de-duplicated order)
   const int bo = blockIdx.x, b = bo / NOBJ, op = bo % NOBJ, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   if (tid < TRANS * 3) {
@@ -31,13 +32,15 @@ __global__ void __launch_bounds__(PA_T) point_attention_kernel(SceneWeights w, c
     s_bv[tid] = w.p_inb[2 * TRANS + tid];
     s_qq[tid] = qq[(int64_t)bo * TRANS + tid];
   }
-  if (tid < NOBJ) s_aw[tid] = attn_w[(int64_t)b * NOBJ + tid];
+  if (tid < NOBJ) {
+    s_aw[tid] = attn_w[(int64_t)b * NOBJ + tid];
+    s_src[tid] = remap ? remap[b * NOBJ + tid] : b * NOBJ + tid;
+  }
   __syncthreads();
-  const float* Fb = backbone + (int64_t)b * NOBJ * NPTS * 3;
   for (int e = tid; e < NPTS * 3; e += PA_T) {
     int g = op * (NPTS * 3) + e;
     int o = g % NOBJ, c = g / NOBJ;
-    s_p1[e] = Fb[o * (NPTS * 3) + c] * s_aw[o];
+    s_p1[e] = backbone[(int64_t)s_src[o] * (NPTS * 3) + c] * s_aw[o];
   }
   __syncthreads();
 
@@ -152,8 +155,8 @@ __global__ void __launch_bounds__(256) scene_mix_kernel(const float* __restrict_
 }  // namespace
 
 int launch_point_attention(const SceneWeights& w, const float* backbone, const float* attn_w, const float* qq, int B,
-                           float* pa, float* pw, cudaStream_t st) {
-  point_attention_kernel<<<B * NOBJ, PA_T, 0, st>>>(w, backbone, attn_w, qq, pa, pw);
+                           float* pa, float* pw, cudaStream_t st, const int* remap) {
+  point_attention_kernel<<<B * NOBJ, PA_T, 0, st>>>(w, backbone, attn_w, qq, pa, pw, remap);
   return 1;
 }
 

@@ -66,6 +66,7 @@ class Engine:
         self.set_option("gemm_tma", int(os.environ.get("LSDM_GEMM_TMA", "1")))
         self.set_option("fp_tail", int(os.environ.get("LSDM_FP_TAIL", "1")))
         self.set_option("fp_fused", int(os.environ.get("LSDM_FP_FUSED", "1")))
+        self.set_option("dedup_absent", int(os.environ.get("LSDM_DEDUP_ABSENT", "1")))
 
     # ------------------------------------------------------------------ lifecycle
     @_on_device

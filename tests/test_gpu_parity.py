@@ -529,3 +529,47 @@ def test_uniform_cloud_shortcuts_are_exact():
         lvl_xyz = O._gather(lvl_xyz, ref_idx)
     uni = out[1]["fps_idx0"].view(C, 1024)[[1, 2, 3]]
     assert (uni[:, 1:] == 0).all()   # the closed form really is {start, 0, 0, ...}
+
+
+def test_absent_cloud_dedup_is_bit_identical():
+    """lsdm_sample_loop encodes ONE all-zero (absent, zero-padded) cloud per step and shares its backbone output with the other
+    absent clouds ("dedup_absent").  Eval-mode clouds are independent and an absent cloud's output does not depend on its FPS
+    starts, so every returned tensor must be BIT-identical to the run that encodes all 9B clouds -- also when no cloud is absent,
+    when only one is, and when a cloud is all -0.0 (not the zero-padded pattern: it must be encoded on its own)."""
+    B, K = 6, 4
+    m, diff = _model("wellcond")
+    inp = syn.make_inputs(77, B)
+    objs = inp["given_objs"].clone()
+    objs[1] = torch.rand(9, 1024, 3) - 0.5          # sample 1: every object present
+    objs[2, 1:] = 0.0                               # sample 2: only the human slot present
+    objs[3, 4] = -0.0                               # all -0.0: numerically zero, but not the dataset's padding bits
+    objs[4, 2] = 0.0
+    objs[4, 2, 1023, 2] = 1e-38                     # one denormal-ish coordinate: present
+    inp["given_objs"] = objs
+    fps, noise = syn.make_step_randoms(78, B, K)
+    g = _cuda(inp)
+    eng = diff._engine(m, B, torch.device("cuda", 0))
+    outs = {}
+    for flag in (1, 0):
+        eng.set_option("dedup_absent", flag)
+        try:
+            x = g["x_T"].clone()
+            x0, gd_ = eng.sample_loop(x, g["text_emb"], g["given_objs"], g["given_cats"], g["mask"], fps.cuda(), noise.cuda(), 999, False)
+            torch.cuda.synchronize()
+            outs[flag] = (x.clone(), x0.clone(), gd_.clone(), eng.out_cat().clone())
+        finally:
+            eng.set_option("dedup_absent", 1)
+    for a, b in zip(outs[1], outs[0]):
+        assert torch.equal(a, b)
+    # and nothing absent at all
+    objs2 = torch.rand(B, 9, 1024, 3) - 0.5
+    res = []
+    for flag in (1, 0):
+        eng.set_option("dedup_absent", flag)
+        try:
+            x = g["x_T"].clone()
+            eng.sample_loop(x, g["text_emb"], objs2.cuda(), g["given_cats"], g["mask"], fps.cuda(), noise.cuda(), 999, False)
+            res.append(x.clone())
+        finally:
+            eng.set_option("dedup_absent", 1)
+    assert torch.equal(res[0], res[1])
