@@ -70,20 +70,20 @@ struct Workspace {
   float* human_scratch;
   double* bn_stats;
   int64_t* t_dev;
-  // selection results (depend only on the clouds and the FPS start draws); two sets so that lsdm_sample_loop can run the
-  // selection chain of step k+1 on a side stream while the dense layers of step k run on the caller's stream
+  // selection results (depend only on the clouds and the FPS start draws); three sets so that lsdm_sample_loop can run the
+  // selection chain up to two steps ahead on a side stream while the dense layers and the x0 network of earlier steps run
   struct Sel {
     float *enc, *out_cat, *attn_w, *tr, *qq, *hm;  // step-invariant condition-MLP / human-decoder outputs
     int64_t* fps_start;
     int *idx[4], *grp[4], *nn_idx[4];
     float *xyz[5], *nn_w[4];
-  } sel[2];
+  } sel[3];  // NSEL
   int cur;  // set used by the last encode (debug taps)
   float* feat[5];
   // absent-cloud de-duplication (lsdm_sample_loop): compacted clouds, cloud -> compact position, compact -> cloud
   float* clouds_c;
   int *remap, *active, *n_active;
-  float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out[2];  // pcd_out: one per selection set (the step of k reads it while dense(k+1) writes the other)
+  float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out[3];  // pcd_out: one per selection set (the step of k reads it while dense(k+1), dense(k+2) write the others)
   // step
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
   float *H1_lo, *H2_lo, *embpre_lo, *cat_lo, *h1_lo, *c1_lo, *c2_lo;  // 3xTF32 residual planes of the step network's activations
@@ -125,7 +125,8 @@ struct lsdm_handle {
   bool have_ws = false;
   int64_t launches = 0;
   cudaStream_t side = nullptr, dense_st = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_sel[2] = {nullptr, nullptr}, ev_dense[2] = {nullptr, nullptr}, ev_step[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_sel[3] = {nullptr, nullptr, nullptr}, ev_dense[3] = {nullptr, nullptr, nullptr},
+              ev_step[3] = {nullptr, nullptr, nullptr};
   // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
   int precision = 0;       // dense layers of the condition encoder (PointNet++): 0 fp32, 1 tf32, 2 3xtf32
   int precision_step = 0;
@@ -254,7 +255,7 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   w->cur = 0;
   const size_t fn[4] = {64, 256, 1024, 1024};  // fine-point count of fp4, fp3, fp2, fp1
   for (int l = 1; l <= 4; ++l) w->feat[l] = a.take<float>(C * np[l] * fc[l]);
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 3; ++k) {
     Workspace::Sel& s = w->sel[k];
     s.enc = a.take<float>(B * LAT);
     s.out_cat = a.take<float>(B * nc);
@@ -288,8 +289,7 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   w->backbone = a.take<float>(C * NPTS * 3);
   w->pa = a.take<float>(C * TRANS);
   w->pw = a.take<float>(C * NPTS * 3);
-  w->pcd_out[0] = a.take<float>(B * NPTS * 3);
-  w->pcd_out[1] = a.take<float>(B * NPTS * 3);
+  for (int k = 0; k < 3; ++k) w->pcd_out[k] = a.take<float>(B * NPTS * 3);
   const size_t rows = B * NPTS;
   w->s256 = a.take<float>(B * 256);
   w->H1 = a.take<float>(B * 256 * 128);
@@ -626,9 +626,11 @@ __global__ void add_planes_kernel(const float* __restrict__ hi, const float* __r
   if (i < n) dst[i] = hi[i] + lo[i];
 }
 
-// Absent objects are zero-padded by the dataset (reference posa/dataset.py:456): a cloud whose 3072 floats are all +0.0f.
+// Absent objects are zero-padded by the dataset (reference posa/dataset.py:456): a cloud whose 3072 coordinates are all 0.0.
 // In eval mode every cloud goes through PointNet++ independently and the output for such a cloud does not depend on its
 // FPS start draws (every point, hence every gathered row, is the same), so all absent clouds of a batch share ONE result.
+// (A -0.0 coordinate compares equal to +0.0 in every selection and can only flip the sign of an activation that is
+// exactly zero: results are equal as values -- torch.equal -- which the tests and bench.py check against the full run.)
 __global__ void classify_clouds_kernel(const float* __restrict__ clouds, int* __restrict__ absent) {
   const uint4* p = reinterpret_cast<const uint4*>(clouds + (int64_t)blockIdx.x * NPTS * 3);
   unsigned acc = 0;
@@ -636,6 +638,7 @@ __global__ void classify_clouds_kernel(const float* __restrict__ clouds, int* __
     const uint4 v = p[i];
     acc |= v.x | v.y | v.z | v.w;
   }
+  acc &= 0x7fffffffu;  // value zero: +0.0 and -0.0 (an all-zero cloud multiplied by a 0 mask has both)
   const int any = __syncthreads_or(acc != 0);
   if (threadIdx.x == 0) absent[blockIdx.x] = any ? 0 : 1;
 }
@@ -714,7 +717,7 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
   cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, pmode >= 1 ? prio_hi : prio_lo);
   cudaStreamCreateWithPriority(&h->dense_st, cudaStreamNonBlocking, pmode >= 2 ? prio_hi : prio_lo);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     cudaEventCreateWithFlags(&h->ev_sel[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_dense[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming);
@@ -734,7 +737,7 @@ LSDM_API void lsdm_destroy(lsdm_handle* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->dense_st) cudaStreamDestroy(h->dense_st);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     if (h->ev_sel[i]) cudaEventDestroy(h->ev_sel[i]);
     if (h->ev_dense[i]) cudaEventDestroy(h->ev_dense[i]);
     if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
@@ -1085,10 +1088,11 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
   int64_t* tvec = h->ws.t_dev;
   if (!text || !objs || !cats || !mask_global) return fail(LSDM_EINVAL, "null argument");
   // STRICT, three-stage software pipeline over steps (nothing in the condition encoder depends on x):
-  //   side stream  : selection chain + condition MLPs + human decoder of step k+1   (FPS -> ball queries -> 3-NN)
-  //   dense stream : PointNet++ dense layers + scene branch of step k               -> pcd_out[k&1]
-  //   caller stream: x0 network + posterior of step k-... (the only part that is serial in x)
-  // Two buffer sets; events order producer -> consumer and consumer -> reuse.
+  //   side stream  : selection chain + condition MLPs + human decoder, up to two steps ahead   (FPS -> ball queries -> 3-NN)
+  //   dense stream : PointNet++ dense layers + scene branch of step k               -> pcd_out[k%3]
+  //   caller stream: x0 network + posterior of step k (the only part that is serial in x)
+  // Three buffer sets (selection(k+1) only has to wait for the consumers of step k-2); events order producer -> consumer and
+  // consumer -> reuse.
   // absent-cloud de-duplication: classify once per call (the clouds are constant over the loop), run the encoder on the
   // compacted list, read the shared result through `remap` in the scene branch
   const float* clouds = nullptr;
@@ -1114,6 +1118,26 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
   } else {
     h->n_active = C;
   }
+  // LSDM_TIMELINE=1: timing events at the start / end of every stage of every step, printed (after a synchronize) to stderr
+  static const bool timeline = getenv("LSDM_TIMELINE") && atoi(getenv("LSDM_TIMELINE")) != 0;
+  struct TL { int k; char stage; cudaEvent_t a, b; };
+  std::vector<TL> tl;
+  cudaEvent_t tl0 = nullptr;
+  auto tl_begin = [&](int k, char stage, cudaStream_t s) {
+    if (!timeline) return;
+    TL e{k, stage, nullptr, nullptr};
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, s);
+    tl.push_back(e);
+  };
+  auto tl_end = [&](cudaStream_t s) {
+    if (timeline) cudaEventRecord(tl.back().b, s);
+  };
+  if (timeline) {
+    cudaEventCreate(&tl0);
+    cudaEventRecord(tl0, st);
+  }
   const bool pipelined = !hoisted && n_steps > 1 && !h->profiling;
   cudaStream_t side = pipelined ? h->side : st;
   cudaStream_t dst = pipelined ? h->dense_st : st;
@@ -1122,27 +1146,32 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     CK(cudaStreamWaitEvent(side, h->ev_fork, 0));
     CK(cudaStreamWaitEvent(dst, h->ev_fork, 0));
   }
+  tl_begin(0, 'S', side);
   GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side, clouds, nc, active));
+  tl_end(side);
   if (pipelined) CK(cudaEventRecord(h->ev_sel[0], side));
   for (int k = 0; k < n_steps; ++k) {
-    const int si = hoisted ? 0 : (k & 1);
+    const int si = hoisted ? 0 : (k % 3);
     if (pipelined && k + 1 < n_steps) {
-      const int sn = (k + 1) & 1;
-      if (k >= 1) {  // set sn was last read by dense(k-1) and step(k-1)
+      const int sn = (k + 1) % 3;
+      if (k >= 2) {  // set sn (selection results, condition MLP outputs, pcd_out[sn]) was last read by dense(k-2) and step(k-2)
         CK(cudaStreamWaitEvent(side, h->ev_dense[sn], 0));
         CK(cudaStreamWaitEvent(side, h->ev_step[sn], 0));
       }
+      tl_begin(k + 1, 'S', side);
       GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active));
+      tl_end(side);
       CK(cudaEventRecord(h->ev_sel[sn], side));
     }
     if (!pipelined && !hoisted && k >= 1)
       GE(select_phase(h, h->ws.sel[si], text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, st, clouds, nc, active));
     if (!hoisted || k == 0) {
       if (pipelined) {
-        CK(cudaStreamWaitEvent(dst, h->ev_sel[si], 0));
-        if (k >= 2) CK(cudaStreamWaitEvent(dst, h->ev_step[si], 0));  // pcd_out[si] was last read by step(k-2)
+        CK(cudaStreamWaitEvent(dst, h->ev_sel[si], 0));  // (select(k) already waited for step(k-3), the last reader of pcd_out[si])
       }
+      tl_begin(k, 'D', dst);
       GE(encode_dense(h, text, objs, cats, mask_global, si, dst, nullptr, clouds, nc, remap));
+      tl_end(dst);
       if (pipelined) {
         CK(cudaEventRecord(h->ev_dense[si], dst));
         CK(cudaStreamWaitEvent(st, h->ev_dense[si], 0));
@@ -1155,9 +1184,24 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     const bool last = (k == n_steps - 1);
     // STRICT recomputes the guiding points every step like the reference; hoisted only needs them at the end
     const bool want_guiding = !hoisted || last;
+    tl_begin(k, 'X', st);
     GE(step_core(h, x, tvec, noise_all + (size_t)k * per, x, last ? x0_out : nullptr, last ? guiding_out : nullptr,
                  want_guiding, clip_denoised, st, si));
+    tl_end(st);
     if (pipelined) CK(cudaEventRecord(h->ev_step[si], st));
+  }
+  if (timeline) {
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[lsdm timeline] n_steps=%d clouds=%d/%d  (stage S=selection D=dense X=x0-network; ms since call start)\n", n_steps, h->n_active, C);
+    for (auto& e : tl) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, tl0, e.a);
+      cudaEventElapsedTime(&b, tl0, e.b);
+      if (e.k < 6 || e.k >= n_steps - 2) fprintf(stderr, "[lsdm timeline] k=%3d %c  %8.3f -> %8.3f  (%.3f)\n", e.k, e.stage, a, b, b - a);
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    cudaEventDestroy(tl0);
   }
   return LSDM_OK;
 }
