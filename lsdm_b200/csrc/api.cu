@@ -114,6 +114,7 @@ struct lsdm_handle {
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
   int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
   int fp_fused = 0;              // 1: fused fp2 level (fine GEMM + interpolation + second conv in one kernel)
+  int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
   int dedup_absent = 1;          // 1: lsdm_sample_loop encodes ONE all-zero (absent, zero-padded) cloud per step and shares its
                                  //    backbone output with every other absent cloud (bit-identical: eval-mode clouds are independent)
   int n_active = 0;              // clouds the encoder runs on in the current lsdm_sample_loop call
@@ -573,6 +574,33 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   }
   GE(gemm(h, st, w.embpre, 256, h->W("combine_extraction.0.weight"), 256, w.cat + 128, 256,
           h->W("combine_extraction.0.bias"), rows, 128, 256, ACT_GELU, 0, ps, 0, sp ? w.embpre_lo : nullptr, sp ? w.cat_lo + 128 : nullptr));
+  if (sp && h->x0_fused && (rows & 127) == 0) {
+    // the whole x0 network (both passes), `x += pcd_out`, the posterior and the ancestral noise in one persistent kernel
+    auto hi = [&](const char* k) { return h->W(k) + h->round_delta; };
+    auto lo = [&](const char* k) { return h->W(k) + h->lo_delta; };
+    const int n_pass = want_guiding ? 2 : 1;
+    const double fl = 2.0 * rows * n_pass * (64.0 * 128 + 256.0 * 192 + 192.0 * 128 + 128.0 * 64);
+    float* gd = want_guiding ? (guiding_out ? guiding_out : w.guiding) : nullptr;
+    int r = prof_launch(h, st, K_GEMM, [&] {
+      return launch_x0net_fused(x, w.pcd_out[si], noise, sample_out, x0_out ? x0_out : w.x0, gd, w.t_dev, h->sched,
+                                h->sched ? h->sched + h->T : nullptr, h->sched ? h->sched + 2 * h->T : nullptr, rows, n_pass, clip,
+                                w.cat + 128, w.cat_lo + 128, 256, hi("input_process.pose_embedding.2.weight"),
+                                lo("input_process.pose_embedding.2.weight"), hi("input_process.combination_extraction.0.weight"),
+                                lo("input_process.combination_extraction.0.weight"), hi("input_process.combination_extraction.2.weight"),
+                                lo("input_process.combination_extraction.2.weight"), hi("output_process.pose_final.0.weight"),
+                                lo("output_process.pose_final.0.weight"), h->W("input_process.pose_embedding.0.weight"),
+                                h->W("input_process.pose_embedding.0.bias"), h->W("input_process.pose_embedding.2.bias"),
+                                h->W("input_process.combination_extraction.0.bias"), h->W("input_process.combination_extraction.2.bias"),
+                                h->W("output_process.pose_final.0.bias"), h->W("output_process.pose_final.2.weight"),
+                                h->W("output_process.pose_final.2.bias"), st);
+    }, "x0net_fused", fl);
+    if (r > 0) {
+      if (h->profiling) h->gemm_flops += fl;
+      CK(cudaPeekAtLastError());
+      return LSDM_OK;
+    }
+    // TMA descriptors unavailable: the layer-by-layer chain below
+  }
   const int M = want_guiding ? 2 * rows : rows;
   if (want_guiding) {
     CK(cudaMemcpy2DAsync(w.cat + (size_t)rows * 256 + 128, 256 * sizeof(float), w.cat + 128, 256 * sizeof(float),
@@ -1334,6 +1362,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   }
   if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 3) {
     h->sa_fused = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "x0_fused") == 0 && (value == 0 || value == 1)) {
+    h->x0_fused = value;
     return LSDM_OK;
   }
   if (strcmp(name, "dedup_absent") == 0 && (value == 0 || value == 1)) {

@@ -342,6 +342,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(GemmArgs g, int 
   if (warp == 0) tmem_dealloc(tmem, 2 * TCOLS_PER);
 }
 
+}  // namespace
+
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeFn tma_encoder() {
@@ -367,6 +369,8 @@ bool tma_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int K, int64_t l
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+namespace {
 
 template <int BN, bool SPLIT, bool ASYNC>
 int launch_ws2(const GemmArgs& g, cudaStream_t st) {

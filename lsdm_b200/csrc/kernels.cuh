@@ -56,6 +56,16 @@ int launch_fp1_fused(const float* Pb, const int* nn_idx, const float* nn_w, cons
 int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const float* Wh, const float* h_consts, int64_t rows,
                     float* out, cudaStream_t st);
 
+// ---- x0net_fused.cu ---------------------------------------------------------------------------
+// the x0 network of one step (3 -> 64 -> 128 || emb -> 192 -> 128 -> 64 -> 3, 3xTF32) + in-place x += pcd_out + posterior mean +
+// ancestral noise, per 128-row tile; n_pass == 2 also runs the guiding-points pass.  Returns -1 if TMA descriptors cannot be built.
+int launch_x0net_fused(float* x, const float* pcd_out, const float* noise, float* sample_out, float* x0_out, float* guiding_out,
+                       const int64_t* t, const float* c1, const float* c2, const float* logvar, int rows, int n_pass, int clip,
+                       const float* emb_hi, const float* emb_lo, int64_t ld_emb, const float* w1, const float* w1_lo, const float* w2,
+                       const float* w2_lo, const float* w3, const float* w3_lo, const float* w4, const float* w4_lo, const float* w0,
+                       const float* b0, const float* b1, const float* b2, const float* b3, const float* b4, const float* w5,
+                       const float* b5, cudaStream_t st);
+
 // ---- bn_train.cu ------------------------------------------------------------------------------
 // train-mode BatchNorm: column statistics (double), then normalise + ReLU [+ dropout mask] [+ 32-row max-pool] and the
 // running-statistics update (momentum 0.1, unbiased variance)

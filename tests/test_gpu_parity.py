@@ -573,3 +573,39 @@ def test_absent_cloud_dedup_is_bit_identical():
         finally:
             eng.set_option("dedup_absent", 1)
     assert torch.equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_x0net_fused_kernel_matches_layer_chain(B):
+    """The fused x0-network kernel (x0net_fused.cu: x += pcd_out, five layers in tensor memory, posterior + noise) against the
+    layer-by-layer GEMM chain it replaces ("x0_fused" = 0): same 3xTF32 arithmetic, so 1e-5 relative; and against the oracle."""
+    sd = syn.make_state_dict(0, "wellcond")
+    tables = O.diffusion_tables(O.cosine_betas(1000))
+    inp = syn.make_inputs(61, B)
+    fps, noise = syn.make_step_randoms(62, B, 1)
+    m, diff = _model("wellcond")
+    g = _cuda(inp)
+    eng = diff._engine(m, B, torch.device("cuda", 0))
+    outs = {}
+    for clip in (False, True):
+        for flag in (1, 0):
+            eng.set_option("x0_fused", flag)
+            try:
+                x = g["x_T"].clone()
+                t = torch.tensor([999, 0, 417][:B], dtype=torch.long, device="cuda")
+                m.encode(g["mask"], g["given_objs"], g["given_cats"], g["text_emb"], fps[0])
+                sample, x0, gd_ = eng.denoise_step(x, t, noise[0].cuda(), clip_denoised=clip)
+                torch.cuda.synchronize()
+                outs[(clip, flag)] = (sample.clone(), x0.clone(), gd_.clone(), x.clone())
+            finally:
+                eng.set_option("x0_fused", 1)
+        for a, b in zip(outs[(clip, 1)], outs[(clip, 0)]):
+            assert rel_l2(a.cpu(), b.cpu()) < 1e-5
+    xo = inp["x_T"].clone()
+    ref = O.p_sample(sd, tables, xo, inp["mask"], torch.tensor([999, 0, 417][:B]), inp["given_objs"], inp["given_cats"], inp["text_emb"],
+                     list(fps[0]), noise[0])
+    sample, x0, gd_, xm = outs[(False, 1)]
+    assert rel_l2(sample.cpu(), ref["sample"]) < TOL_E2E
+    assert rel_l2(x0.cpu(), ref["pred_xstart"]) < TOL_E2E
+    assert rel_l2(gd_.cpu(), ref["guiding"]) < TOL_E2E
+    assert rel_l2(xm.cpu(), xo) < TOL_E2E
