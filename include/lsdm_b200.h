@@ -150,6 +150,29 @@ LSDM_API int lsdm_chamfer(lsdm_handle* h, const float* x, const float* y, int32_
  * sum_b CrossEntropy(probs[b,:] treated as logits, argmax(target_cat[b,:])) accumulated into *sum. */
 LSDM_API int lsdm_cat_loss(lsdm_handle* h, const float* probs, const float* target_cat, int32_t batch, float* sum, void* stream);
 
+/* ---- Training backward.  Replaces `mp_trainer.backward(loss)` of run/train_sdm.py:78-84 (autograd through
+ * diffusion/gaussian_diffusion.py:1256-1342 and model/sdm.py:131-218 in model.train() mode) and the AdamW step of
+ * diffusion/fp16_util.py:198-214 / run/train_sdm.py:268.
+ *
+ * lsdm_training_backward runs a taped fp32 forward of training_losses (BatchNorm batch statistics -- all-reduced through the
+ * lsdm_set_allreduce hook when sharded --, the caller's q_sample noise, FPS starts and Dropout mask) and the reverse sweep, and
+ * ACCUMULATES the gradient of  g_mse * chamfer + g_cat * lambda_cat * CE  into `grads`: a float buffer of lsdm_grad_floats()
+ * elements in which state-dict entry i occupies [offset, offset + numel) as reported by lsdm_weight_slot() (same order and
+ * keys as lsdm_weight_key; BatchNorm running statistics and the dead attn_layer v_proj / out_proj slots stay untouched).
+ * `tape`: device scratch of lsdm_train_tape_bytes() bytes.  losses_out (device, nullable): [chamfer, mean cross-entropy].
+ * x0_out (device, nullable): the model output [Bl,1024,3].  All pointers device except fps_start (host or device). */
+LSDM_API size_t lsdm_train_tape_bytes(const lsdm_handle* h);
+LSDM_API int64_t lsdm_grad_floats(const lsdm_handle* h);
+LSDM_API int lsdm_weight_slot(const lsdm_handle* h, int32_t i, int64_t* offset, int64_t* numel);
+LSDM_API int lsdm_training_backward(lsdm_handle* h, const float* x_start, const int64_t* t, const float* noise, const float* text_emb,
+                                    const float* given_objs, const float* given_cats, const float* mask_global, const float* target_cat,
+                                    const int64_t* fps_start, const float* drop_mask, float lambda_cat, float g_mse, float g_cat, void* tape,
+                                    size_t tape_bytes, float* grads, float* losses_out, float* x0_out, void* stream);
+/* torch.optim.AdamW update of one flat tensor (decoupled weight decay, bias correction with `step` >= 1; grad is multiplied by
+ * grad_scale first, e.g. 1/world_size after a summing all-reduce). */
+LSDM_API int lsdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+
 /* ---- Evaluation metrics of the sampling path (reference run/test_sdm.py:186-207).  Handle-free. ----
  *
  * lsdm_eval_emd replaces util/evaluation.py:5-11 `emd(x, y)` = scipy cdist + linear_sum_assignment: for each of `batch`

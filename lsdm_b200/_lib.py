@@ -63,6 +63,11 @@ PROTOTYPES = {
     "lsdm_q_sample": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "lsdm_chamfer": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lsdm_cat_loss": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
+    "lsdm_train_tape_bytes": (C.c_size_t, [_P]),
+    "lsdm_grad_floats": (C.c_int64, [_P]),
+    "lsdm_weight_slot": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lsdm_training_backward": (C.c_int, [_P] + [_P] * 10 + [C.c_float, C.c_float, C.c_float, _P, C.c_size_t, _P, _P, _P, _P]),
+    "lsdm_adamw_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_float, _P]),
     "lsdm_eval_emd": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "lsdm_eval_fscore": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P]),
     "lsdm_eval_chamfer": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

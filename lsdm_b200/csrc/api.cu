@@ -9,6 +9,7 @@
 
 #include "../../include/lsdm_b200.h"
 #include "kernels.cuh"
+#include "train_bw.cuh"
 
 using namespace lsdm;
 
@@ -1308,6 +1309,70 @@ LSDM_API int lsdm_cat_loss(lsdm_handle* h, const float* probs, const float* targ
   if (!h || !probs || !target_cat || !sum || batch <= 0) return fail(LSDM_EINVAL, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   prof_launch(h, st, K_OTHER, [&] { return launch_cat_loss(probs, target_cat, batch, h->cfg.n_cats, sum, st); });
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
+// ---- training backward: reference run/train_sdm.py:78-84 `mp_trainer.backward(loss)` ----
+LSDM_API size_t lsdm_train_tape_bytes(const lsdm_handle* h) { return h ? train_tape_bytes(h->cfg.batch_local, h->cfg.n_cats) : 0; }
+LSDM_API int64_t lsdm_grad_floats(const lsdm_handle* h) { return h ? h->arena_floats : 0; }
+LSDM_API int lsdm_weight_slot(const lsdm_handle* h, int32_t i, int64_t* offset, int64_t* numel) {
+  if (!h || i < 0 || i >= (int)h->entries.size() || !offset || !numel) return fail(LSDM_EINVAL, "bad argument");
+  *offset = h->entries[i].off;
+  *numel = h->entries[i].numel;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_training_backward(lsdm_handle* h, const float* x_start, const int64_t* t, const float* noise, const float* text,
+                                    const float* objs, const float* cats, const float* mask_global, const float* target_cat,
+                                    const int64_t* fps_start, const float* drop_mask, float lambda_cat, float g_mse, float g_cat, void* tape,
+                                    size_t tape_bytes, float* grads, float* losses_out, float* x0_out, void* stream) {
+  GE(check_ready(h, false));
+  if (!h->have_sched) return fail(LSDM_ESTATE, "no schedule (lsdm_set_schedule)");
+  if (!x_start || !t || !noise || !text || !objs || !cats || !mask_global || !target_cat || !fps_start || !drop_mask || !tape || !grads)
+    return fail(LSDM_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace& w = h->ws;
+  const int B = h->cfg.batch_local;
+  // selection chain (FPS order, ball-query groups, 3-NN) for these clouds and FPS starts: integer / piecewise-constant, no gradient
+  GE(select_phase(h, w.sel[0], text, objs, cats, mask_global, fps_start, st));
+  CK(cudaMemcpyAsync(w.t_dev, t, sizeof(int64_t) * B, cudaMemcpyDefault, st));
+  TrainCtx ctx;
+  ctx.W = [h](const std::string& k) { return h->W(k); };
+  ctx.G = [h, grads](const std::string& k) { return grads + h->entries[h->index.at(k)].off; };
+  ctx.B = B;
+  ctx.Bg = h->cfg.batch_global;
+  ctx.b_off = h->cfg.batch_offset;
+  ctx.n_cats = h->cfg.n_cats;
+  ctx.tape = tape;
+  ctx.tape_bytes = tape_bytes;
+  ctx.allreduce = h->allreduce;
+  ctx.allreduce_ctx = h->allreduce_ctx;
+  ctx.sched_sa = h->sched + 3 * h->T;
+  ctx.sched_s1a = h->sched + 4 * h->T;
+  TrainIO io;
+  io.text = text; io.objs = objs; io.cats = cats; io.mask_global = mask_global; io.x_start = x_start; io.noise = noise;
+  io.target_cat = target_cat; io.drop_mask = drop_mask; io.t = w.t_dev;
+  const Workspace::Sel& q = w.sel[0];
+  for (int l = 1; l <= 4; ++l) io.xyz[l] = q.xyz[l];
+  for (int l = 0; l < 4; ++l) {
+    io.grp[l] = q.grp[l];
+    io.nn_idx[l] = q.nn_idx[l];
+    io.nn_w[l] = q.nn_w[l];
+  }
+  io.g_mse = g_mse; io.g_cat = g_cat; io.lambda_cat = lambda_cat;
+  io.losses_out = losses_out;
+  io.x0_out = x0_out;
+  int r = train_forward_backward(ctx, io, st);
+  if (r != 0) return r;
+  h->launches += 1;
+  return LSDM_OK;
+}
+
+LSDM_API int lsdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return fail(LSDM_EINVAL, "bad argument");
+  launch_adamw(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream);
   CK(cudaPeekAtLastError());
   return LSDM_OK;
 }

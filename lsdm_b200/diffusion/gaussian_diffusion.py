@@ -331,12 +331,24 @@ class GaussianDiffusion:
 
     # ------------------------------------------------------------------ training
     def training_losses(self, model, cf, mask, t, given_objs, given_cats, target_cat, y=None, noise=None):
-        """Reference gaussian_diffusion.py:1256-1342 (MSE loss type, START_X): forward value of
-        ``{'cat_loss','mse','loss'}`` as scalar tensors.  (Backward is SURVEY.md 8f row 1, not built yet.)"""
+        """Reference gaussian_diffusion.py:1256-1342 (MSE loss type, START_X): ``{'cat_loss','mse','loss'}`` as scalar tensors.
+        Under ``torch.no_grad()`` (or with frozen parameters) only the forward runs.  Otherwise the scalars carry an autograd
+        node whose backward is ``lsdm_training_backward`` (taped fp32 forward + reverse sweep inside the library), so that the
+        reference's ``loss.backward()`` / ``mp_trainer.backward(loss)`` (run/train_sdm.py:78-84) fills ``.grad`` of every
+        trainable parameter."""
         net = self._unwrap(model)
         x_start = cf
         if noise is None:
             noise = th.randn_like(x_start)
+        params = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+        if th.is_grad_enabled() and params:
+            if not net.training:
+                raise NotImplementedError("backward through training_losses is implemented for model.train() (BatchNorm batch statistics, "
+                                          "as run/train_sdm.py trains); call it under torch.no_grad() for the eval-mode forward value")
+            mse, ce = _TrainingLossFn.apply(self, model, x_start, mask, t, given_objs, given_cats, target_cat, y, noise,
+                                            [n for n, _ in params], *[p for _, p in params])
+            cat_loss = ce * self.lambda_cat
+            return {"cat_loss": cat_loss, "mse": mse, "loss": mse + cat_loss}
         eng = self._engine(model, x_start.shape[0], x_start.device)
         x_t = eng.q_sample(x_start.float(), t, noise.float())
         out_cat, model_output = net(x_t, mask, self._scale_timesteps(t), given_objs, given_cats, y)
@@ -347,3 +359,51 @@ class GaussianDiffusion:
         terms["mse"] = eng.chamfer(model_output.float(), x_start.float())
         terms["loss"] = terms["mse"] + cat_loss
         return terms
+
+
+# attn_layer's value / output projections never reach the loss (only the attention WEIGHTS are used, model/sdm.py:182): the
+# reference leaves their .grad at None
+_DEAD_PARAMS = ("attn_layer.v_proj_weight", "attn_layer.out_proj.weight", "attn_layer.out_proj.bias")
+
+
+class _TrainingLossFn(th.autograd.Function):
+    """(chamfer, mean cross-entropy) of one training forward, with the library's backward."""
+
+    @staticmethod
+    def forward(ctx, diffusion, model, x_start, mask, t, given_objs, given_cats, target_cat, y, noise, names, *params):
+        net = diffusion._unwrap(model)
+        B = x_start.shape[0]
+        eng = diffusion._engine(model, B, x_start.device)
+        text = net._encode_text(y)
+        # RNG exactly as the reference's forward consumes it: four CPU FPS-start draws, then the Dropout(0.5) mask of the head
+        fps = net.draw_fps_starts(B)
+        drop = net.draw_dropout_mask(B, eng.device)
+        with th.no_grad():
+            x_t = eng.q_sample(x_start.float(), t, noise.float())
+            net.encode(mask, given_objs, given_cats, text, fps, device=eng.device, drop_mask=drop)   # updates the BatchNorm running stats
+            out_cat, x0, guiding = eng.forward(x_t, diffusion._scale_timesteps(t))
+            net.saved_cat, net.saved_guiding_points = out_cat.unsqueeze(1), guiding
+            ce = eng.cat_loss(out_cat, target_cat)
+            mse = eng.chamfer(x0, x_start.float())
+        ctx.saved = (diffusion, model, x_start, mask, t, given_objs, given_cats, target_cat, text, noise, fps, drop, list(names),
+                     [tuple(p.shape) for p in params])
+        return mse, ce
+
+    @staticmethod
+    def backward(ctx, g_mse, g_ce):
+        diffusion, model, x_start, mask, t, given_objs, given_cats, target_cat, text, noise, fps, drop, names, shapes = ctx.saved
+        net = diffusion._unwrap(model)
+        eng = diffusion._engine(model, x_start.shape[0], x_start.device)
+        if net._shard is not None and net._sync_bn_group is not None:
+            eng.set_allreduce(net._sync_bn_group if net._sync_bn_group is not True else None)
+        flat, _, _ = eng.training_backward(x_start, t, noise, text, given_objs, given_cats, mask, target_cat, fps, drop, 1.0,
+                                           float(g_mse), float(g_ce))
+        slots = eng.weight_slots()
+        grads = []
+        for n, shp in zip(names, shapes):
+            if n in _DEAD_PARAMS or n not in slots:
+                grads.append(None)
+                continue
+            off, num = slots[n]
+            grads.append(flat[off:off + num].view(shp))
+        return (None,) * 11 + tuple(grads)

@@ -301,6 +301,46 @@ class Engine:
         return s[0] / B
 
     @_on_device
+    # ------------------------------------------------------------------ training backward
+    def weight_slots(self):
+        """{state-dict key: (offset, numel)} of the flat gradient buffer ``lsdm_training_backward`` accumulates into."""
+        if getattr(self, "_slots", None) is None:
+            slots = {}
+            off, num = C.c_int64(), C.c_int64()
+            for i in range(self.lib.lsdm_num_weights(self.h)):
+                _lib.check(self.lib.lsdm_weight_slot(self.h, i, C.byref(off), C.byref(num)))
+                if off.value >= 0:
+                    slots[self.lib.lsdm_weight_key(self.h, i).decode()] = (off.value, num.value)
+            self._slots = slots
+        return self._slots
+
+    @_on_device
+    def training_backward(self, x_start, t, noise, text_emb, given_objs, given_cats, mask_global, target_cat, fps_start, drop_mask,
+                          lambda_cat, g_mse, g_cat, want_x0=False):
+        """Taped train-mode forward + reverse sweep inside the library.  Returns (flat gradient [lsdm_grad_floats], losses[2], x0)."""
+        B = self.batch_local
+        x_start, noise, text_emb, given_objs, given_cats, mask_global, target_cat, drop_mask = map(
+            self._f32, (x_start, noise, text_emb, given_objs, given_cats, mask_global, target_cat, drop_mask))
+        t = self._i64(t).to(self.device)
+        fps_start = self._i64(fps_start)
+        assert fps_start.shape == (4, B * N_OBJ) and drop_mask.shape == (B * N_OBJ, 128, N_POINTS)
+        need = int(self.lib.lsdm_train_tape_bytes(self.h))
+        if getattr(self, "_tape", None) is None or self._tape.numel() < need + 256:
+            self._tape = None
+            self._tape = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        base = (self._tape.data_ptr() + 255) & ~255
+        grads = torch.zeros(int(self.lib.lsdm_grad_floats(self.h)), device=self.device)
+        losses = torch.zeros(2, device=self.device)
+        x0 = torch.empty(B, N_POINTS, 3, device=self.device) if want_x0 else None
+        self._cond_keep = (x_start, noise, text_emb, given_objs, given_cats, mask_global, target_cat, drop_mask, t, fps_start)
+        _lib.check(self.lib.lsdm_training_backward(self.h, _ptr(x_start), _ptr(t), _ptr(noise), _ptr(text_emb), _ptr(given_objs), _ptr(given_cats),
+                                                   _ptr(mask_global), _ptr(target_cat), _ptr(fps_start), _ptr(drop_mask), float(lambda_cat),
+                                                   float(g_mse), float(g_cat), C.c_void_p(base), C.c_size_t(need), _ptr(grads), _ptr(losses),
+                                                   _ptr(x0), _stream(self.device)))
+        if not fps_start.is_cuda:
+            torch.cuda.current_stream(self.device).synchronize()
+        return grads, losses, x0
+
     def debug_tensor(self, name, dtype=torch.float32):
         n = self.lib.lsdm_debug_tensor(self.h, name.encode(), None, 0, None)
         if n < 0:

@@ -288,6 +288,13 @@ class SceneDiffusionModel(nn.Module):
         draws = [torch.randint(0, n, (bg * N_OBJ,), dtype=torch.long) for n in FPS_LEVEL_N]
         return torch.stack([d.view(bg, N_OBJ)[off:off + batch_local].reshape(-1) for d in draws])
 
+    def draw_dropout_mask(self, batch_local, device):
+        """The mask ``F.dropout`` would draw for the reference's ``[9B,128,1024]`` head activation (pointnet2.py:76, p = 0.5, values 0
+        or 2; same generator, GLOBAL shape, sliced to the shard)."""
+        bg, off = self._shard if self._shard is not None else (batch_local, 0)
+        full = torch.nn.functional.dropout(torch.ones(bg * N_OBJ, 128, N_POINTS, device=device), 0.5, True)
+        return full[off * N_OBJ:(off + batch_local) * N_OBJ].contiguous()
+
     def encode(self, mask, given_objs, given_cats, y, fps_start=None, device=None, drop_mask=None):
         """Step-invariant part of forward (reference sdm.py:147-203).  Returns the engine."""
         B = given_objs.shape[0]
@@ -305,9 +312,7 @@ class SceneDiffusionModel(nn.Module):
                     raise NotImplementedError("sharded train-mode forward needs set_shard(..., sync_bn_group=<process group>) (SyncBN)")
                 eng.set_allreduce(self._sync_bn_group if self._sync_bn_group is not True else None)
             if drop_mask is None:
-                bg, off = self._shard if self._shard is not None else (B, 0)
-                full = torch.nn.functional.dropout(torch.ones(bg * N_OBJ, 128, N_POINTS, device=eng.device), 0.5, True)
-                drop_mask = full[off * N_OBJ:(off + B) * N_OBJ].contiguous()
+                drop_mask = self.draw_dropout_mask(B, eng.device)
             eng.encode_conditions_train(self._encode_text(y), given_objs, given_cats, mask, fps_start, drop_mask)
             self._pull_bn_stats(eng)
         else:
