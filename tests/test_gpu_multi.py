@@ -31,3 +31,13 @@ def test_train_mode_syncbn_two_ranks():
            "--master-port", "29613", os.path.join(ROOT, "tests", "multi_train_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0 and "SYNCBN_OK" in out.stdout, out.stderr[-3000:]
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_training_backward_two_ranks():
+    """Data-parallel training step (global batch 4 over 2 ranks): SyncBN forward + backward sums over NCCL inside the library, one
+    all-reduce of the flat gradient; the averaged gradients equal those of the unsharded batch on one GPU."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", os.path.join(ROOT, "tests", "multi_backward_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0 and "SHARDED_BACKWARD_OK" in out.stdout, out.stderr[-3000:]
