@@ -191,8 +191,13 @@ class Engine:
 
         def hook(_ctx, ptr, n):
             try:
-                off = int(ptr) - self._ws.data_ptr()
-                buf = self._ws[off:off + 8 * n].view(torch.float64)
+                buf = None
+                for owner in (self._ws, getattr(self, "_tape", None)):   # the statistics live in the workspace or in the training tape
+                    if owner is not None and owner.data_ptr() <= int(ptr) and int(ptr) + 8 * n <= owner.data_ptr() + owner.numel():
+                        off = int(ptr) - owner.data_ptr()
+                        buf = owner[off:off + 8 * n].view(torch.float64)
+                if buf is None:
+                    raise RuntimeError("all-reduce hook: pointer outside the engine's buffers")
                 dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=process_group)
                 return 0
             except Exception:  # pragma: no cover
