@@ -637,8 +637,48 @@ def run_ours(args):
                 cfg4[mode_name] = {"value": B4 * world * K4 / (t_ms * 1e-3), "unit": "samples/s", "ms_per_forward": t_ms / K4, "steps": K4, "warmup": W4,
                                    "loss": float(last[0]), "mse": float(last[1]), "cat_loss": float(last[2]),
                                    "e2e": {"value": B4 * world / dt4, "unit": "samples/s", "h2d_bytes_per_step": int(h2d4), "d2h_bytes_per_step": 12}}
+            # ---- the whole training step of run/train_sdm.py:60-84: training_losses -> loss.backward() -> AdamW.step() ----
+            from lsdm_b200.optim import FusedAdamW
+
+            model.train(True)
+            opt = FusedAdamW(model.parameters(), lr=1e-3, all_reduce=world > 1)
+            w_host = torch.ones(B4)
+
+            def train_step(src):
+                opt.zero_grad(set_to_none=True)
+                terms = diff.training_losses(model, src["x_start"], src["mask"], src["t"], src["given_objs"], src["given_cats"], src["target_cat"],
+                                             y=src["text_emb"])
+                loss = (terms["loss"] * w_host.to(terms["loss"].device)).mean()   # run/train_sdm.py:79
+                loss.backward()
+                opt.step()
+                return loss.detach()
+
+            torch.manual_seed(12)
+            first = float(train_step(g4))
+            KT = 3
+            t_ms = dev_timed(lambda: [train_step(g4) for _ in range(KT)])
+            runs_t = []
+            last_l = None
+            for _ in range(KT):
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                last_l = float(train_step(host4))   # host batch in, loss value read back
+                runs_t.append(time.perf_counter() - t0)
+            dtt = sum(runs_t) / KT
+            if world > 1:
+                tt = torch.tensor([dtt], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dtt = float(tt.item())
+            cfg4["train_step_fwd_bwd_adamw"] = {
+                "value": B4 * world * KT / (t_ms * 1e-3), "unit": "samples/s", "ms_per_step": t_ms / KT, "steps": KT, "warmup": 1,
+                "loss_first": first, "loss_last": last_l, "e2e": {"value": B4 * world / dtt, "unit": "samples/s", "h2d_bytes_per_step": int(h2d4), "d2h_bytes_per_step": 4},
+                "note": "diffusion.training_losses(...) -> (loss * weights).mean().backward() -> FusedAdamW.step(): the forward through the tensor-core path, "
+                        "the backward as a taped fp32 forward + reverse sweep on the CUDA cores (lsdm_training_backward), one gradient all-reduce when N > 1"}
+            del opt
             model.eval()
-            model.load_state_dict(sd0)   # train-mode forwards moved the BatchNorm running statistics
+            model.load_state_dict(sd0)   # train-mode forwards moved the BatchNorm running statistics; the optimiser moved the weights
             cfg4["workload"] = (f"BASELINE configs[3]: diffusion.training_losses forward (q_sample + SDM forward + chamfer + category CE), {B4} samples per GPU, "
                                 f"global batch {B4 * world}; eval_bn = model.eval() (folded BatchNorm), train_bn = model.train() (batch statistics over all "
                                 "9B clouds, running-stat updates, Dropout; SyncBN all-reduce of the statistics when N > 1); one all-reduce of the three loss scalars")
