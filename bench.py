@@ -316,12 +316,12 @@ def run_ours(args):
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     traffic, traffic_src = None, None
     try:  # dram bytes per launch of the same kernel class from the committed `ncu --set full` capture
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_kernel_metrics.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_kernel_metrics.json")) as f:
             tc = json.load(f)["_tensor_class"]
-        traffic, traffic_src = tc["avg_dram_bytes_per_launch"], "profiles/r1_ncu_kernel_metrics.json (" + tc["source"] + ")"
+        traffic, traffic_src = tc["avg_dram_bytes_per_launch"], "profiles/r2_ncu_kernel_metrics.json (" + tc["source"] + ")"
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "tensor-core dense layers (sa_fused*, gemm_ws/gemm_tc, fp1_tail)", "achieved": gemm_tflops,
+    roofline = {"bound": "tensor", "kernel": "tensor-core dense layers (sa_fused*, fp*_fused, x0net_fused, gemm_ws)", "achieved": gemm_tflops,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": f"{peak_src} bf16_tflops_sustained/2 (TF32 dense runs at half the bf16 rate)",
                 "flops_per_launch_avg": gemm_flops / max(1, cls_n["gemm"]), "launches_per_step": cls_n["gemm"] / prof_steps,

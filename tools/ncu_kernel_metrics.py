@@ -6,7 +6,7 @@ import csv
 import json
 import sys
 
-TENSOR = ("gemm_ws_kernel", "gemm_tc_kernel", "sa_fused", "fp_fused_kernel", "fp1_fused_kernel", "fp1_tail_kernel")
+TENSOR = ("gemm_ws_kernel", "gemm_tc_kernel", "sa_fused", "fp_fused_kernel", "fp1_fused_kernel", "fp1_tail_kernel", "x0net_fused_kernel")
 
 
 def main(path, source):
