@@ -54,7 +54,8 @@ def main():
             continue
         name = demangle(fn)
         name = re.sub(r"^void ", "", name)
-        name = re.sub(r"\(.*\)$", "", name)
+        name = re.sub(r"\((int|bool|unsigned int)\)", "", name)   # template-argument casts
+        name = re.sub(r"\(.*\)$", "", name)                       # the parameter list
         print(name[:110] + "\t" + str(c["_total"]) + "\t" + "\t".join(str(c[k]) for k in MNEMS))
         tot.update(c)
     print("TOTAL\t" + str(tot["_total"]) + "\t" + "\t".join(str(tot[k]) for k in MNEMS))
