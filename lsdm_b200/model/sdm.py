@@ -210,6 +210,13 @@ class SceneDiffusionModel(nn.Module):
         its vocabulary file is not shipped here).  With it and a loaded text tower, ``y`` may be a list of strings."""
         self._tokenizer = fn
 
+    def set_tokenizer_vocab(self, path):
+        """Path of openai/CLIP's ``bpe_simple_vocab_16e6.txt.gz``: strings are then tokenised by ``lsdm_b200.model.clip_tokenizer``
+        (the same BPE as ``clip.tokenize``).  Also picked up from the ``LSDM_CLIP_BPE`` environment variable."""
+        from .clip_tokenizer import ClipBpeTokenizer
+
+        self._tokenizer = ClipBpeTokenizer(path)
+
     def set_text_encoder(self, fn):
         """``fn(list[str]) -> [B,512]`` float tensor: an external replacement for the whole CLIP text path."""
         self._text_encoder = fn
@@ -235,8 +242,13 @@ class SceneDiffusionModel(nn.Module):
         if self._text_encoder is not None:
             return self._text_encoder(list(y)).float()
         tok = getattr(self, "_tokenizer", None)
+        if tok is None and tower is not None:
+            import os
+            if os.environ.get("LSDM_CLIP_BPE"):
+                self.set_tokenizer_vocab(os.environ["LSDM_CLIP_BPE"])
+                tok = self._tokenizer
         if tower is None or tok is None:
-            raise NotImplementedError("text strings need clip.tokenize (host-side BPE, vocabulary not shipped: set_tokenizer()) and the "
+            raise NotImplementedError("text strings need the CLIP BPE vocabulary (set_tokenizer_vocab(path) / LSDM_CLIP_BPE, or set_tokenizer(clip.tokenize)) and the "
                                       "CLIP text tower weights (load_clip_state_dict()); or pass the [B,512] embedding / [B,77] token ids "
                                       "as `y`, or install an external encoder with set_text_encoder()")
         # model/sdm.py:248-256: tokenise to 20 + 2 positions, zero-pad to the 77-token context

@@ -166,3 +166,29 @@ def test_model_accepts_reference_checkpoint_with_clip_and_token_ids():
     e1 = model._encode_text(["a chair", "chair"])
     e2 = model.clip_text.encode_text(torch.cat([tokenize(["a chair", "chair"], 22), torch.zeros(2, 55, dtype=torch.int64)], 1))
     assert torch.equal(e1, e2)
+
+
+@pytest.mark.gpu
+def test_strings_run_natively_through_the_bpe_tokenizer_and_the_device_tower():
+    """y: tuple of strings as run/test_sdm.py passes it -> lsdm_b200's own BPE tokeniser (restatement of clip.tokenize, here with a
+    toy merge table: the clip vocabulary file is not available offline) -> device CLIP tower -> the [B,512] embedding the oracle
+    tower computes from the same token ids."""
+    from lsdm_b200.model.clip_tokenizer import ClipBpeTokenizer
+    from lsdm_b200.model.sdm import SceneDiffusionModel
+    from lsdm_b200.util.model_util import get_default_model_proxd
+
+    merges = [("c", "h"), ("ch", "a"), ("i", "r</w>"), ("cha", "ir</w>"), ("t", "h"), ("th", "e</w>"), ("s", "o"), ("f", "a</w>")]
+    tok = ClipBpeTokenizer(merges=merges)
+    vocab = tok.eot + 1
+    clip_sd = syn.make_clip_state_dict(5, vocab=vocab, prefix="clip_model.")
+    model = SceneDiffusionModel(**get_default_model_proxd())
+    model.load_state_dict({**syn.make_state_dict(0, "wellcond"), **clip_sd})
+    model.eval()
+    model._tokenizer = tok
+    texts = ("the chair", "a sofa next to the chair, facing the tv")
+    ids = tok.tokenize(list(texts), context_length=22, truncate=True)
+    assert ids[0, 0] == tok.sot and (ids == tok.eot).sum(1).tolist() == [1, 1]
+    e = model._encode_text(texts)
+    with torch.no_grad():
+        ref = CO.encode_text({k[len("clip_model."):]: v for k, v in clip_sd.items()}, torch.cat([ids, torch.zeros(2, 55, dtype=torch.long)], 1))
+    assert rel_l2(e.cpu(), ref) < 1e-4

@@ -199,3 +199,65 @@ def test_fps_kernel_has_no_contracted_fma():
     assert fps, "fps4_kernel not found in the library"
     for b in fps:
         assert not re.search(r"\bFFMA2?\b", b), "FPS kernel contains a fused multiply-add (contracted mul+add)"
+
+
+def test_clip_bpe_tokenizer_matches_transformers_on_a_synthetic_vocabulary(tmp_path):
+    """lsdm_b200.model.clip_tokenizer (restatement of clip.tokenize; the clip package and its vocabulary file are absent) against
+    transformers.CLIPTokenizer -- an independent implementation of the same BPE -- on a merge table learned from a toy corpus,
+    written in the clip package's file format."""
+    import collections
+    import gzip
+
+    import torch
+    from transformers import CLIPTokenizer
+
+    from lsdm_b200.model.clip_tokenizer import ClipBpeTokenizer, _byte_alphabet
+
+    corpus = ("a person sits on the chair next to the table . the sofa is in front of the television , a lamp stands behind the bed "
+              "place a small wooden cabinet near the window and the door ; it's the person's desk , they've moved it 3 times in 2021 !").split()
+    _, alphabet = _byte_alphabet()
+    words = collections.Counter(tuple(list(w[:-1]) + [w[-1] + "</w>"]) for w in corpus)
+    merges = []
+    for _ in range(120):   # plain BPE training: most frequent pair first
+        pairs = collections.Counter()
+        for w, c in words.items():
+            for p in zip(w, w[1:]):
+                pairs[p] += c
+        if not pairs:
+            break
+        best = max(sorted(pairs), key=lambda p: pairs[p])
+        merges.append(best)
+        new = collections.Counter()
+        for w, c in words.items():
+            out, i = [], 0
+            while i < len(w):
+                if i + 1 < len(w) and (w[i], w[i + 1]) == best:
+                    out.append(w[i] + w[i + 1]); i += 2
+                else:
+                    out.append(w[i]); i += 1
+            new[tuple(out)] += c
+        words = new
+    path = tmp_path / "bpe_toy.txt.gz"
+    with gzip.open(path, "wb") as f:
+        f.write(("#version: toy\n" + "\n".join(a + " " + b for a, b in merges) + "\n").encode("utf-8"))
+    mine = ClipBpeTokenizer(str(path))
+    symbols = alphabet + [s + "</w>" for s in alphabet] + [a + b for a, b in merges] + ["<|startoftext|>", "<|endoftext|>"]
+    assert len(set(symbols)) == len(symbols) and mine.sot == len(symbols) - 2 and mine.eot == len(symbols) - 1
+    ref = CLIPTokenizer(vocab={s: i for i, s in enumerate(symbols)}, merges=[(a, b) for a, b in merges])
+    texts = ["A person sits on the chair next to the table.", "it's the person's desk, they've moved it 3 times in 2021!",
+             "  place   a small wooden cabinet\tnear the window  ", "café naïve über 12ab", "the sofa&amp;the bed", "zzz qqq ???", ""]
+    import html
+    for t in texts:   # (clip's text cleaning un-escapes HTML entities twice; transformers' tokenizer does not: done here for it)
+        assert mine.encode(t) == ref(html.unescape(html.unescape(t)), add_special_tokens=False)["input_ids"], t
+    out = mine.tokenize(texts, context_length=22, truncate=True)
+    assert out.shape == (len(texts), 22) and out.dtype == torch.long
+    for row, t in zip(out, texts):
+        ids = [mine.sot] + mine.encode(t) + [mine.eot]
+        if len(ids) > 22:
+            ids = ids[:22]
+            ids[-1] = mine.eot
+        assert row[:len(ids)].tolist() == ids and (row[len(ids):] == 0).all()
+    with pytest.raises(RuntimeError):
+        mine.tokenize(["the chair " * 40], context_length=22, truncate=False)
+    with pytest.raises(FileNotFoundError):
+        ClipBpeTokenizer(str(tmp_path / "missing.gz"))
