@@ -42,6 +42,13 @@ int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float*
                        const float* h_wf, const float* h_b1, const float* h_b2, const float* d_wx, const float* d_b1, const float* W2,
                        const float* W3, const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
 
+// sa1 on the DISTINCT rows of every group only (the ball query pads with the first hit; the max-pool ignores duplicates):
+// plan (selection stream) + the fused kernel on the packed tiles.  Bit-identical to launch_sa_fused_v2(level 0).
+int launch_sa1_plan(const int* grp, int n_clouds, int* rows, int* tile_used, int* tiles, int* tile_off, int* n_tiles, cudaStream_t st);
+int launch_sa1_compact(const float* xyz, const float* new_xyz, const int* rows, const int* tile_used, const int* tile_off, const int* n_tiles,
+                       const float* h_wx, const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
+                       int n_clouds, float* out, int round_out, cudaStream_t st);
+
 // fused feature-propagation level (fp2): first conv (fine half on the tensor core + interpolated coarse projection) + second conv
 int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, const float* Pb, const int* nn_idx, const float* nn_w,
                     const float* W1, const float* b1, int n_clouds, int N, int S, int C1, int C2, float* out, int round_out,

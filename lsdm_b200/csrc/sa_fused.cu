@@ -561,6 +561,281 @@ int launch_v2(const SaArgs& a, const float* h_wx, const float* h_wf, const float
   return 1;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// sa1 on DISTINCT rows only.  The ball query pads a group with its first hit (reference pointnet2_utils.py:100-103), and at
+// r = 0.1 most of a group's 32 slots are padding (about 5 distinct neighbours in the benchmark's clouds).  Duplicate rows give
+// duplicate activations, and the 32-sample max-pool ignores duplicates -- so only the distinct rows need to go through the two
+// dense layers.  sa1_plan_kernel packs the distinct (centroid, neighbour) rows of a cloud into 128-row tiles without splitting a
+// centroid over two tiles; sa1_compact_kernel is the v2 kernel on those tiles: each row computes its own centroid term of
+// layer 1 (same FMA chains as the per-warp form, so every activation is bit-identical), and the last epilogue takes a
+// SEGMENTED max over the tile's columns (thread = channel, segments = centroids).  6x fewer tiles on the benchmark's clouds;
+// a cloud whose balls are all full simply yields 256 tiles of 4 centroids, the uncompacted layout.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SA1_S = 1024, SA1_MAXT = 256;  // centroids per cloud, worst-case tiles per cloud
+
+__global__ void __launch_bounds__(1024) sa1_plan_kernel(const int* __restrict__ grp, int* __restrict__ rows, int* __restrict__ tile_used,
+                                                        int* __restrict__ tiles) {
+  __shared__ int s_cnt[SA1_S], s_slot[SA1_S];
+  const int c = blockIdx.x, s = threadIdx.x;
+  const int* row = grp + ((int64_t)c * SA1_S + s) * 32;
+  int idx[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int4 v = reinterpret_cast<const int4*>(row)[q];
+    idx[4 * q] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
+  }
+  int cnt = 1;  // hits come first, in ascending (distinct) index order; the padding repeats the first hit
+#pragma unroll
+  for (int k = 1; k < 32; ++k) cnt += idx[k] != idx[0] ? 1 : 0;
+  s_cnt[s] = cnt;
+  __syncthreads();
+  if (s == 0) {
+    int tile = 0, pos = 0;
+    for (int i = 0; i < SA1_S; ++i) {
+      const int n = s_cnt[i];
+      if (pos + n > 128) {
+        tile_used[c * SA1_MAXT + tile] = pos;
+        ++tile;
+        pos = 0;
+      }
+      s_slot[i] = tile * 128 + pos;
+      pos += n;
+    }
+    tile_used[c * SA1_MAXT + tile] = pos;
+    tiles[c] = tile + 1;
+  }
+  __syncthreads();
+  int* dst = rows + (int64_t)c * (SA1_MAXT * 128) + s_slot[s];
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < cnt) dst[k] = idx[k] | (s << 10);
+}
+
+// tile_off[c] = exclusive prefix sum of tiles[0..C), tile_off[C] = *n_tiles = the total
+__global__ void __launch_bounds__(1024) sa1_scan_kernel(const int* __restrict__ tiles, int C, int* __restrict__ tile_off, int* __restrict__ n_tiles) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x, per = (C + 1023) / 1024;
+  const int lo = tid * per, hi = min(C, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += tiles[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - sum;
+  for (int i = lo; i < hi; ++i) {
+    tile_off[i] = run;
+    run += tiles[i];
+  }
+  if (tid == 1023) {
+    tile_off[C] = s_part[1023];
+    *n_tiles = s_part[1023];
+  }
+}
+
+struct Sa1Plan {
+  const int *rows, *tile_used, *tile_off, *n_tiles;
+  int n_clouds;
+};
+
+__global__ void __launch_bounds__(128, 4) sa1_compact_kernel(SaArgs a, Sa1Plan p, const __grid_constant__ SaConst<32, 32, 64, true> k) {
+  constexpr int C1 = 32, C2 = 32, C3 = 64;
+  constexpr int W2_BYTES = C2 * C1 * 4, W3_BYTES = 128 * C2 * 4;
+  constexpr uint32_t COL_H1 = 0, COL_D2 = C1, COL_D3T = 0, TCOLS = 128;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_b3[128];
+  __shared__ int s_seg[2][128];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW2 = base, sW3 = sW2 + W2_BYTES, sH2 = sW3 + W3_BYTES;
+  const uint32_t bar = smem_u32(&s_bar);
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), TCOLS);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (int q = tid; q < C2 * C1 / 4; q += 128) {
+    int n = q / (C1 / 4), k4 = q % (C1 / 4);
+    float4 v = *reinterpret_cast<const float4*>(a.W2 + (int64_t)n * C1 + k4 * 4);
+    st_shared_v4(sW2 + (k4 >> 3) * (C2 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  for (int q = tid; q < 128 * C2 / 4; q += 128) {
+    int n = q / (C2 / 4), k4 = q % (C2 / 4);
+    float4 v = n < C3 ? *reinterpret_cast<const float4*>(a.W3 + (int64_t)n * C2 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    st_shared_v4(sW3 + (k4 >> 3) * (128 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
+  }
+  s_b3[tid] = tid < C3 ? a.b3[tid] : 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr uint32_t idesc2 = umma_idesc_tf32(128, C2), idesc3 = umma_idesc_tf32(128, 128);
+  const float bias3 = s_b3[tid];
+
+  const int n_tiles = *p.n_tiles;
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = (t0 + per < n_tiles) ? t0 + per : n_tiles;
+  int c = 0;
+  if (t0 < t1) {  // cloud of the first tile: the last c with tile_off[c] <= t0
+    int lo = 0, hi = p.n_clouds;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.tile_off[mid] <= t0) lo = mid;
+      else hi = mid;
+    }
+    c = lo;
+  }
+  uint32_t phase = 0;
+  for (int tile = t0; tile < t1; ++tile) {
+    while (tile >= p.tile_off[c + 1]) ++c;
+    const int tl = tile - p.tile_off[c];
+    const int used = p.tile_used[c * SA1_MAXT + tl];
+    const int par = (tile - t0) & 1;
+    int seg = -1;
+    float jx = 0.f, jy = 0.f, jz = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+    if (tid < used) {
+      const int v = p.rows[((int64_t)c * SA1_MAXT + tl) * 128 + tid];
+      seg = v >> 10;
+      const float* pj = a.xyz + ((int64_t)c * SA1_S + (v & 1023)) * 3;
+      const float* pc = a.new_xyz + ((int64_t)c * SA1_S + seg) * 3;
+      jx = pj[0]; jy = pj[1]; jz = pj[2];
+      cx = pc[0]; cy = pc[1]; cz = pc[2];
+    }
+    s_seg[par][tid] = seg;
+    // ---- layer 1, thread = row: (b1 - Wx.c) + (Wx + Wf).p_j with the FMA chains of the per-warp form ----
+    {
+      uint32_t v[32];
+#pragma unroll
+      for (int ch = 0; ch < 32; ++ch) {
+        float x = fmaf(-k.wx[ch * 3 + 0], cx, fmaf(-k.wx[ch * 3 + 1], cy, fmaf(-k.wx[ch * 3 + 2], cz, k.b1[ch])));
+        x = fmaf(k.wf[ch * 3 + 0], jx, x);
+        x = fmaf(k.wf[ch * 3 + 1], jy, x);
+        x = fmaf(k.wf[ch * 3 + 2], jz, x);
+        v[ch] = rna_tf32_mma(fmaxf(x, 0.0f));
+      }
+      tmem_st32(tlane + COL_H1, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t db = umma_desc_sw128(sW2);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_tf32_ts(tmem + COL_D2, tmem + COL_H1 + kk * 8, db + (uint64_t)(kk * 2), idesc2, kk != 0 ? 1u : 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t v[32];
+      tmem_ld32(tlane + COL_D2, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 o;
+        o.x = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 0]) + k.b2[q * 4 + 0], 0.0f)));
+        o.y = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 1]) + k.b2[q * 4 + 1], 0.0f)));
+        o.z = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 2]) + k.b2[q * 4 + 2], 0.0f)));
+        o.w = __uint_as_float(rna_tf32_mma(fmaxf(__uint_as_float(v[q * 4 + 3]) + k.b2[q * 4 + 3], 0.0f)));
+        st_shared_v4(sH2 + sw128_off(tid, q), o);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t da = umma_desc_sw128(sW3), db = umma_desc_sw128(sH2);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_tf32_ss(tmem + COL_D3T, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc3, kk != 0 ? 1u : 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 3: thread = channel; segmented max over the tile's columns (segments = centroids, complete within the tile) ----
+    if (tid < C3) {
+      float* outc = a.out + (int64_t)c * SA1_S * C3 + tid;
+      int cur = -1;
+      float m = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        if (g * 32 >= used) break;
+        uint32_t v[32];
+        tmem_ld32(tlane + COL_D3T + g * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int sg = s_seg[par][g * 32 + e];
+          const float val = __uint_as_float(v[e]);
+          if (sg != cur) {
+            if (cur >= 0) {
+              const float r = fmaxf(m + bias3, 0.0f);
+              outc[(int64_t)cur * C3] = a.round_out ? rna_tf32_fin(r) : r;
+            }
+            cur = sg;
+            m = val;
+          } else {
+            m = fmaxf(m, val);
+          }
+        }
+      }
+      if (cur >= 0) {
+        const float r = fmaxf(m + bias3, 0.0f);
+        outc[(int64_t)cur * C3] = a.round_out ? rna_tf32_fin(r) : r;
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+}  // namespace
+
+// plan of the distinct rows of sa1 (selection stream, after the level-0 ball query); rows [C, 256*128], tile_used [C, 256],
+// tiles [C], tile_off [C + 1], n_tiles [1]
+int launch_sa1_plan(const int* grp, int n_clouds, int* rows, int* tile_used, int* tiles, int* tile_off, int* n_tiles, cudaStream_t st) {
+  sa1_plan_kernel<<<n_clouds, 1024, 0, st>>>(grp, rows, tile_used, tiles);
+  sa1_scan_kernel<<<1, 1024, 0, st>>>(tiles, n_clouds, tile_off, n_tiles);
+  return 2;
+}
+
+int launch_sa1_compact(const float* xyz, const float* new_xyz, const int* rows, const int* tile_used, const int* tile_off, const int* n_tiles,
+                       const float* h_wx, const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
+                       int n_clouds, float* out, int round_out, cudaStream_t st) {
+  SaConst<32, 32, 64, true> k;
+  for (int i = 0; i < 96; ++i) {
+    k.wx[i] = h_wx[i];
+    k.wf[i] = h_wx[i] + h_wf[i];
+  }
+  for (int i = 0; i < 32; ++i) {
+    k.b1[i] = h_b1[i];
+    k.b2[i] = h_b2[i];
+  }
+  SaArgs a{nullptr, xyz, new_xyz, nullptr, nullptr, nullptr, nullptr, W2, nullptr, W3, b3, out, 0, 1024, 1024, round_out, 10};
+  Sa1Plan p{rows, tile_used, tile_off, n_tiles, n_clouds};
+  constexpr int need = 32 * 32 * 4 + 2 * 128 * 32 * 4 + 1024;
+  constexpr int floor_smem = (227 * 1024) / 5 + 1;  // at most 4 CTAs per SM (4 x 128 TMEM columns)
+  constexpr int smem = need > floor_smem ? need : floor_smem;
+  static PerDeviceOnce attr_done;
+  if (smem_opt_in(attr_done, sa1_compact_kernel, smem) != cudaSuccess) return -1;
+  sa1_compact_kernel<<<device_sm_count() * 4, 128, smem, st>>>(a, p, k);
+  return 1;
+}
+
+namespace {
 }  // namespace
 
 // level: 0 (sa1: 6->32->32->64) or 1 (sa2: 67->64->64->128).  a_tmem selects the A-from-TMEM variant.

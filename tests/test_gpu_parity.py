@@ -609,3 +609,34 @@ def test_x0net_fused_kernel_matches_layer_chain(B):
     assert rel_l2(x0.cpu(), ref["pred_xstart"]) < TOL_E2E
     assert rel_l2(gd_.cpu(), ref["guiding"]) < TOL_E2E
     assert rel_l2(xm.cpu(), xo) < TOL_E2E
+
+
+def test_sa1_distinct_row_compaction_is_bit_identical():
+    """sa1 on the distinct rows of every ball-query group only (the padding repeats the first hit and the max-pool ignores
+    duplicates; `sa1_compact`): level-1 features, backbone output and x0 must be BIT-identical to the kernel that runs all 32
+    slots -- on sparse clouds (few neighbours), dense clouds (every ball full: no compaction possible), absent clouds and a
+    cloud with a single far-away point."""
+    B = 3
+    m, _ = _model("wellcond")
+    inp = syn.make_inputs(51, B)
+    objs = inp["given_objs"].clone()
+    objs[0, 1] = (torch.rand(1024, 3) - 0.5) * 0.05        # dense: every r = 0.1 ball holds all 1024 points
+    objs[0, 2] = (torch.rand(1024, 3) - 0.5) * 4.0         # very sparse: most balls hold only their centroid
+    objs[1, 3] = 0.0
+    objs[1, 3, 7] = torch.tensor([3.0, 3.0, 3.0])          # 1023 coincident points + one outlier
+    inp["given_objs"] = objs
+    fps, _ = syn.make_step_randoms(52, B, 1)
+    g = _cuda(inp)
+    out = {}
+    for flag in (1, 0):
+        eng = m.engine(B, torch.device("cuda", 0))
+        eng.set_option("sa1_compact", flag)
+        try:
+            x = g["x_T"].clone()
+            with injected_rng(fps_starts=list(fps[0])):
+                _, x0 = m(x, g["mask"], torch.full((B,), 123, device="cuda"), g["given_objs"], g["given_cats"], g["text_emb"])
+            out[flag] = (m._engine.debug_tensor("l1_feat").clone(), m._engine.debug_tensor("backbone").clone(), x0.clone())
+        finally:
+            eng.set_option("sa1_compact", 1)
+    for a, b in zip(out[1], out[0]):
+        assert torch.equal(a, b)
