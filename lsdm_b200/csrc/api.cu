@@ -88,6 +88,7 @@ struct Workspace {
   float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out[3];  // pcd_out: one per selection set (the step of k reads it while dense(k+1), dense(k+2) write the others)
   // step
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
+  float *ctext, *a_t;  // hoisted loop: loop-invariant text half [rows,128] and batch-shared time half [1024,128] of the embedding pre-activation
   float *H1_lo, *H2_lo, *embpre_lo, *cat_lo, *h1_lo, *c1_lo, *c2_lo;  // 3xTF32 residual planes of the step network's activations
   size_t bytes;
 };
@@ -116,6 +117,7 @@ struct lsdm_handle {
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
   int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
   int fp_fused = 0;              // 1: fused fp2 level (fine GEMM + interpolation + second conv in one kernel)
+  int hoist_split = 1;           // 1: the hoisted loop computes the time half of the embedding once per step for the whole batch and the text half once per loop
   int sa1_compact = 1;           // 1: sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles)
   int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
   int dedup_absent = 1;          // 1: lsdm_sample_loop encodes ONE all-zero (absent, zero-padded) cloud per step and shares its
@@ -316,6 +318,8 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   w->c2 = a.take<float>(2 * rows * 128);
   w->c2_lo = a.take<float>(2 * rows * 128);
   w->f1 = a.take<float>(2 * rows * 64);
+  w->ctext = a.take<float>(rows * 128);
+  w->a_t = a.take<float>((size_t)NPTS * 128);
   w->x0 = a.take<float>(rows * 3);
   w->guiding = a.take<float>(rows * 3);
   w->loss_scratch = a.take<float>(64);
@@ -549,9 +553,27 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
   return LSDM_OK;
 }
 
+// emb[row, :] = gelu(A_t[row % 1024, :] + C_text[row, :]) as hi / lo TF32 planes with leading dimension 256 (thread = 4 channels)
+__global__ void emb_combine_kernel(const float* __restrict__ a_t, const float* __restrict__ ctext, int64_t rows, float* __restrict__ hi,
+                                   float* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 32) return;
+  const int64_t row = i >> 5;
+  const int q = (int)(i & 31);
+  const float4 a = *reinterpret_cast<const float4*>(a_t + (row & (NPTS - 1)) * 128 + q * 4);
+  const float4 c = *reinterpret_cast<const float4*>(ctext + row * 128 + q * 4);
+  float v[4] = {gelu_erf(a.x + c.x), gelu_erf(a.y + c.y), gelu_erf(a.z + c.z), gelu_erf(a.w + c.w)}, l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_tf32(v[j], v[j], l[j]);
+  *reinterpret_cast<float4*>(hi + row * 256 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(lo + row * 256 + q * 4) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
 // x/t-dependent part: timestep embedding, upsampler, x += pcd_out, Input/OutputProcess, optional posterior.
 int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,
-              float* guiding_out, bool want_guiding, int clip, cudaStream_t st, int si = -1) {
+              float* guiding_out, bool want_guiding, int clip, cudaStream_t st, int si = -1, int hoist_split = 0) {
+  // hoist_split (hoisted sampling loop only, every sample shares t): 1 = first step (also builds the loop-invariant text half of
+  // the embedding), 2 = later steps
   Workspace& w = h->ws;
   if (si < 0) si = w.cur;
   const int B = h->cfg.batch_local;
@@ -561,33 +583,52 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   // GEMMs stage all four operand planes with cp.async (no per-tile splitting in registers)
   const bool sp = h->precision_step == 2 && g_gemm_async != 0;
   const int ps = h->precision_step;
-  prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
-                                   h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
-                                   h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.sel[si].enc, h->W("upsampling_layer.0.weight"),
-                                   h->W("upsampling_layer.0.bias"), B, w.s256, w.H1, sp ? w.H1_lo : nullptr, st); });
-  GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), B * 256, 512,
-          128, ACT_GELU, 0, ps, 0, sp ? w.H1_lo : nullptr, sp ? w.H2_lo : nullptr));
-  {
-    // embpre[b][p][s] = gelu(sum_k U4[p][k] H2[b][s][k] + b4[p]): the upsampler's last layer written point-major
-    GemmArgs g{};
-    g.A = h->W("upsampling_layer.4.weight"); g.lda = 512; g.strideA = 0;
-    g.W = w.H2; g.ldw = 512; g.strideW = 256 * 512;
-    g.C = w.embpre; g.ldc = 256; g.strideC = (int64_t)NPTS * 256;
-    g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
-    g.M = NPTS; g.N = 256; g.K = 512; g.batch = B; g.act = ACT_GELU; g.group_max = 0; g.precision = ps;
-    if (sp) {
-      g.A_lo = g.A + h->lo_delta;
-      g.A = g.A + h->round_delta;
-      g.W_lo = w.H2_lo;
-      g.C_lo = w.embpre_lo;
+  // ---- the step's embedding emb[b,p,:] = gelu(Wc . [u_ts(p) || u_text(b,p)] + bc)  (model/sdm.py:164-167,208) ----
+  // `nb` samples, scalars [s0, s0 + ns) of [ts || enc], combine columns [s0, s0 + ns): the full chain is (B, 0, 256); the
+  // hoisted loop splits it into a batch-shared time half (1, 0, 128) and a loop-invariant text half (B, 128, 128).
+  auto upsample = [&](int nb, int s0, int ns, const float* combine_bias, int combine_act, float* out, int64_t ld_out, float* out_lo) -> int {
+    prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
+                                     h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
+                                     h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.sel[si].enc, h->W("upsampling_layer.0.weight"),
+                                     h->W("upsampling_layer.0.bias"), nb, w.s256, w.H1, sp ? w.H1_lo : nullptr, st); });
+    GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), nb * 256, 512,
+            128, ACT_GELU, 0, ps, 0, sp ? w.H1_lo : nullptr, sp ? w.H2_lo : nullptr));
+    {
+      // embpre[b][p][s] = gelu(sum_k U4[p][k] H2[b][s0 + s][k] + b4[p]): the upsampler's last layer written point-major
+      GemmArgs g{};
+      g.A = h->W("upsampling_layer.4.weight"); g.lda = 512; g.strideA = 0;
+      g.W = w.H2 + (size_t)s0 * 512; g.ldw = 512; g.strideW = 256 * 512;
+      g.C = w.embpre; g.ldc = ns; g.strideC = (int64_t)NPTS * ns;
+      g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
+      g.M = NPTS; g.N = ns; g.K = 512; g.batch = nb; g.act = ACT_GELU; g.group_max = 0; g.precision = ps;
+      if (sp) {
+        g.A_lo = g.A + h->lo_delta;
+        g.A = g.A + h->round_delta;
+        g.W_lo = w.H2_lo + (size_t)s0 * 512;
+        g.C_lo = w.embpre_lo;
+      }
+      int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); }, "gemm p2 upsampler K512 batched",
+                          2.0 * g.M * (double)g.N * g.K * g.batch);
+      if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
+      if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
     }
-    int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); }, "gemm p2 upsampler N256 K512 batched",
-                        2.0 * g.M * (double)g.N * g.K * g.batch);
-    if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
-    if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
+    GE(gemm(h, st, w.embpre, ns, h->W("combine_extraction.0.weight") + s0, 256, out, ld_out, combine_bias, nb * NPTS, 128, ns, combine_act, 0, ps, 0,
+            sp ? w.embpre_lo : nullptr, out_lo));
+    return LSDM_OK;
+  };
+  if (hoist_split && sp) {
+    if (hoist_split == 1)   // once per loop: C_text[b,p,:] = Wc[:, 128:] . u_text(b,p) + bc
+      GE(upsample(B, 128, 128, h->W("combine_extraction.0.bias"), ACT_NONE, w.ctext, 128, nullptr));
+    // every step: A_t[p,:] = Wc[:, :128] . u_ts(p) for the ONE timestep all samples of the loop share, then emb = gelu(A_t + C_text)
+    GE(upsample(1, 0, 128, nullptr, ACT_NONE, w.a_t, 128, nullptr));
+    prof_launch(h, st, K_DENOISE, [&] {
+      const int64_t n = (int64_t)rows * 32;
+      emb_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.a_t, w.ctext, rows, w.cat + 128, w.cat_lo + 128);
+      return 1;
+    });
+  } else {
+    GE(upsample(B, 0, 256, h->W("combine_extraction.0.bias"), ACT_GELU, w.cat + 128, 256, sp ? w.cat_lo + 128 : nullptr));
   }
-  GE(gemm(h, st, w.embpre, 256, h->W("combine_extraction.0.weight"), 256, w.cat + 128, 256,
-          h->W("combine_extraction.0.bias"), rows, 128, 256, ACT_GELU, 0, ps, 0, sp ? w.embpre_lo : nullptr, sp ? w.cat_lo + 128 : nullptr));
   if (sp && h->x0_fused && (rows & 127) == 0) {
     // the whole x0 network (both passes), `x += pcd_out`, the posterior and the ancestral noise in one persistent kernel
     auto hi = [&](const char* k) { return h->W(k) + h->round_delta; };
@@ -1228,8 +1269,9 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     // STRICT recomputes the guiding points every step like the reference; hoisted only needs them at the end
     const bool want_guiding = !hoisted || last;
     tl_begin(k, 'X', st);
+    const int hs = (hoisted && h->hoist_split && h->x0_fused) ? (k == 0 ? 1 : 2) : 0;
     GE(step_core(h, x, tvec, noise_all + (size_t)k * per, x, last ? x0_out : nullptr, last ? guiding_out : nullptr,
-                 want_guiding, clip_denoised, st, si));
+                 want_guiding, clip_denoised, st, si, hs));
     tl_end(st);
     if (pipelined) CK(cudaEventRecord(h->ev_step[si], st));
   }
@@ -1441,6 +1483,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   }
   if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 3) {
     h->sa_fused = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "hoist_split") == 0 && (value == 0 || value == 1)) {
+    h->hoist_split = value;
     return LSDM_OK;
   }
   if (strcmp(name, "sa1_compact") == 0 && (value == 0 || value == 1)) {

@@ -640,3 +640,25 @@ def test_sa1_distinct_row_compaction_is_bit_identical():
             eng.set_option("sa1_compact", 1)
     for a, b in zip(out[1], out[0]):
         assert torch.equal(a, b)
+
+
+def test_hoisted_loop_embedding_split_matches_full_chain():
+    """Hoisted loop: the embedding's time half computed once per step for the whole batch (every sample shares t) and its text half
+    once per loop ("hoist_split") against the full per-sample chain: same sums, split after 128 of 256 terms -> 1e-5."""
+    B, K = 3, 5
+    m, diff = _model("wellcond")
+    inp = _cuda(syn.make_inputs(71, B))
+    fps, noise = syn.make_step_randoms(72, B, K)
+    eng = diff._engine(m, B, torch.device("cuda", 0))
+    outs = []
+    for flag in (1, 0):
+        eng.set_option("hoist_split", flag)
+        try:
+            x = inp["x_T"].clone()
+            x0, gd_ = eng.sample_loop(x, inp["text_emb"], inp["given_objs"], inp["given_cats"], inp["mask"], fps.cuda()[:1], noise.cuda(), 420, True)
+            torch.cuda.synchronize()
+            outs.append((x.clone(), x0.clone(), gd_.clone()))
+        finally:
+            eng.set_option("hoist_split", 1)
+    for a, b in zip(*outs):
+        assert rel_l2(a.cpu(), b.cpu()) < 1e-5
