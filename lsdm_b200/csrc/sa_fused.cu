@@ -576,7 +576,8 @@ constexpr int SA1_S = 1024, SA1_MAXT = 256;  // centroids per cloud, worst-case 
 __global__ void __launch_bounds__(1024) sa1_plan_kernel(const int* __restrict__ grp, int* __restrict__ rows, int* __restrict__ tile_used,
                                                         int* __restrict__ tiles) {
   // eight groups of 128 centroids are packed independently (one thread each walks its 128 counts), so the serial part is 128
-  // steps instead of 1024; a group's last tile may stay partly empty (about 8 % more tiles than packing the cloud as a whole)
+  // steps instead of 1024; a group's last tile may stay partly empty (about 8 % more tiles than packing the cloud as a whole).
+  // tile_used[c][t] = rows used in the low half | rows used in the high half << 8
   __shared__ int s_cnt[SA1_S], s_slot[SA1_S], s_gtiles[8], s_used[8][32];
   const int c = blockIdx.x, s = threadIdx.x;
   const int* row = grp + ((int64_t)c * SA1_S + s) * 32;
@@ -592,20 +593,22 @@ __global__ void __launch_bounds__(1024) sa1_plan_kernel(const int* __restrict__ 
   s_cnt[s] = cnt;
   __syncthreads();
   if ((s & 127) == 0) {
+    // rows are packed into 64-row HALF tiles (a centroid never straddles a half: each half of the CTA pools its own 64 columns)
     const int g = s >> 7;
-    int tile = 0, pos = 0;
+    int half = 0, pos = 0;
+    for (int i = 0; i < 32; ++i) s_used[g][i] = 0;
     for (int i = s; i < s + 128; ++i) {
       const int n = s_cnt[i];
-      if (pos + n > 128) {
-        s_used[g][tile] = pos;
-        ++tile;
+      if (pos + n > 64) {
+        s_used[g][half >> 1] |= pos << ((half & 1) * 8);
+        ++half;
         pos = 0;
       }
-      s_slot[i] = tile * 128 + pos;  // relative to the group's first tile
+      s_slot[i] = half * 64 + pos;  // relative to the group's first tile
       pos += n;
     }
-    s_used[g][tile] = pos;
-    s_gtiles[g] = tile + 1;
+    s_used[g][half >> 1] |= pos << ((half & 1) * 8);
+    s_gtiles[g] = (half >> 1) + 1;
   }
   __syncthreads();
   const int g = s >> 7;
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(1024) sa1_plan_kernel(const int* __restrict__ 
   int* dst = rows + (int64_t)c * (SA1_MAXT * 128) + t0 * 128 + s_slot[s];
 #pragma unroll
   for (int k = 0; k < 32; ++k)
-    if (k < cnt) dst[k] = idx[k] | (s << 10);
+    if (k < cnt) dst[k] = idx[k] | (s << 10) | (k == 0 ? 1 << 20 : 0);  // neighbour | centroid << 10 | first-row flag << 20
 }
 
 // tile_off[c] = exclusive prefix sum of tiles[0..C), tile_off[C] = *n_tiles = the total
@@ -668,6 +671,7 @@ __global__ void __launch_bounds__(128, 4) sa1_compact_kernel(SaArgs a, Sa1Plan p
   __shared__ uint32_t s_tmem;
   __shared__ float s_b3[128];
   __shared__ int s_seg[2][128];
+  __shared__ uint32_t s_mask[2][4];  // per warp: bit r set when row r starts a new centroid
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW2 = base, sW3 = sW2 + W2_BYTES, sH2 = sW3 + W3_BYTES;
@@ -682,12 +686,12 @@ __global__ void __launch_bounds__(128, 4) sa1_compact_kernel(SaArgs a, Sa1Plan p
     float4 v = *reinterpret_cast<const float4*>(a.W2 + (int64_t)n * C1 + k4 * 4);
     st_shared_v4(sW2 + (k4 >> 3) * (C2 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
   }
-  for (int q = tid; q < 128 * C2 / 4; q += 128) {
+  for (int q = tid; q < 128 * C2 / 4; q += 128) {  // W3 twice: TMEM lanes 64..127 carry the same 64 channels for the second half of the CTA
     int n = q / (C2 / 4), k4 = q % (C2 / 4);
-    float4 v = n < C3 ? *reinterpret_cast<const float4*>(a.W3 + (int64_t)n * C2 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = *reinterpret_cast<const float4*>(a.W3 + (int64_t)(n & (C3 - 1)) * C2 + k4 * 4);
     st_shared_v4(sW3 + (k4 >> 3) * (128 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
   }
-  s_b3[tid] = tid < C3 ? a.b3[tid] : 0.f;
+  s_b3[tid] = a.b3[tid & (C3 - 1)];
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -712,18 +716,20 @@ __global__ void __launch_bounds__(128, 4) sa1_compact_kernel(SaArgs a, Sa1Plan p
   }
   uint32_t phase = 0;
   // this thread's row of a tile: source point, centroid, segment id; the next tile's is in flight while the current one computes
-  struct Row { int c, used, seg; float jx, jy, jz, cx, cy, cz; };
+  struct Row { int c, used, seg, start; float jx, jy, jz, cx, cy, cz; };
   int cnext = c;
   auto load_row = [&](int tile) -> Row {
-    Row r{0, 0, -1, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    Row r{0, 0, -1, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (tile >= t1) return r;
     while (tile >= p.tile_off[cnext + 1]) ++cnext;
     r.c = cnext;
     const int tl = tile - p.tile_off[cnext];
-    r.used = p.tile_used[cnext * SA1_MAXT + tl];
-    if (tid < r.used) {
+    const int packed = p.tile_used[cnext * SA1_MAXT + tl];
+    r.used = (tid >> 6) ? (packed >> 8) : (packed & 255);   // rows used in this thread's half tile
+    if ((tid & 63) < r.used) {
       const int v = p.rows[((int64_t)cnext * SA1_MAXT + tl) * 128 + tid];
-      r.seg = v >> 10;
+      r.seg = (v >> 10) & 1023;
+      r.start = (v >> 20) & 1;
       const float* pj = a.xyz + ((int64_t)cnext * SA1_S + (v & 1023)) * 3;
       const float* pc = a.new_xyz + ((int64_t)cnext * SA1_S + r.seg) * 3;
       r.jx = pj[0]; r.jy = pj[1]; r.jz = pj[2];
@@ -741,6 +747,10 @@ __global__ void __launch_bounds__(128, 4) sa1_compact_kernel(SaArgs a, Sa1Plan p
     const int seg = cur.seg;
     const float jx = cur.jx, jy = cur.jy, jz = cur.jz, cx = cur.cx, cy = cur.cy, cz = cur.cz;
     s_seg[par][tid] = seg;
+    {
+      const uint32_t starts = __ballot_sync(0xffffffffu, cur.start != 0);
+      if ((tid & 31) == 0) s_mask[par][warp] = starts;
+    }
     // ---- layer 1, thread = row: (b1 - Wx.c) + (Wx + Wf).p_j with the FMA chains of the per-warp form ----
     {
       uint32_t v[32];
@@ -794,30 +804,35 @@ __global__ void __launch_bounds__(128, 4) sa1_compact_kernel(SaArgs a, Sa1Plan p
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue 3: thread = channel; segmented max over the tile's columns (segments = centroids, complete within the tile) ----
-    if (tid < C3) {
-      float* outc = a.out + (int64_t)c * SA1_S * C3 + tid;
+    // ---- epilogue 3: thread = (half, channel); segmented max over the 64 columns of its half tile (segments = centroids) ----
+    {
+      const int half = tid >> 6, ch = tid & (C3 - 1);
+      float* outc = a.out + (int64_t)c * SA1_S * C3 + ch;
       int cur = -1;
       float m = 0.f;
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
+        const int col0 = half * 64 + g * 32;
         if (g * 32 >= used) break;
         uint32_t v[32];
-        tmem_ld32(tlane + COL_D3T + g * 32, v);
+        tmem_ld32(tlane + COL_D3T + col0, v);
         tmem_ld_wait();
+        const uint32_t starts = s_mask[par][half * 2 + g];
+        const int n = used - g * 32 < 32 ? used - g * 32 : 32;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const int sg = s_seg[par][g * 32 + e];
-          const float val = __uint_as_float(v[e]);
-          if (sg != cur) {
-            if (cur >= 0) {
-              const float r = fmaxf(m + bias3, 0.0f);
-              outc[(int64_t)cur * C3] = a.round_out ? rna_tf32_fin(r) : r;
+          if (e < n) {
+            const float val = __uint_as_float(v[e]);
+            if ((starts >> e) & 1u) {
+              if (cur >= 0) {
+                const float r = fmaxf(m + bias3, 0.0f);
+                outc[(int64_t)cur * C3] = a.round_out ? rna_tf32_fin(r) : r;
+              }
+              cur = s_seg[par][col0 + e];
+              m = val;
+            } else {
+              m = fmaxf(m, val);
             }
-            cur = sg;
-            m = val;
-          } else {
-            m = fmaxf(m, val);
           }
         }
       }

@@ -343,8 +343,10 @@ class GaussianDiffusion:
         params = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
         if th.is_grad_enabled() and params:
             if not net.training:
-                raise NotImplementedError("backward through training_losses is implemented for model.train() (BatchNorm batch statistics, "
-                                          "as run/train_sdm.py trains); call it under torch.no_grad() for the eval-mode forward value")
+                # eval-mode forward value; a .backward() on it says what is missing instead of torch's opaque "does not require grad"
+                with th.no_grad():
+                    terms = self.training_losses(model, cf, mask, t, given_objs, given_cats, target_cat, y=y, noise=noise)
+                return {k: _NoEvalBackward.apply(v, params[0][1]) for k, v in terms.items()}
             mse, ce = _TrainingLossFn.apply(self, model, x_start, mask, t, given_objs, given_cats, target_cat, y, noise,
                                             [n for n, _ in params], *[p for _, p in params])
             cat_loss = ce * self.lambda_cat
@@ -364,6 +366,20 @@ class GaussianDiffusion:
 # attn_layer's value / output projections never reach the loss (only the attention WEIGHTS are used, model/sdm.py:182): the
 # reference leaves their .grad at None
 _DEAD_PARAMS = ("attn_layer.v_proj_weight", "attn_layer.out_proj.weight", "attn_layer.out_proj.bias")
+
+
+class _NoEvalBackward(th.autograd.Function):
+    """Carries an eval-mode loss value; its backward raises (the library's backward implements model.train(): BatchNorm batch
+    statistics, as run/train_sdm.py trains)."""
+
+    @staticmethod
+    def forward(ctx, value, _param):
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("backward through training_losses is implemented for model.train() (BatchNorm batch statistics, as "
+                                  "run/train_sdm.py trains), not for model.eval()")
 
 
 class _TrainingLossFn(th.autograd.Function):
