@@ -115,8 +115,24 @@ struct Lin {  // Y = X W^T + b with W[N, K] (row stride ldw); gW / gb: gradient 
   const float* W; const float* b; float* gW; float* gb; int N, K, ldw;
 };
 
+// The large forward and dgrad products go through the library's tcgen05 GEMM in 3xTF32 (hi / lo split of both operands inside the
+// kernel: fp32-grade accuracy); everything it cannot take (tiny or odd shapes, strided weight slices, wgrad) stays on the SGEMM.
+float* g_wt_scratch = nullptr;  // [1024 x 1024] transposed-weight scratch inside the tape (set per call)
+void transpose(cudaStream_t st, const float* in, float* out, int batch, int R, int Cn);
+
+bool tc_linear(cudaStream_t st, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, const float* bias, int M, int N, int K) {
+  if (M < 4096) return false;
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc;
+  g.bias = bias; g.bias_mode = bias ? 1 : 0;
+  g.M = M; g.N = N; g.K = K; g.batch = 1; g.act = ACT_NONE; g.precision = 2;
+  if (!gemm_tc_eligible(g)) return false;
+  return launch_gemm(g, st) > 0;
+}
+
 // Z[M,N] = X W^T + b
 void lin_fw(cudaStream_t st, const float* X, int64_t ldx, int M, const Lin& L, float* Z, int64_t ldz, bool accumulate = false) {
+  if (!accumulate && tc_linear(st, X, ldx, L.W, L.ldw, Z, ldz, L.b, M, L.N, L.K)) return;
   sgemm(st, X, ldx, 1, L.W, 1, L.ldw, Z, ldz, L.b, M, L.N, L.K, accumulate);
 }
 
@@ -147,7 +163,14 @@ void lin_bw(cudaStream_t st, const float* X, int64_t ldx, int M, const Lin& L, c
             bool accumulate_dx = false) {
   if (L.gW) sgemm(st, dZ, 1, ldz, X, ldx, 1, L.gW, L.ldw, nullptr, L.N, L.K, M, true, true);
   if (L.gb) colsum(st, dZ, ldz, M, L.N, L.gb);
-  if (dX) sgemm(st, dZ, ldz, 1, L.W, L.ldw, 1, dX, lddx, nullptr, M, L.K, L.N, accumulate_dx);
+  if (dX) {
+    // dX = dZ W == dZ (W^T)^T: a linear layer with the transposed weight
+    if (!accumulate_dx && g_wt_scratch && M >= 4096 && L.ldw == L.K && (int64_t)L.N * L.K <= 1024 * 1024 && (L.N % 32) == 0) {
+      transpose(st, L.W, g_wt_scratch, 1, L.N, L.K);
+      if (tc_linear(st, dZ, ldz, g_wt_scratch, L.N, dX, lddx, nullptr, M, L.K, L.N)) return;
+    }
+    sgemm(st, dZ, ldz, 1, L.W, L.ldw, 1, dX, lddx, nullptr, M, L.K, L.N, accumulate_dx);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -198,24 +221,35 @@ void act_bw(cudaStream_t st, float* d, int64_t ldd, const float* z, int64_t ldz,
 // ------------------------------------------------------------------------------------------------------------------
 // BatchNorm (train): statistics over all M rows (+ the other shards through the all-reduce hook), ReLU, optional mask
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void bn_fw_kernel(const float* __restrict__ y, int64_t M, int N, const double* __restrict__ sums, double Mstat,
-                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ stat,
-                             float* __restrict__ a, const float* __restrict__ mask, int mask_points) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
-  const int64_t r = i / N;
-  const int c = (int)(i % N);
+// stat[c] = batch mean, stat[N + c] = 1 / sqrt(biased variance + eps)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double Mstat, int N, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float* __restrict__ stat) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
   const double mean = sums[c] / Mstat;
   double var = sums[N + c] / Mstat - mean * mean;
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  if (r == 0) {
-    stat[c] = (float)mean;
-    stat[N + c] = rstd;
+  stat[c] = (float)mean;
+  stat[N + c] = rstd;
+}
+// a = [mask *] relu((y - mean) * rstd * gamma + beta), four channels per thread (N is a multiple of 4)
+__global__ void bn_fw_kernel(const float* __restrict__ y, int64_t M, int N, const float* __restrict__ stat, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float* __restrict__ a, const float* __restrict__ mask, int mask_points) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= M * N) return;
+  const int64_t r = (i4 * 4) / N;
+  const int c = (int)((i4 * 4) % N);
+  const float4 v = reinterpret_cast<const float4*>(y)[i4];
+  const float in[4] = {v.x, v.y, v.z, v.w};
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float t = fmaxf((in[j] - stat[c + j]) * stat[N + c + j] * gamma[c + j] + beta[c + j], 0.0f);
+    if (mask) t *= mask[((r / mask_points) * N + c + j) * mask_points + (r % mask_points)];
+    o[j] = t;
   }
-  float v = fmaxf((y[i] - (float)mean) * rstd * gamma[c] + beta[c], 0.0f);
-  if (mask) v *= mask[((r / mask_points) * N + c) * mask_points + (r % mask_points)];
-  a[i] = v;
+  reinterpret_cast<float4*>(a)[i4] = make_float4(o[0], o[1], o[2], o[3]);
 }
 // sums2[c] += sum_r dyh, sums2[N + c] += sum_r dyh * xhat, with dyh = dA * mask * [relu > 0]
 __global__ void __launch_bounds__(256) bn_bw_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ a,
@@ -241,22 +275,32 @@ __global__ void __launch_bounds__(256) bn_bw_reduce_kernel(const float* __restri
     atomicAdd(&sums2[N + col], q);
   }
 }
+// means[c] = sum dyh / M, means[N + c] = sum dyh * xhat / M (floats, from the double sums)
+__global__ void bn_bw_means_kernel(const double* __restrict__ sums2, double Mstat, int N, float* __restrict__ means) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < 2 * N) means[c] = (float)(sums2[c] / Mstat);
+}
 __global__ void bn_bw_apply_kernel(float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ a, int64_t M, int N,
-                                   const float* __restrict__ stat, const float* __restrict__ gamma, const double* __restrict__ sums2, double Mstat,
+                                   const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ means,
                                    const float* __restrict__ mask, int mask_points) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
-  const int64_t r = i / N;
-  const int c = (int)(i % N);
-  const float mean = stat[c], rstd = stat[N + c];
-  float d = 0.f;
-  if (a[i] > 0.f) {
-    d = dA[i];
-    if (mask) d *= mask[((r / mask_points) * N + c) * mask_points + (r % mask_points)];
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= M * N) return;
+  const int64_t r = (i4 * 4) / N;
+  const int c = (int)((i4 * 4) % N);
+  const float4 dv = reinterpret_cast<const float4*>(dA)[i4], yv = reinterpret_cast<const float4*>(y)[i4], av = reinterpret_cast<const float4*>(a)[i4];
+  const float din[4] = {dv.x, dv.y, dv.z, dv.w}, yin[4] = {yv.x, yv.y, yv.z, yv.w}, ain[4] = {av.x, av.y, av.z, av.w};
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float d = 0.f;
+    if (ain[j] > 0.f) {
+      d = din[j];
+      if (mask) d *= mask[((r / mask_points) * N + c + j) * mask_points + (r % mask_points)];
+    }
+    const float xh = (yin[j] - stat[c + j]) * stat[N + c + j];
+    o[j] = gamma[c + j] * stat[N + c + j] * (d - means[c + j] - xh * means[N + c + j]);
   }
-  const float xh = (y[i] - mean) * rstd;
-  const float sb = (float)(sums2[c] / Mstat), sg = (float)(sums2[N + c] / Mstat);
-  dA[i] = gamma[c] * rstd * (d - sb - xh * sg);
+  reinterpret_cast<float4*>(dA)[i4] = make_float4(o[0], o[1], o[2], o[3]);
 }
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums2, int N, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1014,12 +1058,15 @@ int train_forward_backward(const TrainCtx& ctx, const TrainIO& io, cudaStream_t 
         *d_te = t.f(B * 128);
   double* dsum = reinterpret_cast<double*>(t.f(4 * 1024));
   float* vals = t.f(64);
+  float* bnmeans = t.f(2 * 1024);
+  float* wt_scratch = t.f(1024 * 1024);
   if (dry) {
     *size_only = t.off + 256;
     return 0;
   }
   if (t.off + 256 > ctx.tape_bytes) return set_error(-1, "train tape too small: need " + std::to_string(t.off + 256));
 
+  g_wt_scratch = wt_scratch;
   const int64_t shards = ctx.allreduce ? ctx.Bg / ctx.B : 1;
   int hook_err = 0;
   auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
@@ -1029,7 +1076,8 @@ int train_forward_backward(const TrainCtx& ctx, const TrainIO& io, cudaStream_t 
   auto bn_fw = [&](const std::string& key, const float* Y, int64_t M, int N, float* stat, float* A, const float* mask) {
     launch_col_stats(Y, M, N, dsum, st);
     if (ctx.allreduce && ctx.allreduce(ctx.allreduce_ctx, dsum, 2 * N) != 0) hook_err = 1;
-    bn_fw_kernel<<<blocks(M * N), 256, 0, st>>>(Y, M, N, dsum, (double)(M * shards), W(key + ".weight"), W(key + ".bias"), 1e-5f, stat, A, mask, NPTS);
+    bn_finalize_kernel<<<(N + 127) / 128, 128, 0, st>>>(dsum, (double)(M * shards), N, W(key + ".weight"), W(key + ".bias"), 1e-5f, stat);
+    bn_fw_kernel<<<blocks(M * N / 4), 256, 0, st>>>(Y, M, N, stat, W(key + ".weight"), W(key + ".bias"), A, mask, NPTS);
   };
   auto bn_bw = [&](const std::string& key, float* dA, const float* Y, const float* A, int64_t M, int N, const float* stat, const float* mask) {
     cudaMemsetAsync(dsum, 0, sizeof(double) * 2 * N, st);
@@ -1038,7 +1086,8 @@ int train_forward_backward(const TrainCtx& ctx, const TrainIO& io, cudaStream_t 
     bn_bw_reduce_kernel<<<(unsigned)g, 256, 0, st>>>(dA, Y, A, M, N, stat, mask, NPTS, dsum);
     bn_param_grad_kernel<<<(N + 127) / 128, 128, 0, st>>>(dsum, N, G(key + ".weight"), G(key + ".bias"));  // local sums: like DDP + SyncBN
     if (ctx.allreduce && ctx.allreduce(ctx.allreduce_ctx, dsum, 2 * N) != 0) hook_err = 1;
-    bn_bw_apply_kernel<<<blocks(M * N), 256, 0, st>>>(dA, Y, A, M, N, stat, W(key + ".weight"), dsum, (double)(M * shards), mask, NPTS);
+    bn_bw_means_kernel<<<(2 * N + 127) / 128, 128, 0, st>>>(dsum, (double)(M * shards), N, bnmeans);
+    bn_bw_apply_kernel<<<blocks(M * N / 4), 256, 0, st>>>(dA, Y, A, M, N, stat, W(key + ".weight"), bnmeans, mask, NPTS);
   };
 
   // =====================================================================================================================
