@@ -5,9 +5,9 @@ step against ``torch.optim.AdamW``.
 
 Tolerances.  The gradient of the deepest layers passes through ~25 train-mode BatchNorms; in fp32 its value depends on the
 evaluation order at the few-1e-3 level: the oracle run in fp32 differs from the SAME oracle run in fp64 by up to 2.1e-3 on the
-set-abstraction tensors, the library (fp32, its own summation order, atomics in the scatter ops) by up to 3.7e-3
-(tools/gpu_grad_diag.py prints both tables; the tensors next to the loss agree to < 1e-3).  The bounds asserted here: 5e-3 against
-the fp64 oracle -- the truth -- and 6e-3 against fp32 torch results (the reference's fixture)."""
+set-abstraction tensors, the library (fp32 / 3xTF32, its own summation order, atomics in the scatter ops) by up to 2.1e-3 as well
+(tools/gpu_grad_diag.py prints both tables; the tensors next to the loss agree to < 1e-3).  The bounds asserted here: 3.5e-3 against
+the fp64 oracle -- the truth -- and 4.5e-3 against fp32 torch results (the reference's fixture: two fp32 noise floors)."""
 import numpy as np
 import pytest
 import torch
@@ -66,7 +66,7 @@ def test_training_backward_vs_reference_golden_and_oracle():
     for n in FULL:
         if ".mlp_convs." in n and n.endswith(".bias"):
             continue
-        assert rel_l2(got[n].cpu(), gd["grad/" + n]) < 6e-3, n
+        assert rel_l2(got[n].cpu(), gd["grad/" + n]) < 4.5e-3, n
     # (b) every tensor against the autograd oracle evaluated in float64
     tables = O.diffusion_tables(O.cosine_betas(1000))
     d = lambda x: x.double()
@@ -85,7 +85,7 @@ def test_training_backward_vs_reference_golden_and_oracle():
         e = rel_l2(p.grad.cpu(), r)
         if e > worst[1]:
             worst = (n, e)
-        assert e < 5e-3, (n, e, float(r.norm()))
+        assert e < 3.5e-3, (n, e, float(r.norm()))
     print("worst gradient rel-L2:", worst)
 
 
