@@ -115,8 +115,6 @@ struct lsdm_handle {
   float *head_w, *head_b;
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
-  int fp_tail = 0;               // 1: fused fp1 tail kernel (tensor path only)
-  int fp_fused = 0;              // 1: fused fp2 level (fine GEMM + interpolation + second conv in one kernel)
   int hoist_split = 1;           // 1: the hoisted loop computes the time half of the embedding once per step for the whole batch and the text half once per loop
   int sa1_compact = 1;           // 1: sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles)
   int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
@@ -136,8 +134,7 @@ struct lsdm_handle {
   // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
   int precision = 0;       // dense layers of the condition encoder (PointNet++): 0 fp32, 1 tf32, 2 3xtf32
   int precision_step = 0;
-  int sa_fused = 0;  // 0: gather + GEMMs; 1: fused SA kernel, A operands in smem; 2: fused, A operands in TMEM;
-                     // 3: levels 0-1 with the transposed-last-layer kernel (v2), level 2 as in 2  // dense layers of the per-step x0 network + upsampler
+  int sa_fused = 1;  // 1 (tensor-core builds): fused set-abstraction kernels for levels 1-3; 0: gather + one GEMM per layer
   bool profiling = false;
   struct ProfRec { int cls; cudaEvent_t a, b; std::string tag; double flops; };
   std::string prof_report;
@@ -447,7 +444,7 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   for (int l = 0; l < 4; ++l)
     prof_launch(h, st, K_BALL, [&] { return launch_ball_query(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st); });
-  if (h->sa1_compact && h->precision >= 1 && h->sa_fused == 3)
+  if (h->sa1_compact && h->precision >= 1 && h->sa_fused > 0)
     prof_launch(h, st, K_BALL, [&] { return launch_sa1_plan(q.grp[0], C, q.plan_rows, q.plan_used, q.plan_tiles, q.plan_off, q.plan_n, st); });
   const int fine[4] = {3, 2, 1, 0}, coarse[4] = {4, 3, 2, 1};
   const int fineN[4] = {64, 256, 1024, 1024}, coarseN[4] = {16, 64, 256, 1024};
@@ -470,18 +467,17 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE, 0, -1, GF_A_ROUNDED));
       P = w.tP;
     }
-    const int fused_max_level = h->sa_fused >= 2 ? 2 : 1;
-    if (h->precision >= 1 && h->sa_fused > 0 && l <= fused_max_level) {
+    if (h->precision >= 1 && h->sa_fused > 0 && l <= 2) {
       int r = prof_launch(h, st, K_GEMM, [&] {
-        if (h->sa_fused == 3 && l == 0 && h->sa1_compact)
+        if (l == 0 && h->sa1_compact)
           return launch_sa1_compact(xyz[0], xyz[1], q.plan_rows, q.plan_used, q.plan_off, q.plan_n, h->host_wx[0].data(), h->host_wf[0].data(),
                                     h->host_b1[0].data(), h->host_b2[0].data(), h->sa_w[0][1], h->sa_w[0][2], h->sa_b[0][2], C, w.feat[1],
                                     h->precision == 1, st);
-        if (h->sa_fused == 3 && l <= 1)
+        if (l <= 1)
           return launch_sa_fused_v2(l, P, xyz[l], xyz[l + 1], q.grp[l], h->host_wx[l].data(), h->host_wf[l].data(), h->host_b1[l].data(),
                                     h->host_b2[l].data(), h->sa_wx[l], h->sa_b[l][0], h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1],
                                     h->precision == 1, st);
-        return launch_sa_fused(l, h->sa_fused >= 2, P, xyz[l], xyz[l + 1], q.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
+        return launch_sa_fused(l, P, xyz[l], xyz[l + 1], q.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
                                h->sa_w[l][1], h->sa_b[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1], h->precision == 1, st);
       }, l == 0 ? "sa_fused sa1" : (l == 1 ? "sa_fused sa2" : "sa_fused sa3"), 2.0 * C * S * 32 * ((double)C1 * C2 + (double)C2 * C3));
       if (r < 0) return fail(LSDM_EINVAL, "fused SA kernel unavailable for this level");
@@ -503,7 +499,7 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     const FPSpec& s = kFP[l];
     const int N = fineN[l], S = coarseN[l], C1 = s.mlp[0];
     const float* Pa = nullptr;
-    const bool fused_level = h->precision >= 1 && h->fp_fused && l == 2;  // fp2: both weight matrices fit in shared memory
+    const bool fused_level = h->precision >= 1 && l == 2;  // fp2: both weight matrices fit in shared memory
     if (s.Ca > 0 && !fused_level) {
       GE(gemm(h, st, feat[fine[l]], s.Ca, h->fp_wa[l], s.Ca, w.tA, C1, h->fp_b[l][0], C * N, C1, s.Ca, ACT_NONE, 0, -1, GF_A_ROUNDED));
       Pa = w.tA;
@@ -520,7 +516,7 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       coarse_feat = outs[l];
       continue;
     }
-    if (l == 3 && h->precision >= 1 && h->fp_tail && h->fp_fused) {  // fp1 + head: interpolation gathered inside the fused kernel
+    if (l == 3 && h->precision >= 1) {  // fp1 + head: interpolation gathered inside the fused kernel
       const double fl = 2.0 * C * N * 3.0 * 128 * 128;
       int r = prof_launch(h, st, K_GEMM, [&] {
         return launch_fp1_fused(w.tB, q.nn_idx[l], q.nn_w[l], h->host_fp1_b1.data(), h->fp_w[l][1], h->fp_w[l][2], h->head_w,
@@ -535,14 +531,6 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
       GE(gemm(h, st, w.tP, C1, h->fp_w[l][1], C1, outs[l], s.mlp[1], h->fp_b[l][1], C * N, s.mlp[1], C1, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
       coarse_feat = outs[l];
     } else {
-      if (h->precision >= 1 && h->fp_tail) {
-        int r = prof_launch(h, st, K_GEMM, [&] {
-          return launch_fp1_tail(w.tP, h->fp_w[l][1], h->fp_w[l][2], h->head_w, h->host_tail.data(), (int64_t)C * N, w.backbone, st);
-        }, "fp1_tail", 2.0 * C * N * 3.0 * 128 * 128);
-        if (r < 0) return fail(LSDM_EINVAL, "fused fp1 tail unavailable");
-        if (h->profiling) h->gemm_flops += 2.0 * C * N * 3.0 * 128 * 128;
-        continue;
-      }
       GE(gemm(h, st, w.tP, 128, h->fp_w[l][1], 128, w.tA, 128, h->fp_b[l][1], C * N, 128, 128, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
       GE(gemm(h, st, w.tA, 128, h->fp_w[l][2], 128, w.tP, 128, h->fp_b[l][2], C * N, 128, 128, ACT_RELU, 0, -1, GF_A_ROUNDED | GF_ROUND_OUT));
       GE(gemm(h, st, w.tP, 128, h->head_w, 128, w.tA, 128, h->head_b, C * N, 128, 128, ACT_RELU, 0, -1, GF_A_ROUNDED));
@@ -1477,12 +1465,8 @@ LSDM_API const char* lsdm_profile_report(const lsdm_handle* h) { return h ? h->p
 
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   if (!h || !name) return fail(LSDM_EINVAL, "null argument");
-  if (strcmp(name, "fp_fused") == 0 && (value == 0 || value == 1)) {
-    h->fp_fused = value;
-    return LSDM_OK;
-  }
   if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 3) {
-    h->sa_fused = value;
+    h->sa_fused = value > 0 ? 1 : 0;  // (values 1..3 named round-1 kernel variants; one fused form is left)
     return LSDM_OK;
   }
   if (strcmp(name, "hoist_split") == 0 && (value == 0 || value == 1)) {
@@ -1501,24 +1485,8 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
     h->dedup_absent = value;
     return LSDM_OK;
   }
-  if (strcmp(name, "fp_tail") == 0 && (value == 0 || value == 1)) {
-    h->fp_tail = value;
-    return LSDM_OK;
-  }
   if (strcmp(name, "select_uniform") == 0 && (value == 0 || value == 1)) {
     g_select_uniform_shortcut = value;  // process-wide
-    return LSDM_OK;
-  }
-  if (strcmp(name, "gemm_tma") == 0 && (value == 0 || value == 1)) {
-    g_gemm_tma = value;  // process-wide
-    return LSDM_OK;
-  }
-  if (strcmp(name, "gemm_async") == 0 && (value == 0 || value == 1)) {
-    g_gemm_async = value;  // process-wide
-    return LSDM_OK;
-  }
-  if (strcmp(name, "gemm_ws") == 0 && (value == 0 || value == 1)) {
-    g_gemm_ws = value;  // process-wide
     return LSDM_OK;
   }
   return fail(LSDM_EINVAL, std::string("unknown option or bad value: ") + name);

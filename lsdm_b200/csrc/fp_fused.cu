@@ -493,7 +493,7 @@ int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, co
 
 namespace lsdm {
 
-// fp1 + head.  h_consts: host copy of [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)] (as launch_fp1_tail);
+// fp1 + head.  h_consts: host copy of [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)];
 // h_b1: host copy of the first conv's folded bias [128].  N (points per cloud) must be a power of two and a multiple of 128.
 int launch_fp1_fused(const float* Pb, const int* nn_idx, const float* nn_w, const float* h_b1, const float* W2, const float* W3,
                      const float* Wh, const float* h_consts, int n_clouds, int N, int S, float* out, cudaStream_t st) {

@@ -34,7 +34,7 @@ int launch_copy_cols(const float* src, int ld_src, int col0, int ncols, int rows
 // ---- sa_fused.cu ----------------------------------------------------------------------------
 // Fused set-abstraction block on the tensor cores (gather + 2 dense layers + max-pool), levels 0..2.
 // Returns -1 when the (level, variant) combination is not built.
-int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, const float* new_xyz, const int* grp,
+int launch_sa_fused(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp,
                     const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
                     const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st);
 
@@ -57,11 +57,6 @@ int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, co
 // fused last level + head: fp1 (interpolation gathered in-kernel, 3 x 128x128 convs) + conv2; h_b1 / h_consts are HOST arrays
 int launch_fp1_fused(const float* Pb, const int* nn_idx, const float* nn_w, const float* h_b1, const float* W2, const float* W3,
                      const float* Wh, const float* h_consts, int n_clouds, int N, int S, float* out, cudaStream_t st);
-
-// fused tail of the backbone: fp1 layers 2-3 + conv1/bn1 head + conv2, TF32 tensor cores; h_consts is a HOST array
-// [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]
-int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const float* Wh, const float* h_consts, int64_t rows,
-                    float* out, cudaStream_t st);
 
 // ---- x0net_fused.cu ---------------------------------------------------------------------------
 // the x0 network of one step (3 -> 64 -> 128 || emb -> 192 -> 128 -> 64 -> 3, 3xTF32) + in-place x += pcd_out + posterior mean +

@@ -884,16 +884,13 @@ int launch_sa1_compact(const float* xyz, const float* new_xyz, const int* rows, 
 namespace {
 }  // namespace
 
-// level: 0 (sa1: 6->32->32->64) or 1 (sa2: 67->64->64->128).  a_tmem selects the A-from-TMEM variant.
-int launch_sa_fused(int level, bool a_tmem, const float* P, const float* xyz, const float* new_xyz, const int* grp,
+// level 2 (sa3: 131 -> 128 -> 128 -> 256): every activation in tensor memory.  (Levels 0 and 1 use the v2 kernel below.)
+int launch_sa_fused(int level, const float* P, const float* xyz, const float* new_xyz, const int* grp,
                     const float* Wx, const float* Wf3, const float* b1, const float* W2, const float* b2, const float* W3,
                     const float* b3, int n_clouds, int N, int S, float* out, int round_out, cudaStream_t st) {
-  if (S <= 0 || (S & (S - 1)) != 0) return -1;
+  if (S <= 0 || (S & (S - 1)) != 0 || level != 2) return -1;
   SaArgs a{P, xyz, new_xyz, grp, Wx, Wf3, b1, W2, b2, W3, b3, out, n_clouds * S / 4, N, S, round_out, __builtin_ctz(S)};
-  if (level == 0) return a_tmem ? launch_t<32, 32, 64, true, true>(a, st) : launch_t<32, 32, 64, true, false>(a, st);
-  if (level == 1) return a_tmem ? launch_t<64, 64, 128, false, true>(a, st) : launch_t<64, 64, 128, false, false>(a, st);
-  if (level == 2) return a_tmem ? launch_t<128, 128, 256, false, true, 256>(a, st) : -1;
-  return -1;
+  return launch_t<128, 128, 256, false, true, 256>(a, st);
 }
 
 // v2 (transposed last layer, constant-bank vectors) for levels 0 and 1; h_* are HOST copies of the small per-channel vectors.
@@ -905,179 +902,6 @@ int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float*
   if (level == 0) return launch_v2<32, 32, 64, true, 128>(a, h_wx, h_wf, h_b1, h_b2, st);
   if (level == 1) return launch_v2<64, 64, 128, false, 256>(a, h_wx, h_wf, h_b1, h_b2, st);
   return -1;
-}
-
-}  // namespace lsdm
-
-// ------------------------------------------------------------------------------------------------------------------
-// Fused tail of the backbone (reference pointnet2.py:71-79, pointnet2_utils.py:308-311): the last two fp1 layers, the
-// conv1+bn1+ReLU head and conv2 (128 -> 3), for 128 rows per tile:
-//   A0 = tP[row, 0:128] (thread = row, rounded to TF32, written to TMEM) -> W2 -> ReLU -> W3 -> ReLU -> Wh -> ReLU -> 3 dots.
-// All three 128x128 weight matrices stay resident in shared memory (192 KB); activations ping-pong between two 128-column
-// TMEM regions with in-place epilogues (A-from-TMEM MMAs), so only the [rows,3] result leaves the SM.
-// ------------------------------------------------------------------------------------------------------------------
-namespace lsdm {
-namespace {
-
-using namespace tc;
-
-struct TailConst {
-  float b2[128], b3[128], bh[128];
-  float wc[3 * 128];
-  float bc[3];
-};
-
-__global__ void __launch_bounds__(128, 1) fp1_tail_kernel(const float* __restrict__ X0, const float* __restrict__ W2,
-                                                          const float* __restrict__ W3, const float* __restrict__ Wh,
-                                                          float* __restrict__ out, int64_t rows, int n_tiles,
-                                                          const __grid_constant__ TailConst k) {
-  constexpr int WB = 128 * 128 * 4;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t s_bar;
-  __shared__ uint32_t s_tmem;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sW[3] = {base, base + WB, base + 2 * WB};
-  const uint32_t bar = smem_u32(&s_bar);
-  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 256);
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  const float* Ws[3] = {W2, W3, Wh};
-  for (int m = 0; m < 3; ++m)
-    for (int q = tid; q < 128 * 128 / 4; q += 128) {
-      int n = q >> 5, k4 = q & 31;
-      float4 v = *reinterpret_cast<const float4*>(Ws[m] + (int64_t)n * 128 + k4 * 4);
-      st_shared_v4(sW[m] + (k4 >> 3) * (128 * 128) + sw128_off(n, k4 & 7), rna_tf32(v));
-    }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = s_tmem;
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-  constexpr uint32_t idesc = umma_idesc_tf32(128, 128);
-  uint32_t phase = 0;
-  auto mma_layer = [&](int m, uint32_t col_a, uint32_t col_d) {
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
-        const uint64_t db = umma_desc_sw128(sW[m] + kb * (128 * 128));
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_tf32_ts(tmem + col_d, tmem + col_a + kb * 32 + kk * 8, db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
-      }
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-  };
-
-  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
-  const int t0 = blockIdx.x * per, t1 = (t0 + per < n_tiles) ? t0 + per : n_tiles;
-  for (int tile = t0; tile < t1; ++tile) {
-    int64_t row = (int64_t)tile * 128 + tid;
-    const int64_t rrow = row < rows ? row : rows - 1;
-    const float* src = X0 + rrow * 128;
-    // ---- A0: own row -> TF32 -> TMEM columns [0,128) ----
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      uint32_t v[32];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 p = *reinterpret_cast<const float4*>(src + kb * 32 + q * 4);
-        v[q * 4 + 0] = rna_tf32_mma(p.x);
-        v[q * 4 + 1] = rna_tf32_mma(p.y);
-        v[q * 4 + 2] = rna_tf32_mma(p.z);
-        v[q * 4 + 3] = rna_tf32_mma(p.w);
-      }
-      tmem_st32(tlane + kb * 32, v);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncthreads();
-    mma_layer(0, 0, 128);  // Y = A0 . W2^T
-    // ---- Y = relu(Y + b2) in place ----
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      uint32_t v[32];
-      tmem_ld32(tlane + 128 + kb * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = rna_tf32_mma(fmaxf(__uint_as_float(v[e]) + k.b2[kb * 32 + e], 0.0f));
-      tmem_st32(tlane + 128 + kb * 32, v);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncthreads();
-    mma_layer(1, 128, 0);  // X = Y . W3^T
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      uint32_t v[32];
-      tmem_ld32(tlane + kb * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = rna_tf32_mma(fmaxf(__uint_as_float(v[e]) + k.b3[kb * 32 + e], 0.0f));
-      tmem_st32(tlane + kb * 32, v);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncthreads();
-    mma_layer(2, 0, 128);  // Y = X . Wh^T   (conv1 with bn1 folded)
-    // ---- head: relu(Y + bh) . conv2^T + bc (128 -> 3), fp32 CUDA cores ----
-    float o0 = k.bc[0], o1 = k.bc[1], o2 = k.bc[2];
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      uint32_t v[32];
-      tmem_ld32(tlane + 128 + kb * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int ch = kb * 32 + e;
-        float x = fmaxf(__uint_as_float(v[e]) + k.bh[ch], 0.0f);
-        o0 = fmaf(k.wc[ch], x, o0);
-        o1 = fmaf(k.wc[128 + ch], x, o1);
-        o2 = fmaf(k.wc[256 + ch], x, o2);
-      }
-    }
-    if (row < rows) {
-      out[row * 3 + 0] = o0;
-      out[row * 3 + 1] = o1;
-      out[row * 3 + 2] = o2;
-    }
-    tc_fence_before();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-}  // namespace
-
-// h_consts: host copy of [b2(128) | b3(128) | bh(128) | conv2.weight(3x128) | conv2.bias(3)]
-int launch_fp1_tail(const float* X0, const float* W2, const float* W3, const float* Wh, const float* h_consts, int64_t rows,
-                    float* out, cudaStream_t st) {
-  TailConst k;
-  for (int i = 0; i < 128; ++i) {
-    k.b2[i] = h_consts[i];
-    k.b3[i] = h_consts[128 + i];
-    k.bh[i] = h_consts[256 + i];
-  }
-  for (int i = 0; i < 384; ++i) k.wc[i] = h_consts[384 + i];
-  for (int i = 0; i < 3; ++i) k.bc[i] = h_consts[768 + i];
-  constexpr int smem = 3 * 128 * 128 * 4 + 1024;
-  static PerDeviceOnce attr_done;
-  if (smem_opt_in(attr_done, fp1_tail_kernel, smem) != cudaSuccess) return -1;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_tiles = (int)((rows + 127) / 128);
-  const int grid = n_tiles < sms ? n_tiles : sms;
-  fp1_tail_kernel<<<grid, 128, smem, st>>>(X0, W2, W3, Wh, out, rows, n_tiles, k);
-  return 1;
 }
 
 }  // namespace lsdm
