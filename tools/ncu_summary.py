@@ -8,7 +8,9 @@ WANT = [("gpu__time_duration.sum", "dur_us"), ("dram__bytes_read.sum", "dram_rd_
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
         ("launch__registers_per_thread", "regs"), ("launch__occupancy_limit_shared_mem", "occ_lim_smem"),
-        ("launch__occupancy_limit_registers", "occ_lim_regs"), ("lts__t_bytes.sum", "l2_MB")]
+        ("launch__occupancy_limit_registers", "occ_lim_regs"), ("lts__t_bytes.sum", "l2_MB"),
+        # global loads that missed L1 (32-byte sectors): what the gather-fused kernels pull from L2
+        ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum", "l2_gather_MB")]
 
 
 def conv(val, unit, want_mb):
@@ -35,6 +37,9 @@ def main(path):
         out = [name, r[idx["Grid Size"]].replace(",", " ")]
         for m, n in cols:
             try:
+                if n == "l2_gather_MB":
+                    out.append(f"{float(r[idx[m]].replace(',', '')) * 32e-6:.3f}")
+                    continue
                 out.append(f"{conv(r[idx[m]], units[idx[m]], n.endswith('_MB')):.3f}")
             except Exception:
                 out.append("")
