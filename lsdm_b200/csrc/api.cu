@@ -115,6 +115,7 @@ struct lsdm_handle {
   float *head_w, *head_b;
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
+  int select_grid = 1;           // 1: ball queries / 3-NN over 1024 source points use a per-cloud cell grid (identical selections)
   int hoist_split = 1;           // 1: the hoisted loop computes the time half of the embedding once per step for the whole batch and the text half once per loop
   int sa1_compact = 1;           // 1: sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles)
   int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
@@ -443,13 +444,25 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
                                                      q.xyz[3], q.xyz[4], st); });
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   for (int l = 0; l < 4; ++l)
-    prof_launch(h, st, K_BALL, [&] { return launch_ball_query(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st); });
+    prof_launch(h, st, K_BALL, [&] {
+      if (h->select_grid && kSA[l].N == 1024) {  // levels 0 and 1: cell grid instead of the 1024 x 1024 / 256 x 1024 scan (identical groups)
+        const int r = launch_ball_query_grid(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st);
+        if (r > 0) return r;
+      }
+      return launch_ball_query(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st);
+    });
   if (h->sa1_compact && h->precision >= 1 && h->sa_fused > 0)
     prof_launch(h, st, K_BALL, [&] { return launch_sa1_plan(q.grp[0], C, q.plan_rows, q.plan_used, q.plan_tiles, q.plan_off, q.plan_n, st); });
   const int fine[4] = {3, 2, 1, 0}, coarse[4] = {4, 3, 2, 1};
   const int fineN[4] = {64, 256, 1024, 1024}, coarseN[4] = {16, 64, 256, 1024};
   for (int l = 0; l < 4; ++l)
-    prof_launch(h, st, K_3NN, [&] { return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st); });
+    prof_launch(h, st, K_3NN, [&] {
+      if (h->select_grid && fineN[l] == 1024) {  // fp2 (1024 <- 256) and fp1 (1024 <- 1024)
+        const int r = launch_three_nn_grid(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st);
+        if (r > 0) return r;
+      }
+      return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st);
+    });
   CK(cudaPeekAtLastError());
   return LSDM_OK;
 }
@@ -1467,6 +1480,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   if (!h || !name) return fail(LSDM_EINVAL, "null argument");
   if (strcmp(name, "sa_fused") == 0 && value >= 0 && value <= 3) {
     h->sa_fused = value > 0 ? 1 : 0;  // (values 1..3 named round-1 kernel variants; one fused form is left)
+    return LSDM_OK;
+  }
+  if (strcmp(name, "select_grid") == 0 && (value == 0 || value == 1)) {
+    h->select_grid = value;
     return LSDM_OK;
   }
   if (strcmp(name, "hoist_split") == 0 && (value == 0 || value == 1)) {

@@ -15,6 +15,10 @@ int launch_ball_query(const float* xyz, const float* new_xyz, int n_clouds, int 
 int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, int S, int* nn_idx, float* nn_w,
                     cudaStream_t st);
 
+// ---- pointnet_grid.cu: cell-grid forms of the two scans for 1024 source points (identical results) ----
+int launch_ball_query_grid(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group, cudaStream_t st);
+int launch_three_nn_grid(const float* xyz1, const float* xyz2, int n_clouds, int N, int S, int* nn_idx, float* nn_w, cudaStream_t st);
+
 // ---- pointnet_glue.cu -----------------------------------------------------------------------
 // h1[(c,s,k), ch] = relu(P[c*N + j, ch] + Wx[ch,:] . (xyz[c,j] - new_xyz[c,s])),  j = group[c,s,k]
 // P == nullptr (sa1): P is replaced by bias[ch] + Wf[ch,0:3] . xyz[c,j]   (features are the coordinates)

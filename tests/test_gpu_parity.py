@@ -662,3 +662,50 @@ def test_hoisted_loop_embedding_split_matches_full_chain():
             eng.set_option("hoist_split", 1)
     for a, b in zip(*outs):
         assert rel_l2(a.cpu(), b.cpu()) < 1e-5
+
+
+def test_cell_grid_selections_are_identical_to_the_full_scans():
+    """Ball queries (levels 0, 1) and 3-NN (fp2, fp1) through the per-cloud cell grid ("select_grid") against the full O(N^2) scans:
+    every index and every interpolation weight must be IDENTICAL, on random clouds and on adversarial ones -- one tight cluster, far
+    offsets (large norms: large rounding slack), collinear and coplanar points, heavy duplication (distance ties), lattice points
+    (distances exactly on the ball radius, many equal distances), two distant clusters, a single outlier."""
+    B = 4
+    m, _ = _model("wellcond")
+    inp = syn.make_inputs(81, B)
+    objs = inp["given_objs"].clone()
+    rs = np.random.RandomState(5)
+    u = lambda *s: torch.from_numpy(rs.uniform(-0.5, 0.5, size=s).astype(np.float32))
+    objs[0, 1] = u(1024, 3) * 0.05                                   # one tight cluster: every ball holds every point
+    objs[0, 2] = u(1024, 3) + torch.tensor([100.0, -50.0, 25.0])     # large norms
+    objs[0, 3] = torch.cat([u(1024, 1), torch.zeros(1024, 2)], 1)    # collinear
+    objs[0, 4] = torch.cat([u(1024, 2), torch.full((1024, 1), 0.25)], 1)   # coplanar
+    objs[0, 5] = u(64, 3).repeat(16, 1)                              # every point 16 times
+    lat = torch.stack(torch.meshgrid(*[torch.arange(16) * 0.05 - 0.375] * 3, indexing="ij"), -1).reshape(-1, 3)[:1024].float()
+    objs[0, 6] = lat[torch.from_numpy(rs.permutation(1024))]         # lattice: distances exactly r, 2r, ... and many ties
+    objs[0, 7] = torch.cat([u(512, 3) * 0.1 - 0.4, u(512, 3) * 0.1 + 0.4])   # two distant clusters
+    objs[0, 8] = u(1024, 3) * 0.2
+    objs[0, 8, 500] = torch.tensor([5.0, 5.0, 5.0])                  # one far outlier
+    objs[1, 1] = u(1024, 3) * torch.tensor([1.0, 0.01, 0.3])         # anisotropic
+    inp["given_objs"] = objs
+    fps, _ = syn.make_step_randoms(82, B, 1)
+    g = _cuda(inp)
+    names = ["ball_idx0", "ball_idx1", "nn_idx2", "nn_idx3", "fps_idx0"]
+    out = {}
+    for flag in (1, 0):
+        eng = m.engine(B, torch.device("cuda", 0))
+        eng.set_option("select_grid", flag)
+        try:
+            x = g["x_T"].clone()
+            with injected_rng(fps_starts=list(fps[0])):
+                _, x0 = m(x, g["mask"], torch.full((B,), 77, device="cuda"), g["given_objs"], g["given_cats"], g["text_emb"])
+            out[flag] = {n: m._engine.debug_tensor(n, torch.int32).cpu().clone() for n in names}
+            for l in (2, 3):
+                out[flag][f"nn_w{l}"] = m._engine.debug_tensor(f"nn_w{l}").cpu().clone()
+            out[flag]["x0"] = x0.cpu().clone()
+        finally:
+            eng.set_option("select_grid", 1)
+    for n in out[1]:
+        same = torch.equal(out[1][n], out[0][n])
+        if not same:
+            diff = (out[1][n] != out[0][n]).nonzero()
+            raise AssertionError(f"{n}: {diff.shape[0]} entries differ, first at {diff[0].tolist()}")
