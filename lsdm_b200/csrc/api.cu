@@ -115,7 +115,7 @@ struct lsdm_handle {
   float *head_w, *head_b;
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
-  int select_grid = 1;           // 1: ball queries / 3-NN over 1024 source points use a per-cloud cell grid (identical selections)
+  int select_grid = 9;           // bit mask: ball query level 0 (1), level 1 (2), 3-NN of fp2 (4), of fp1 (8) through a per-cloud cell grid (identical selections)
   int hoist_split = 1;           // 1: the hoisted loop computes the time half of the embedding once per step for the whole batch and the text half once per loop
   int sa1_compact = 1;           // 1: sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles)
   int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
@@ -129,7 +129,9 @@ struct lsdm_handle {
   Workspace ws{};
   bool have_ws = false;
   int64_t launches = 0;
-  cudaStream_t side = nullptr, dense_st = nullptr;
+  cudaStream_t side = nullptr, dense_st = nullptr, cond_st = nullptr;
+  cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;  // condition MLPs + human decoder beside the selection chain (cond_stream)
+  int cond_stream = 1;  // 1: in the pipelined loop the per-sample condition MLPs / human decoder run on their own stream, overlapping the FPS chain
   cudaEvent_t ev_fork = nullptr, ev_sel[3] = {nullptr, nullptr, nullptr}, ev_dense[3] = {nullptr, nullptr, nullptr},
               ev_step[3] = {nullptr, nullptr, nullptr};
   // optional per-class CUDA-event profiler (bench.py's kernel shares / roofline numerator)
@@ -411,10 +413,18 @@ __global__ void gather_fps_start_kernel(const int64_t* __restrict__ src, const i
 // runs on: the same tensor, or the de-duplicated copy (Workspace::clouds_c, `active` = compact -> original cloud index).
 int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const float* objs, const float* cats,
                  const float* mask_global, const int64_t* fps_start, cudaStream_t st, const float* clouds = nullptr, int C = -1,
-                 const int* active = nullptr) {
+                 const int* active = nullptr, bool fork_cond = false) {
   const int B = h->cfg.batch_local;
   if (!clouds) clouds = objs, C = B * NOBJ;
   Workspace& w = h->ws;
+  // fork_cond (pipelined loop): the condition MLPs and the human decoder do not depend on the selection chain -- they run on their
+  // own stream beside it (both are latency-bound, few warps per SM) and join before the phase's completion event is recorded
+  cudaStream_t sel_st = st;
+  if (fork_cond) {
+    CK(cudaEventRecord(h->ev_cfork, st));  // carries the buffer-reuse waits of this phase over to the condition stream
+    CK(cudaStreamWaitEvent(h->cond_st, h->ev_cfork, 0));
+    st = h->cond_st;
+  }
   {
     CondWeights cw{h->W("embed_text.0.weight"), h->W("embed_text.0.bias"), h->W("embed_text.2.weight"), h->W("embed_text.2.bias"),
                    h->W("embed_text.4.weight"), h->W("embed_text.4.bias"), h->W("predict_cat.0.weight"), h->W("predict_cat.0.bias"),
@@ -435,6 +445,10 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
     hw.w3 = h->W("human_backbone.de_spiral.3.layer.weight"); hw.b3 = h->W("human_backbone.de_spiral.3.layer.bias");
     prof_launch(h, st, K_COND, [&] { return launch_human(hw, objs, B, w.human_scratch, q.hm, st); });
   }
+  if (fork_cond) {
+    CK(cudaEventRecord(h->ev_cjoin, h->cond_st));
+    st = sel_st;
+  }
   if (active) {
     gather_fps_start_kernel<<<(4 * C + 255) / 256, 256, 0, st>>>(fps_start, active, B * NOBJ, C, q.fps_start);
   } else if (fps_start != q.fps_start) {
@@ -445,7 +459,7 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   for (int l = 0; l < 4; ++l)
     prof_launch(h, st, K_BALL, [&] {
-      if (h->select_grid && kSA[l].N == 1024) {  // levels 0 and 1: cell grid instead of the 1024 x 1024 / 256 x 1024 scan (identical groups)
+      if (l <= 1 && ((h->select_grid >> l) & 1)) {  // levels 0 and 1: cell grid instead of the 1024 x 1024 / 256 x 1024 scan (identical groups)
         const int r = launch_ball_query_grid(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st);
         if (r > 0) return r;
       }
@@ -457,12 +471,13 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   const int fineN[4] = {64, 256, 1024, 1024}, coarseN[4] = {16, 64, 256, 1024};
   for (int l = 0; l < 4; ++l)
     prof_launch(h, st, K_3NN, [&] {
-      if (h->select_grid && fineN[l] == 1024) {  // fp2 (1024 <- 256) and fp1 (1024 <- 1024)
+      if (l >= 2 && ((h->select_grid >> l) & 1)) {  // fp2 (1024 <- 256) and fp1 (1024 <- 1024)
         const int r = launch_three_nn_grid(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st);
         if (r > 0) return r;
       }
       return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st);
     });
+  if (fork_cond) CK(cudaStreamWaitEvent(st, h->ev_cjoin, 0));
   CK(cudaPeekAtLastError());
   return LSDM_OK;
 }
@@ -801,6 +816,9 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
   // modes: 0 no priorities, 1 side stream high, 2 side + dense high, 3 dense high only
   cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, (pmode == 1 || pmode == 2) ? prio_hi : prio_lo);
   cudaStreamCreateWithPriority(&h->dense_st, cudaStreamNonBlocking, pmode >= 2 ? prio_hi : prio_lo);
+  cudaStreamCreateWithPriority(&h->cond_st, cudaStreamNonBlocking, prio_lo);
+  cudaEventCreateWithFlags(&h->ev_cfork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_cjoin, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < 3; ++i) {
     cudaEventCreateWithFlags(&h->ev_sel[i], cudaEventDisableTiming);
@@ -821,6 +839,9 @@ LSDM_API void lsdm_destroy(lsdm_handle* h) {
   if (h->sched) cudaFree(h->sched);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->dense_st) cudaStreamDestroy(h->dense_st);
+  if (h->cond_st) cudaStreamDestroy(h->cond_st);
+  if (h->ev_cfork) cudaEventDestroy(h->ev_cfork);
+  if (h->ev_cjoin) cudaEventDestroy(h->ev_cjoin);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 3; ++i) {
     if (h->ev_sel[i]) cudaEventDestroy(h->ev_sel[i]);
@@ -1232,7 +1253,8 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     CK(cudaStreamWaitEvent(dst, h->ev_fork, 0));
   }
   tl_begin(0, 'S', side);
-  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side, clouds, nc, active));
+  const bool fork_cond = pipelined && h->cond_stream;
+  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side, clouds, nc, active, fork_cond));
   tl_end(side);
   if (pipelined) CK(cudaEventRecord(h->ev_sel[0], side));
   for (int k = 0; k < n_steps; ++k) {
@@ -1244,7 +1266,7 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
         CK(cudaStreamWaitEvent(side, h->ev_step[sn], 0));
       }
       tl_begin(k + 1, 'S', side);
-      GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active));
+      GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active, fork_cond));
       tl_end(side);
       CK(cudaEventRecord(h->ev_sel[sn], side));
     }
@@ -1482,7 +1504,11 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
     h->sa_fused = value > 0 ? 1 : 0;  // (values 1..3 named round-1 kernel variants; one fused form is left)
     return LSDM_OK;
   }
-  if (strcmp(name, "select_grid") == 0 && (value == 0 || value == 1)) {
+  if (strcmp(name, "cond_stream") == 0 && (value == 0 || value == 1)) {
+    h->cond_stream = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "select_grid") == 0 && value >= 0 && value <= 15) {
     h->select_grid = value;
     return LSDM_OK;
   }

@@ -31,6 +31,33 @@ inline int device_sm_count() {
   return sms;
 }
 
+// Shared-memory accesses by explicit 32-bit shared-window address.  nvcc (12.9, sm_100a) re-derives the address of a shared
+// object that is reached through a pointer (a struct of sub-array pointers, a device-function argument) from the generic
+// address on every access -- S2R SR_CgaCtaId + LEA + adds, not hoisted out of loops -- which costs more than the access in the
+// selection kernels' inner loops.  `smem_addr` converts once; the accessors below are plain ld/st.shared.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 constexpr int NPTS = 1024;  // points per cloud
 constexpr int NOBJ = 9;     // object slots per scene
 constexpr int CLIP = 512;

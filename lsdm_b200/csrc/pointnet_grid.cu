@@ -1,7 +1,7 @@
 // Cell-grid forms of the two O(N^2) selection scans of PointNet++ (reference pointnet2_utils.py:84-104 query_ball_point,
-// :293-295 the 3-NN of PointNetFeaturePropagation), for the levels with 1024 source points.  Results are IDENTICAL to the
-// full scans of pointnet_select.cu (and therefore to the reference): every candidate's distance is computed with the same
-// IEEE operations in the same order,
+// :293-295 the 3-NN of PointNetFeaturePropagation), for the levels with up to 1024 source points.  Results are IDENTICAL to
+// the full scans of pointnet_select.cu (and therefore to the reference): every candidate's distance is computed with the
+// same IEEE operations in the same order,
 //     d = ((-2 * (q.p)) + |q|^2) + |p|^2,   q.p = fma(qz, pz, fma(qy, py, qx * px)),
 // and the grid only decides WHICH candidates are looked at, with a margin that covers the rounding of that formula:
 //   * |fl(d) - d| <= 40 u (max |p|)^2 (three roundings in the dot product and in each norm, two in the sums; u = 2^-24); E below is
@@ -13,64 +13,137 @@
 //   * 3-NN: rings of cells around the query are visited until the current third-best computed distance is strictly below
 //     ((ring - 1e-4) h)^2 - E, a lower bound of the computed distance of every unvisited point; candidates are ranked by
 //     (distance, index), which is what the index-order scan with strict '<' insertion produces.
-// One block per cloud; the grid (<= 16^3 cells, counting sort in shared memory) is built by the block that uses it.
+// One 256-thread block per cloud builds the grid in shared memory (counting sort of the points by cell: one float4
+// (x, y, z, |p|^2) + the original index per sorted slot, so a candidate costs ONE 128-bit shared load) and then answers the
+// cloud's queries, one query per thread at a time.  The 9 (z, y) rows of a 3 x 3 x 3 block are contiguous runs of the sorted
+// array (three x-adjacent cells); a thread walks them in ONE flattened loop (row advance and candidate evaluation are
+// iterations of the same loop) so that a warp's trip count is the maximum of its lanes' candidate counts, not the sum over
+// rows of per-row maxima.  Queries whose block holds a large share of the cloud (dense clusters, degenerate clouds) take the
+// index-order scan with early exit instead -- the worst case costs what the full scan costs.
 #include "kernels.cuh"
 
 namespace lsdm {
 
 namespace {
 
-constexpr int GN = 1024;      // source points per cloud handled by these kernels
+constexpr int GN = 1024;      // source points per cloud at most
 constexpr int GMAX = 16;      // cells per axis at most
 constexpr int GCELLS = GMAX * GMAX * GMAX;
+constexpr int GT = 256;       // threads per block
+constexpr int GPER = GN / GT;
 
 struct Grid {
   float minx, miny, minz, inv_h, h, E;
   int nx, ny, nz;
+  int uniform;  // every source point has the same coordinates
 };
 
-// Builds the grid over the GN points staged in shared memory (sx, sy, sz).  h_min: smallest admissible cell width (0: choose
-// from the point density).  Outputs cell_start[ncell + 1] and cell_pts[GN] (point indices grouped by cell, any order inside).
-__device__ void build_grid(const float* sx, const float* sy, const float* sz, const float* sn2, int n_pts, float h_req, int target_per_axis,
-                           Grid& g, int* cell_start, unsigned short* cell_pts, int* s_tmp /* >= GCELLS + 64 ints */) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  // bounding box and largest squared norm (block reduction through shared memory)
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, nmax = 0.f;
-  for (int i = tid; i < n_pts; i += nt) {
-    lo[0] = fminf(lo[0], sx[i]); hi[0] = fmaxf(hi[0], sx[i]);
-    lo[1] = fminf(lo[1], sy[i]); hi[1] = fmaxf(hi[1], sy[i]);
-    lo[2] = fminf(lo[2], sz[i]); hi[2] = fmaxf(hi[2], sz[i]);
-    nmax = fmaxf(nmax, sn2[i]);
+struct GridSmem {
+  float4* pts;            // [GN]  sorted by cell: x, y, z, |p|^2
+  unsigned short* oidx;   // [GN]  original index of the sorted slot
+  unsigned short* cstart; // [GCELLS + 8]
+  int* scratch;           // [GCELLS] cell counters during the build (may alias memory the queries use afterwards)
+  float* red;             // [7 * 8] block reduction
+};
+
+__device__ __forceinline__ float sqdist_ref(float qx, float qy, float qz, float q2, float px, float py, float pz, float p2) {
+  const float dot = __fmaf_rn(qz, pz, __fmaf_rn(qy, py, __fmul_rn(qx, px)));
+  return __fadd_rn(__fmaf_rn(-2.0f, dot, q2), p2);  // fma(-2, dot, q2) == (-2 * dot) + q2 bit for bit (exact product)
+}
+
+// Exclusive scan of the GCELLS cell counters into 16-bit start offsets (start[GCELLS] = total): 16 consecutive cells per
+// thread, warp scan of the thread sums, warp totals through shared memory (wtot: GT / 32 ints).  Contains one barrier; the
+// caller synchronises before reading `start`.
+__device__ __forceinline__ void cell_scan(const int* counters, unsigned short* start, int* wtot) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int c16[16];
+  const int4* cp = reinterpret_cast<const int4*>(counters) + tid * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int4 v = cp[q];
+    c16[q * 4] = v.x; c16[q * 4 + 1] = v.y; c16[q * 4 + 2] = v.z; c16[q * 4 + 3] = v.w;
   }
-  float* red = reinterpret_cast<float*>(s_tmp);  // [7][32]
-  for (int k = 0; k < 3; ++k) {
-    float a = lo[k], b = hi[k];
-    for (int o = 16; o > 0; o >>= 1) {
-      a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
-      b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sum += c16[j];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  int base = incl - sum;
+#pragma unroll
+  for (int w = 0; w < GT / 32; ++w) base += (w < warp) ? wtot[w] : 0;
+  unsigned short st16[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    st16[j] = (unsigned short)base;
+    base += c16[j];
+  }
+  uint4* op = reinterpret_cast<uint4*>(start + tid * 16);
+  op[0] = make_uint4(st16[0] | (st16[1] << 16), st16[2] | (st16[3] << 16), st16[4] | (st16[5] << 16), st16[6] | (st16[7] << 16));
+  op[1] = make_uint4(st16[8] | (st16[9] << 16), st16[10] | (st16[11] << 16), st16[12] | (st16[13] << 16), st16[14] | (st16[15] << 16));
+  if (tid == GT - 1) start[GCELLS] = (unsigned short)base;
+}
+
+// Builds the grid over the n_pts (<= GN) points of `src`.  h_req > 0: cells at least sqrt(h_req^2 + E) * 1.001 wide (ball
+// query of radius h_req); h_req == 0: about target_per_axis cells along the longest axis.
+__device__ void build_grid(const float* __restrict__ src, int n_pts, float h_req, int target_per_axis, Grid& g, const GridSmem& s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float px[GPER], py[GPER], pz[GPER];
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, nmax = 0.f;
+#pragma unroll
+  for (int k = 0; k < GPER; ++k) {
+    const int i = tid + k * GT;
+    if (i < n_pts) {
+      px[k] = src[i * 3]; py[k] = src[i * 3 + 1]; pz[k] = src[i * 3 + 2];
+      lo[0] = fminf(lo[0], px[k]); hi[0] = fmaxf(hi[0], px[k]);
+      lo[1] = fminf(lo[1], py[k]); hi[1] = fmaxf(hi[1], py[k]);
+      lo[2] = fminf(lo[2], pz[k]); hi[2] = fmaxf(hi[2], pz[k]);
+      nmax = fmaxf(nmax, sqnorm3(px[k], py[k], pz[k]));
+    } else {
+      px[k] = py[k] = pz[k] = 0.f;
     }
-    if ((tid & 31) == 0) {
-      red[k * 32 + (tid >> 5)] = a;
-      red[(3 + k) * 32 + (tid >> 5)] = b;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
     }
   }
   nmax = warp_max(nmax);
-  if ((tid & 31) == 0) red[6 * 32 + (tid >> 5)] = nmax;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      s.red[k * 8 + warp] = lo[k];
+      s.red[(3 + k) * 8 + warp] = hi[k];
+    }
+    s.red[6 * 8 + warp] = nmax;
+  }
+  // zero the cell counters meanwhile
+  for (int i = tid; i < GCELLS / 4; i += GT) reinterpret_cast<int4*>(s.scratch)[i] = make_int4(0, 0, 0, 0);
   __syncthreads();
-  const int nw = nt >> 5;
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
-    float a = red[k * 32], b = red[(3 + k) * 32];
-    for (int w = 1; w < nw; ++w) {
-      a = fminf(a, red[k * 32 + w]);
-      b = fmaxf(b, red[(3 + k) * 32 + w]);
+    float a = s.red[k * 8], b = s.red[(3 + k) * 8];
+#pragma unroll
+    for (int w = 1; w < GT / 32; ++w) {
+      a = fminf(a, s.red[k * 8 + w]);
+      b = fmaxf(b, s.red[(3 + k) * 8 + w]);
     }
     lo[k] = a;
     hi[k] = b;
   }
-  nmax = red[6 * 32];
-  for (int w = 1; w < nw; ++w) nmax = fmaxf(nmax, red[6 * 32 + w]);
-  __syncthreads();
+  nmax = s.red[6 * 8];
+#pragma unroll
+  for (int w = 1; w < GT / 32; ++w) nmax = fmaxf(nmax, s.red[6 * 8 + w]);
   const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+  g.uniform = (hi[0] == lo[0] && hi[1] == lo[1] && hi[2] == lo[2]) ? 1 : 0;
   g.E = 1e-5f * nmax;
   float h = h_req > 0.f ? h_req : ext / (float)target_per_axis;
   if (h_req > 0.f) h = sqrtf(h_req * h_req + g.E) * 1.001f;          // ball query: covers every point that can pass the fp32 test
@@ -82,107 +155,172 @@ __device__ void build_grid(const float* sx, const float* sy, const float* sz, co
   g.nx = min(GMAX, (int)((hi[0] - lo[0]) * g.inv_h) + 1);
   g.ny = min(GMAX, (int)((hi[1] - lo[1]) * g.inv_h) + 1);
   g.nz = min(GMAX, (int)((hi[2] - lo[2]) * g.inv_h) + 1);
-  const int ncell = g.nx * g.ny * g.nz;
-  int* cnt = s_tmp;  // [ncell]
-  for (int i = tid; i < ncell + 1; i += nt) cnt[i] = 0;
-  __syncthreads();
-  auto cell_of = [&](int i) {
-    const int cx = min(g.nx - 1, max(0, (int)((sx[i] - g.minx) * g.inv_h)));
-    const int cy = min(g.ny - 1, max(0, (int)((sy[i] - g.miny) * g.inv_h)));
-    const int cz = min(g.nz - 1, max(0, (int)((sz[i] - g.minz) * g.inv_h)));
-    return (cz * g.ny + cy) * g.nx + cx;
-  };
-  for (int i = tid; i < n_pts; i += nt) atomicAdd(&cnt[cell_of(i)], 1);
-  __syncthreads();
-  // exclusive scan of cnt[0..ncell) -> cell_start (one warp, 32 cells per lane step: ncell <= 4096)
-  if (tid < 32) {
-    int run = 0;
-    for (int b0 = 0; b0 < ncell; b0 += 32) {
-      const int i = b0 + tid;
-      const int v = i < ncell ? cnt[i] : 0;
-      int incl = v;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= o) incl += t;
-      }
-      if (i < ncell) cell_start[i] = run + incl - v;
-      run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (tid == 0) cell_start[ncell] = run;
-  }
-  __syncthreads();
-  for (int i = tid; i < ncell; i += nt) cnt[i] = cell_start[i];  // cursors
-  __syncthreads();
-  for (int i = tid; i < n_pts; i += nt) cell_pts[atomicAdd(&cnt[cell_of(i)], 1)] = (unsigned short)i;
-  __syncthreads();
-}
-
-__device__ __forceinline__ float sqdist_ref(float qx, float qy, float qz, float q2, float px, float py, float pz, float p2) {
-  const float dot = __fmaf_rn(qz, pz, __fmaf_rn(qy, py, __fmul_rn(qx, px)));
-  return __fadd_rn(__fmaf_rn(-2.0f, dot, q2), p2);  // fma(-2, dot, q2) == (-2 * dot) + q2 bit for bit (exact product)
-}
-
-// ---- ball query, N = 1024 source points, S centroids (1024 or 256), 32 samples ----
-constexpr int BG_T = 512;
-__global__ void __launch_bounds__(BG_T) ball_query_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int S, float radius,
-                                                               float r2, int* __restrict__ group) {
-  extern __shared__ unsigned char smem[];
-  float* sx = reinterpret_cast<float*>(smem);
-  float* sy = sx + GN;
-  float* sz = sy + GN;
-  float* sn2 = sz + GN;
-  int* cell_start = reinterpret_cast<int*>(sn2 + GN);          // [GCELLS + 1]
-  int* s_tmp = cell_start + GCELLS + 32;                        // [GCELLS + 64]
-  unsigned short* cell_pts = reinterpret_cast<unsigned short*>(s_tmp + GCELLS + 64);   // [GN]
-  unsigned* bits = reinterpret_cast<unsigned*>(cell_pts + GN);  // [32][BG_T]
-  const int c = blockIdx.x, tid = threadIdx.x;
-  const float* src = xyz + (int64_t)c * GN * 3;
-  for (int i = tid; i < GN; i += BG_T) {
-    const float x = src[i * 3], y = src[i * 3 + 1], z = src[i * 3 + 2];
-    sx[i] = x; sy[i] = y; sz[i] = z;
-    sn2[i] = sqnorm3(x, y, z);
-  }
-  __syncthreads();
-  __shared__ Grid g;
-  Grid gl;
-  build_grid(sx, sy, sz, sn2, GN, radius, 0, gl, cell_start, cell_pts, s_tmp);
-  if (tid == 0) g = gl;
-  __syncthreads();
-  gl = g;
-  for (int s = tid; s < S; s += BG_T) {
-    const float* q = new_xyz + ((int64_t)c * S + s) * 3;
-    const float qx = q[0], qy = q[1], qz = q[2], q2 = sqnorm3(qx, qy, qz);
+  // counting sort by cell: the atomic's return value is the point's rank inside its cell
+  int cell[GPER], rank[GPER];
 #pragma unroll
-    for (int w = 0; w < 32; ++w) bits[w * BG_T + tid] = 0u;
-    const int cx = min(gl.nx - 1, max(0, (int)((qx - gl.minx) * gl.inv_h)));
-    const int cy = min(gl.ny - 1, max(0, (int)((qy - gl.miny) * gl.inv_h)));
-    const int cz = min(gl.nz - 1, max(0, (int)((qz - gl.minz) * gl.inv_h)));
-    for (int z = max(0, cz - 1); z <= min(gl.nz - 1, cz + 1); ++z)
-      for (int y = max(0, cy - 1); y <= min(gl.ny - 1, cy + 1); ++y) {
-        const int row = (z * gl.ny + y) * gl.nx;
-        const int k0 = cell_start[row + max(0, cx - 1)], k1 = cell_start[row + min(gl.nx - 1, cx + 1) + 1];  // three x-adjacent cells are contiguous
-        for (int k = k0; k < k1; ++k) {
-          const int j = cell_pts[k];
-          const float d = sqdist_ref(qx, qy, qz, q2, sx[j], sy[j], sz[j], sn2[j]);
-          if (!(d > r2)) bits[(j >> 5) * BG_T + tid] |= 1u << (j & 31);
+  for (int k = 0; k < GPER; ++k) {
+    const int i = tid + k * GT;
+    const int cx = min(g.nx - 1, max(0, (int)((px[k] - g.minx) * g.inv_h)));
+    const int cy = min(g.ny - 1, max(0, (int)((py[k] - g.miny) * g.inv_h)));
+    const int cz = min(g.nz - 1, max(0, (int)((pz[k] - g.minz) * g.inv_h)));
+    cell[k] = (cz * g.ny + cy) * g.nx + cx;
+    rank[k] = i < n_pts ? atomicAdd(&s.scratch[cell[k]], 1) : 0;
+  }
+  __syncthreads();
+  cell_scan(s.scratch, s.cstart, reinterpret_cast<int*>(s.red));  // (the float reductions above were consumed before the last barrier)
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < GPER; ++k) {
+    const int i = tid + k * GT;
+    if (i < n_pts) {
+      const int pos = s.cstart[cell[k]] + rank[k];
+      s.pts[pos] = make_float4(px[k], py[k], pz[k], sqnorm3(px[k], py[k], pz[k]));
+      s.oidx[pos] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+}
+
+// Orders the cloud's queries by grid cell (counting sort, clamped cell of the query): consecutive threads then work on
+// neighbouring queries, whose candidate runs have similar lengths and the same shared-memory addresses (the walk below is
+// one divergent loop per thread).  order[i] = index of the i-th query; `counters` / `qstart` are scratch.
+__device__ void sort_queries(const float* __restrict__ qxyz, int n_q, const Grid& g, int* counters, unsigned short* qstart, int* wtot,
+                             unsigned short* order) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < GCELLS / 4; i += GT) reinterpret_cast<int4*>(counters)[i] = make_int4(0, 0, 0, 0);
+  __syncthreads();
+  int cell[GPER], rank[GPER];
+#pragma unroll
+  for (int k = 0; k < GPER; ++k) {
+    const int i = tid + k * GT;
+    cell[k] = 0;
+    rank[k] = 0;
+    if (i < n_q) {
+      const float x = qxyz[i * 3], y = qxyz[i * 3 + 1], z = qxyz[i * 3 + 2];
+      // (int) of a NaN / out-of-range float is clamped by the min / max below: any value is a valid sort key
+      const int cx = min(g.nx - 1, max(0, (int)((x - g.minx) * g.inv_h)));
+      const int cy = min(g.ny - 1, max(0, (int)((y - g.miny) * g.inv_h)));
+      const int cz = min(g.nz - 1, max(0, (int)((z - g.minz) * g.inv_h)));
+      cell[k] = (cz * g.ny + cy) * g.nx + cx;
+      rank[k] = atomicAdd(&counters[cell[k]], 1);
+    }
+  }
+  __syncthreads();
+  cell_scan(counters, qstart, wtot);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < GPER; ++k) {
+    const int i = tid + k * GT;
+    if (i < n_q) order[qstart[cell[k]] + rank[k]] = (unsigned short)i;
+  }
+  __syncthreads();
+}
+
+// ---- ball query: n_src (<= 1024) source points, S centroids, 32 samples ----
+// Output staging: four consecutive slots of a group leave as one 128-bit store.
+struct Emit {
+  int v0, v1, v2, v3, cnt, first;
+  int* out;
+  __device__ __forceinline__ void init(int* o, int none) { cnt = 0; first = none; out = o; v0 = v1 = v2 = v3 = 0; }
+  __device__ __forceinline__ void push(int j) {
+    if (cnt == 0) first = j;
+    v0 = v1; v1 = v2; v2 = v3; v3 = j;
+    ++cnt;
+    if ((cnt & 3) == 0) *reinterpret_cast<int4*>(out + cnt - 4) = make_int4(v0, v1, v2, v3);
+  }
+  __device__ __forceinline__ void pad() {  // remaining slots repeat the first hit
+    while (cnt & 3) push(first);
+    const int4 f = make_int4(first, first, first, first);
+    for (; cnt < 32; cnt += 4) *reinterpret_cast<int4*>(out + cnt) = f;
+  }
+};
+
+constexpr int BALL_INORDER_MIN = 480;  // candidates in the 3 x 3 x 3 block from which the index-order scan is expected to be shorter
+
+__global__ void __launch_bounds__(GT) ball_query_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int n_src, int S,
+                                                             float radius, float r2, int* __restrict__ group) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  GridSmem s;
+  s.pts = reinterpret_cast<float4*>(smem);
+  s.oidx = reinterpret_cast<unsigned short*>(s.pts + GN);
+  s.cstart = s.oidx + GN;
+  unsigned* bits = reinterpret_cast<unsigned*>(s.cstart + GCELLS + 8);  // [32][GT]: bit j of thread t's hit set in word (j >> 5) * GT + t
+  s.scratch = reinterpret_cast<int*>(bits);                             // 16 KB of the 32 KB bitmap
+  s.red = reinterpret_cast<float*>(bits + 32 * GT);
+  unsigned short* order = reinterpret_cast<unsigned short*>(s.red + 64);  // [GN] queries in cell order
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const float* src = xyz + (int64_t)c * n_src * 3;
+  Grid g;
+  build_grid(src, n_src, radius, 0, g, s);
+  sort_queries(new_xyz + (int64_t)c * S * 3, S, g, s.scratch, reinterpret_cast<unsigned short*>(bits + GCELLS), reinterpret_cast<int*>(s.red), order);
+  for (int i = tid; i < 32 * GT; i += GT) bits[i] = 0u;  // (the counters and the query offsets lived here)
+  __syncthreads();
+  const uint32_t a_pts = smem_addr(s.pts), a_oidx = smem_addr(s.oidx), a_cs = smem_addr(s.cstart), a_bits = smem_addr(bits) + tid * 4;
+  for (int qi = tid; qi < S; qi += GT) {
+    const int q = order[qi];
+    const float* qp = new_xyz + ((int64_t)c * S + q) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2], q2 = sqnorm3(qx, qy, qz);
+    Emit em;
+    em.init(group + ((int64_t)c * S + q) * 32, n_src);
+    const int cx = min(g.nx - 1, max(0, (int)((qx - g.minx) * g.inv_h)));
+    const int cy = min(g.ny - 1, max(0, (int)((qy - g.miny) * g.inv_h)));
+    const int cz = min(g.nz - 1, max(0, (int)((qz - g.minz) * g.inv_h)));
+    const int x0 = max(0, cx - 1), x1 = min(g.nx - 1, cx + 1) + 1;
+    const int y0 = max(0, cy - 1), y1 = min(g.ny - 1, cy + 1);
+    const int z0 = max(0, cz - 1), z1 = min(g.nz - 1, cz + 1);
+    int total = 0;
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const int row = (z * g.ny + y) * g.nx;
+        total += (int)lds_u16(a_cs + (row + x1) * 2) - (int)lds_u16(a_cs + (row + x0) * 2);
+      }
+    if (total >= BALL_INORDER_MIN) {
+      // a large share of the cloud is within reach: scanning in index order stops at the 32nd hit
+      for (int j = 0; j < n_src && em.cnt < 32; ++j) {
+        const float x = src[j * 3], y = src[j * 3 + 1], z = src[j * 3 + 2];
+        const float d = sqdist_ref(qx, qy, qz, q2, x, y, z, sqnorm3(x, y, z));
+        if (!(d > r2)) em.push(j);
+      }
+    } else {
+      unsigned dirty = 0u;
+      int z = z0, y = y0 - 1, k = 0, kend = 0;
+      for (;;) {
+        if (k >= kend) {  // next (z, y) row: three x-adjacent cells are one contiguous run
+          if (++y > y1) {
+            y = y0;
+            if (++z > z1) break;
+          }
+          const int row = (z * g.ny + y) * g.nx;
+          k = (int)lds_u16(a_cs + (row + x0) * 2);
+          kend = (int)lds_u16(a_cs + (row + x1) * 2);
+          continue;
+        }
+        const float4 p = lds_f4(a_pts + k * 16);
+        const float d = sqdist_ref(qx, qy, qz, q2, p.x, p.y, p.z, p.w);
+        if (!(d > r2)) {
+          const int j = (int)lds_u16(a_oidx + k * 2);
+          const uint32_t a = a_bits + (j >> 5) * (GT * 4);
+          sts_u32(a, lds_u32(a) | (1u << (j & 31)));
+          dirty |= 1u << (j >> 5);
+        }
+        ++k;
+      }
+      while (dirty) {  // ascending words, ascending bits: index order
+        const int w = __ffs(dirty) - 1;
+        dirty &= dirty - 1;
+        unsigned b = lds_u32(a_bits + w * (GT * 4));
+        sts_u32(a_bits + w * (GT * 4), 0u);
+        while (b && em.cnt < 32) {
+          em.push(w * 32 + __ffs(b) - 1);
+          b &= b - 1;
         }
       }
-    int* out = group + ((int64_t)c * S + s) * 32;
-    int cnt = 0, first = GN;
-    for (int w = 0; w < 32 && cnt < 32; ++w) {
-      unsigned b = bits[w * BG_T + tid];
-      while (b && cnt < 32) {
-        const int j = w * 32 + __ffs(b) - 1;
-        b &= b - 1;
-        if (cnt == 0) first = j;
-        out[cnt++] = j;
-      }
     }
-    for (int k = cnt; k < 32; ++k) out[k] = first;
+    em.pad();
   }
 }
 
-// ---- 3-NN: N fine points (1024), S coarse points (1024 or 256) ----
+// ---- 3-NN: N fine points, S (<= 1024) coarse points ----
 struct Top3L {  // ranked by (distance, index)
   float d0, d1, d2;
   int i0, i1, i2;
@@ -192,6 +330,7 @@ struct Top3L {  // ranked by (distance, index)
   }
   __device__ __forceinline__ static bool lt(float d, int s, float D, int I) { return d < D || (d == D && s < I); }
   __device__ __forceinline__ void push(float d, int s) {
+    if (!(d <= d2)) return;  // (the common case once three close candidates are known)
     if (lt(d, s, d2, i2)) {
       if (lt(d, s, d1, i1)) {
         d2 = d1; i2 = i1;
@@ -202,69 +341,98 @@ struct Top3L {  // ranked by (distance, index)
   }
 };
 
-constexpr int NG_T = 256;
-__global__ void __launch_bounds__(NG_T) three_nn_grid_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, int N, int S,
-                                                             int* __restrict__ nn_idx, float* __restrict__ nn_w) {
-  extern __shared__ unsigned char smem[];
-  float* sx = reinterpret_cast<float*>(smem);
-  float* sy = sx + GN;
-  float* sz = sy + GN;
-  float* sn2 = sz + GN;
-  int* cell_start = reinterpret_cast<int*>(sn2 + GN);
-  int* s_tmp = cell_start + GCELLS + 32;
-  unsigned short* cell_pts = reinterpret_cast<unsigned short*>(s_tmp + GCELLS + 64);
+__global__ void __launch_bounds__(GT) three_nn_grid_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, int N, int S,
+                                                           int target, int* __restrict__ nn_idx, float* __restrict__ nn_w) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  GridSmem s;
+  s.pts = reinterpret_cast<float4*>(smem);
+  s.oidx = reinterpret_cast<unsigned short*>(s.pts + GN);
+  s.cstart = s.oidx + GN;
+  s.scratch = reinterpret_cast<int*>(s.cstart + GCELLS + 8);
+  s.red = reinterpret_cast<float*>(s.scratch + GCELLS);
+  unsigned short* order = reinterpret_cast<unsigned short*>(s.red + 64);  // [GN] queries in cell order
+  unsigned short* qstart = order + GN;                                     // [GCELLS + 8]
   const int c = blockIdx.x, tid = threadIdx.x;
   const float* src = xyz2 + (int64_t)c * S * 3;
-  for (int i = tid; i < S; i += NG_T) {
-    const float x = src[i * 3], y = src[i * 3 + 1], z = src[i * 3 + 2];
-    sx[i] = x; sy[i] = y; sz[i] = z;
-    sn2[i] = sqnorm3(x, y, z);
-  }
-  __syncthreads();
-  __shared__ Grid g;
-  Grid gl;
-  build_grid(sx, sy, sz, sn2, S, 0.f, S >= 1024 ? 8 : 5, gl, cell_start, cell_pts, s_tmp);
-  if (tid == 0) g = gl;
-  __syncthreads();
-  gl = g;
-  const int rmax = max(gl.nx, max(gl.ny, gl.nz));
-  for (int n = tid; n < N; n += NG_T) {
+  Grid g;
+  build_grid(src, S, 0.f, target, g, s);
+  sort_queries(xyz1 + (int64_t)c * N * 3, N, g, s.scratch, qstart, reinterpret_cast<int*>(s.red), order);
+  const uint32_t a_pts = smem_addr(s.pts), a_oidx = smem_addr(s.oidx), a_cs = smem_addr(s.cstart);
+  const int rmax = max(g.nx, max(g.ny, g.nz));
+  for (int ni = tid; ni < N; ni += GT) {
+    const int n = order[ni];
     const float* q = xyz1 + ((int64_t)c * N + n) * 3;
     const float qx = q[0], qy = q[1], qz = q[2], q2 = sqnorm3(qx, qy, qz);
-    // the query may lie outside the coarse points' bounding box: its (unclamped) cell coordinates define the rings
-    const int cx = (int)floorf((qx - gl.minx) * gl.inv_h), cy = (int)floorf((qy - gl.miny) * gl.inv_h), cz = (int)floorf((qz - gl.minz) * gl.inv_h);
     Top3L t;
     t.init();
-    for (int ring = 0;; ++ring) {
-      const int z0 = max(0, cz - ring), z1 = min(gl.nz - 1, cz + ring), y0 = max(0, cy - ring), y1 = min(gl.ny - 1, cy + ring);
-      const int x0 = max(0, cx - ring), x1 = min(gl.nx - 1, cx + ring);
-      for (int z = z0; z <= z1; ++z)
-        for (int y = y0; y <= y1; ++y) {
-          const bool shell_zy = (abs(z - cz) == ring) || (abs(y - cy) == ring);
-          const int row = (z * gl.ny + y) * gl.nx;
-          if (shell_zy) {  // the whole x range of this row belongs to the ring's shell
-            if (x0 <= x1)
-              for (int k = cell_start[row + x0]; k < cell_start[row + x1 + 1]; ++k) {
-                const int j = cell_pts[k];
-                t.push(sqdist_ref(qx, qy, qz, q2, sx[j], sy[j], sz[j], sn2[j]), j);
+    if (g.uniform) {
+      // all coarse points coincide: every distance is the same value, the (distance, index) ranking keeps indices 0, 1, 2
+      for (int j = 0; j < 3; ++j) {
+        const float x = src[j * 3], y = src[j * 3 + 1], z = src[j * 3 + 2];
+        t.push(sqdist_ref(qx, qy, qz, q2, x, y, z, sqnorm3(x, y, z)), j);
+      }
+    } else {
+      // the query may lie outside the coarse points' bounding box: its (unclamped) cell coordinates define the rings
+      const int cx = (int)floorf((qx - g.minx) * g.inv_h), cy = (int)floorf((qy - g.miny) * g.inv_h), cz = (int)floorf((qz - g.minz) * g.inv_h);
+      const float slack = fmaxf(g.E, 1e-5f * q2);
+      {
+        // rings 0 and 1 together: the 3 x 3 x 3 block as up to nine contiguous runs, one flattened loop
+        const int x0 = max(0, cx - 1), x1 = min(g.nx - 1, cx + 1) + 1;
+        const int y0 = max(0, cy - 1), y1 = min(g.ny - 1, cy + 1);
+        const int z0 = max(0, cz - 1), z1 = min(g.nz - 1, cz + 1);
+        if (x0 < x1 && y0 <= y1 && z0 <= z1) {
+          int z = z0, y = y0 - 1, k = 0, kend = 0;
+          for (;;) {
+            if (k >= kend) {
+              if (++y > y1) {
+                y = y0;
+                if (++z > z1) break;
               }
-          } else {         // only the two end cells at x = cx -+ ring
-            for (int e = 0; e < 2; ++e) {
-              const int x = e == 0 ? cx - ring : cx + ring;
-              if (x < 0 || x >= gl.nx || (e == 1 && ring == 0)) continue;
-              for (int k = cell_start[row + x]; k < cell_start[row + x + 1]; ++k) {
-                const int j = cell_pts[k];
-                t.push(sqdist_ref(qx, qy, qz, q2, sx[j], sy[j], sz[j], sn2[j]), j);
-              }
+              const int row = (z * g.ny + y) * g.nx;
+              k = (int)lds_u16(a_cs + (row + x0) * 2);
+              kend = (int)lds_u16(a_cs + (row + x1) * 2);
+              continue;
             }
+            const float4 p = lds_f4(a_pts + k * 16);
+            const float d = sqdist_ref(qx, qy, qz, q2, p.x, p.y, p.z, p.w);
+            if (d <= t.d2) t.push(d, (int)lds_u16(a_oidx + k * 2));
+            ++k;
           }
         }
-      // every unvisited point is more than (ring - 1e-4) cells away along some axis
-      const float reach = ((float)ring - 1e-4f) * gl.h;
-      const bool covered = (cx - ring <= 0 && cx + ring >= gl.nx - 1) && (cy - ring <= 0 && cy + ring >= gl.ny - 1) && (cz - ring <= 0 && cz + ring >= gl.nz - 1);
-      if (covered) break;
-      if (ring >= 1 && t.d2 < reach * reach - fmaxf(gl.E, 1e-5f * q2)) break;
-      if (ring > 2 * rmax + 64) break;  // (unreachable: `covered` ends the search; guards against a query far outside the box)
+      }
+      for (int ring = 1;; ++ring) {
+        if (ring >= 2) {  // the shell of cells at Chebyshev distance `ring`
+          const int z0 = max(0, cz - ring), z1 = min(g.nz - 1, cz + ring), y0 = max(0, cy - ring), y1 = min(g.ny - 1, cy + ring);
+          const int x0 = max(0, cx - ring), x1 = min(g.nx - 1, cx + ring);
+          for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+              const bool shell_zy = (abs(z - cz) == ring) || (abs(y - cy) == ring);
+              const int row = (z * g.ny + y) * g.nx;
+              if (shell_zy) {  // the whole x range of this row belongs to the shell
+                if (x0 <= x1)
+                  for (int k = (int)lds_u16(a_cs + (row + x0) * 2), ke = (int)lds_u16(a_cs + (row + x1 + 1) * 2); k < ke; ++k) {
+                    const float4 p = lds_f4(a_pts + k * 16);
+                    t.push(sqdist_ref(qx, qy, qz, q2, p.x, p.y, p.z, p.w), (int)lds_u16(a_oidx + k * 2));
+                  }
+              } else {         // only the two end cells at x = cx -+ ring
+                for (int e = 0; e < 2; ++e) {
+                  const int x = e == 0 ? cx - ring : cx + ring;
+                  if (x < 0 || x >= g.nx) continue;
+                  for (int k = (int)lds_u16(a_cs + (row + x) * 2), ke = (int)lds_u16(a_cs + (row + x + 1) * 2); k < ke; ++k) {
+                    const float4 p = lds_f4(a_pts + k * 16);
+                    t.push(sqdist_ref(qx, qy, qz, q2, p.x, p.y, p.z, p.w), (int)lds_u16(a_oidx + k * 2));
+                  }
+                }
+              }
+            }
+        }
+        // every unvisited point is more than (ring - 1e-4) cells away along some axis
+        const float reach = ((float)ring - 1e-4f) * g.h;
+        const bool covered = (cx - ring <= 0 && cx + ring >= g.nx - 1) && (cy - ring <= 0 && cy + ring >= g.ny - 1) && (cz - ring <= 0 && cz + ring >= g.nz - 1);
+        if (covered) break;
+        if (t.d2 < reach * reach - slack) break;
+        if (ring > 2 * rmax + 64) break;  // (unreachable: `covered` ends the search; guards against a query far outside the box)
+      }
     }
     const float r0 = 1.0f / (t.d0 + 1e-8f), r1 = 1.0f / (t.d1 + 1e-8f), r2 = 1.0f / (t.d2 + 1e-8f);
     const float norm = (r0 + r1) + r2;
@@ -274,26 +442,30 @@ __global__ void __launch_bounds__(NG_T) three_nn_grid_kernel(const float* __rest
   }
 }
 
+constexpr int GRID_SMEM_BASE = GN * 16 + GN * 2 + (GCELLS + 8) * 2;
+
 }  // namespace
 
-// N must be 1024.  Same output as launch_ball_query.
+// N (source points) must be <= 1024.  Same output as launch_ball_query.
 int launch_ball_query_grid(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group, cudaStream_t st) {
-  if (N != GN) return -1;
+  if (N > GN || N < 1) return -1;
   const float r2 = (float)(radius * radius);
-  constexpr int smem = 4 * GN * 4 + (GCELLS + 32) * 4 + (GCELLS + 64) * 4 + GN * 2 + 32 * BG_T * 4;
+  if (S > GN) return -1;
+  constexpr int smem = GRID_SMEM_BASE + 32 * GT * 4 + 64 * 4 + GN * 2;
   static PerDeviceOnce attr_done;
   if (smem_opt_in(attr_done, ball_query_grid_kernel, smem) != cudaSuccess) return -1;
-  ball_query_grid_kernel<<<n_clouds, BG_T, smem, st>>>(xyz, new_xyz, S, (float)radius, r2, group);
+  ball_query_grid_kernel<<<n_clouds, GT, smem, st>>>(xyz, new_xyz, N, S, (float)radius, r2, group);
   return 1;
 }
 
-// S (coarse points) must be <= 1024.  Same output as launch_three_nn.
+// S (coarse points) must be in [3, 1024].  Same output as launch_three_nn.
 int launch_three_nn_grid(const float* xyz1, const float* xyz2, int n_clouds, int N, int S, int* nn_idx, float* nn_w, cudaStream_t st) {
-  if (S > GN || S < 3) return -1;
-  constexpr int smem = 4 * GN * 4 + (GCELLS + 32) * 4 + (GCELLS + 64) * 4 + GN * 2;
+  if (S > GN || S < 3 || N > GN) return -1;
+  constexpr int smem = GRID_SMEM_BASE + GCELLS * 4 + 64 * 4 + GN * 2 + (GCELLS + 8) * 2;
   static PerDeviceOnce attr_done;
   if (smem_opt_in(attr_done, three_nn_grid_kernel, smem) != cudaSuccess) return -1;
-  three_nn_grid_kernel<<<n_clouds, NG_T, smem, st>>>(xyz1, xyz2, N, S, nn_idx, nn_w);
+  const int target = S >= 1024 ? 8 : (S >= 256 ? 5 : 3);  // about two coarse points per cell in a filled cube
+  three_nn_grid_kernel<<<n_clouds, GT, smem, st>>>(xyz1, xyz2, N, S, target, nn_idx, nn_w);
   return 1;
 }
 

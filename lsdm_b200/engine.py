@@ -65,7 +65,8 @@ class Engine:
         self.set_option("dedup_absent", int(os.environ.get("LSDM_DEDUP_ABSENT", "1")))
         self.set_option("x0_fused", int(os.environ.get("LSDM_X0_FUSED", "1")))
         self.set_option("sa1_compact", int(os.environ.get("LSDM_SA1_COMPACT", "1")))
-        self.set_option("select_grid", int(os.environ.get("LSDM_SELECT_GRID", "1")))
+        self.set_option("select_grid", int(os.environ.get("LSDM_SELECT_GRID", "9")))
+        self.set_option("cond_stream", int(os.environ.get("LSDM_COND_STREAM", "1")))
 
     # ------------------------------------------------------------------ lifecycle
     @_on_device
