@@ -129,8 +129,8 @@ struct lsdm_handle {
   Workspace ws{};
   bool have_ws = false;
   int64_t launches = 0;
-  cudaStream_t side = nullptr, dense_st = nullptr, cond_st = nullptr;
-  cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr;  // condition MLPs + human decoder beside the selection chain (cond_stream)
+  cudaStream_t side = nullptr, dense_st = nullptr, cond_st = nullptr, nn_st = nullptr;
+  cudaEvent_t ev_cfork = nullptr, ev_cjoin = nullptr, ev_fps = nullptr, ev_nn = nullptr;  // (nn_st: the 3-NN chain beside the ball queries, both only need the FPS result)  // condition MLPs + human decoder beside the selection chain (cond_stream)
   int cond_stream = 1;  // 1: in the pipelined loop the per-sample condition MLPs / human decoder run on their own stream, overlapping the FPS chain
   cudaEvent_t ev_fork = nullptr, ev_sel[3] = {nullptr, nullptr, nullptr}, ev_dense[3] = {nullptr, nullptr, nullptr},
               ev_step[3] = {nullptr, nullptr, nullptr};
@@ -457,26 +457,47 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   prof_launch(h, st, K_FPS, [&] { return launch_fps4(clouds, q.fps_start, C, q.idx[0], q.idx[1], q.idx[2], q.idx[3], q.xyz[1], q.xyz[2],
                                                      q.xyz[3], q.xyz[4], st); });
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
+  static const bool fork_nn_env = !(getenv("LSDM_NN_STREAM") && atoi(getenv("LSDM_NN_STREAM")) == 0);
+  const bool fork_nn = fork_cond && fork_nn_env;  // ball queries and 3-NN searches both depend on the FPS result only: two streams
+  if (fork_nn) {
+    CK(cudaEventRecord(h->ev_fps, st));
+    CK(cudaStreamWaitEvent(h->nn_st, h->ev_fps, 0));
+  }
+  const bool want_plan = h->sa1_compact && h->precision >= 1 && h->sa_fused > 0;
+  bool plan_done = false;
   for (int l = 0; l < 4; ++l)
     prof_launch(h, st, K_BALL, [&] {
       if (l <= 1 && ((h->select_grid >> l) & 1)) {  // levels 0 and 1: cell grid instead of the 1024 x 1024 / 256 x 1024 scan (identical groups)
-        const int r = launch_ball_query_grid(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st);
-        if (r > 0) return r;
+        const bool with_plan = l == 0 && want_plan;  // the level-0 grid kernel also writes the plan of sa1's distinct rows
+        const int r = launch_ball_query_grid(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st,
+                                             with_plan ? q.plan_rows : nullptr, q.plan_used, q.plan_tiles);
+        if (r > 0) {
+          if (with_plan) plan_done = true;
+          return r;
+        }
       }
       return launch_ball_query(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st);
     });
-  if (h->sa1_compact && h->precision >= 1 && h->sa_fused > 0)
-    prof_launch(h, st, K_BALL, [&] { return launch_sa1_plan(q.grp[0], C, q.plan_rows, q.plan_used, q.plan_tiles, q.plan_off, q.plan_n, st); });
+  if (want_plan)
+    prof_launch(h, st, K_BALL, [&] {
+      if (plan_done) return launch_sa1_plan_scan(q.plan_tiles, C, q.plan_off, q.plan_n, st);
+      return launch_sa1_plan(q.grp[0], C, q.plan_rows, q.plan_used, q.plan_tiles, q.plan_off, q.plan_n, st);
+    });
   const int fine[4] = {3, 2, 1, 0}, coarse[4] = {4, 3, 2, 1};
   const int fineN[4] = {64, 256, 1024, 1024}, coarseN[4] = {16, 64, 256, 1024};
-  for (int l = 0; l < 4; ++l)
-    prof_launch(h, st, K_3NN, [&] {
+  cudaStream_t nst = fork_nn ? h->nn_st : st;
+  for (int l = 3; l >= 0; --l)  // (largest search first when it has its own stream)
+    prof_launch(h, nst, K_3NN, [&] {
       if (l >= 2 && ((h->select_grid >> l) & 1)) {  // fp2 (1024 <- 256) and fp1 (1024 <- 1024)
-        const int r = launch_three_nn_grid(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st);
+        const int r = launch_three_nn_grid(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], nst);
         if (r > 0) return r;
       }
-      return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], st);
+      return launch_three_nn(xyz[fine[l]], xyz[coarse[l]], C, fineN[l], coarseN[l], q.nn_idx[l], q.nn_w[l], nst);
     });
+  if (fork_nn) {
+    CK(cudaEventRecord(h->ev_nn, h->nn_st));
+    CK(cudaStreamWaitEvent(st, h->ev_nn, 0));
+  }
   if (fork_cond) CK(cudaStreamWaitEvent(st, h->ev_cjoin, 0));
   CK(cudaPeekAtLastError());
   return LSDM_OK;
@@ -817,6 +838,9 @@ LSDM_API int lsdm_create(lsdm_handle** out, const lsdm_config* cfg) {
   cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, (pmode == 1 || pmode == 2) ? prio_hi : prio_lo);
   cudaStreamCreateWithPriority(&h->dense_st, cudaStreamNonBlocking, pmode >= 2 ? prio_hi : prio_lo);
   cudaStreamCreateWithPriority(&h->cond_st, cudaStreamNonBlocking, prio_lo);
+  cudaStreamCreateWithPriority(&h->nn_st, cudaStreamNonBlocking, prio_lo);
+  cudaEventCreateWithFlags(&h->ev_fps, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_nn, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_cfork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_cjoin, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -840,6 +864,9 @@ LSDM_API void lsdm_destroy(lsdm_handle* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->dense_st) cudaStreamDestroy(h->dense_st);
   if (h->cond_st) cudaStreamDestroy(h->cond_st);
+  if (h->nn_st) cudaStreamDestroy(h->nn_st);
+  if (h->ev_fps) cudaEventDestroy(h->ev_fps);
+  if (h->ev_nn) cudaEventDestroy(h->ev_nn);
   if (h->ev_cfork) cudaEventDestroy(h->ev_cfork);
   if (h->ev_cjoin) cudaEventDestroy(h->ev_cjoin);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1266,6 +1293,8 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
         CK(cudaStreamWaitEvent(side, h->ev_step[sn], 0));
       }
       tl_begin(k + 1, 'S', side);
+      static const int dbg_skip = getenv("LSDM_DEBUG_SKIP") ? atoi(getenv("LSDM_DEBUG_SKIP")) : 0;  // timing experiments only (results are garbage): 1 = no selection after step 0, 2 = no dense phase after step 2
+      if (!(dbg_skip & 1))
       GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active, fork_cond));
       tl_end(side);
       CK(cudaEventRecord(h->ev_sel[sn], side));
@@ -1277,6 +1306,8 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
         CK(cudaStreamWaitEvent(dst, h->ev_sel[si], 0));  // (select(k) already waited for step(k-3), the last reader of pcd_out[si])
       }
       tl_begin(k, 'D', dst);
+      static const int dbg_skip2 = getenv("LSDM_DEBUG_SKIP") ? atoi(getenv("LSDM_DEBUG_SKIP")) : 0;
+      if (!((dbg_skip2 & 2) && k >= 3))
       GE(encode_dense(h, text, objs, cats, mask_global, si, dst, nullptr, clouds, nc, remap));
       tl_end(dst);
       if (pipelined) {

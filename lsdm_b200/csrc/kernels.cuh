@@ -16,7 +16,8 @@ int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, i
                     cudaStream_t st);
 
 // ---- pointnet_grid.cu: cell-grid forms of the two scans for 1024 source points (identical results) ----
-int launch_ball_query_grid(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group, cudaStream_t st);
+int launch_ball_query_grid(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group, cudaStream_t st,
+                           int* plan_rows = nullptr, int* plan_used = nullptr, int* plan_tiles = nullptr);
 int launch_three_nn_grid(const float* xyz1, const float* xyz2, int n_clouds, int N, int S, int* nn_idx, float* nn_w, cudaStream_t st);
 
 // ---- pointnet_glue.cu -----------------------------------------------------------------------
@@ -49,6 +50,7 @@ int launch_sa_fused_v2(int level, const float* P, const float* xyz, const float*
 // sa1 on the DISTINCT rows of every group only (the ball query pads with the first hit; the max-pool ignores duplicates):
 // plan (selection stream) + the fused kernel on the packed tiles.  Bit-identical to launch_sa_fused_v2(level 0).
 int launch_sa1_plan(const int* grp, int n_clouds, int* rows, int* tile_used, int* tiles, int* tile_off, int* n_tiles, cudaStream_t st);
+int launch_sa1_plan_scan(const int* tiles, int n_clouds, int* tile_off, int* n_tiles, cudaStream_t st);  // when the ball query wrote the plan
 int launch_sa1_compact(const float* xyz, const float* new_xyz, const int* rows, const int* tile_used, const int* tile_off, const int* n_tiles,
                        const float* h_wx, const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
                        int n_clouds, float* out, int round_out, cudaStream_t st);

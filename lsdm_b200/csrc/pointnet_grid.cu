@@ -237,8 +237,19 @@ struct Emit {
 
 constexpr int BALL_INORDER_MIN = 480;  // candidates in the 3 x 3 x 3 block from which the index-order scan is expected to be shorter
 
+// Optional plan of sa1's distinct rows (Sa1PlanOut, S == 1024 only): what sa1_plan_kernel (sa_fused.cu) derives from the
+// finished groups -- per centroid the number of distinct neighbours, the centroids of each block of 128 packed greedily into
+// 64-row half tiles, the (neighbour | centroid << 10 | first-row flag << 20) row words -- written by the block that has just
+// produced the groups, so the 39 MB of group lists are not read back by a second kernel.  Same layout, same tiles.
+struct Sa1PlanOut {
+  int* rows;       // [C, 256 * 128]
+  int* tile_used;  // [C, 256]
+  int* tiles;      // [C]
+};
+constexpr int PLAN_MAXT = 256;
+
 __global__ void __launch_bounds__(GT) ball_query_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int n_src, int S,
-                                                             float radius, float r2, int* __restrict__ group) {
+                                                             float radius, float r2, int* __restrict__ group, Sa1PlanOut plan) {
   extern __shared__ __align__(16) unsigned char smem[];
   GridSmem s;
   s.pts = reinterpret_cast<float4*>(smem);
@@ -248,6 +259,7 @@ __global__ void __launch_bounds__(GT) ball_query_grid_kernel(const float* __rest
   s.scratch = reinterpret_cast<int*>(bits);                             // 16 KB of the 32 KB bitmap
   s.red = reinterpret_cast<float*>(bits + 32 * GT);
   unsigned short* order = reinterpret_cast<unsigned short*>(s.red + 64);  // [GN] queries in cell order
+  unsigned short* qcnt = order + GN;                                       // [GN] distinct neighbours per centroid (plan)
   const int c = blockIdx.x, tid = threadIdx.x;
   const float* src = xyz + (int64_t)c * n_src * 3;
   Grid g;
@@ -316,7 +328,122 @@ __global__ void __launch_bounds__(GT) ball_query_grid_kernel(const float* __rest
         }
       }
     }
+    if (plan.rows) qcnt[q] = (unsigned short)max(em.cnt, 1);
     em.pad();
+  }
+  if (plan.rows == nullptr) return;
+  // ---- sa1 plan (S == 1024): the bitmap memory is free now ----
+  __syncthreads();  // every group of the cloud is written (block-visible), every count is in qcnt
+  int* s_slot = reinterpret_cast<int*>(bits);      // [1024]
+  int* s_gtiles = s_slot + 1024;                   // [8]
+  int* s_used = s_gtiles + 8;                      // [8][32]
+  int block_rows = 0;  // distinct rows of this warp's block of 128 centroids
+  {
+    // Rows are packed into 64-row HALF tiles (a centroid never straddles a half: each half of the CTA pools its own 64
+    // columns), greedily in centroid order, independently per block of 128 centroids: one warp per block.  Lane l holds the
+    // counts of centroids 4l .. 4l + 3 and their inclusive prefix sums P; a half that starts at element `start` with `base`
+    // rows before it ends at the first element with P - base > 64 (ballot + ffs): one warp-uniform step per half tile.
+    const int gq = tid >> 5, lane = tid & 31;
+    const uint2 pk = reinterpret_cast<const uint2*>(qcnt)[gq * 32 + lane];
+    const int cn[4] = {(int)(pk.x & 0xffffu), (int)(pk.x >> 16), (int)(pk.y & 0xffffu), (int)(pk.y >> 16)};
+    int P[4];
+    P[0] = cn[0]; P[1] = P[0] + cn[1]; P[2] = P[1] + cn[2]; P[3] = P[2] + cn[3];
+    int incl = P[3];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    block_rows = total;
+    const int off = incl - P[3];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) P[e] += off;
+    int slot[4] = {0, 0, 0, 0};
+    int half = 0, base = 0, start = 0;
+    unsigned usedw = 0u;  // lane t: tile t of the block, rows used in the low half | in the high half << 8
+    for (;;) {
+      int first = 4, before = 0;  // this lane's first element of the half that does not fit, and the rows in front of it
+#pragma unroll
+      for (int e = 3; e >= 0; --e)
+        if (lane * 4 + e >= start && P[e] - base > 64) { first = e; before = P[e] - cn[e]; }
+      const unsigned m = __ballot_sync(0xffffffffu, first < 4);
+      const int L = m ? __ffs(m) - 1 : 0;
+      const int brk = m ? L * 4 + __shfl_sync(0xffffffffu, first, L) : 128;
+      const int next_base = m ? __shfl_sync(0xffffffffu, before, L) : total;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (lane * 4 + e >= start && lane * 4 + e < brk) slot[e] = half * 64 + (P[e] - cn[e] - base);  // relative to the block's first tile
+      if (lane == (half >> 1)) usedw |= (unsigned)(next_base - base) << ((half & 1) * 8);
+      if (!m) break;
+      ++half;
+      base = next_base;
+      start = brk;
+    }
+    *reinterpret_cast<int4*>(s_slot + gq * 128 + lane * 4) = make_int4(slot[0], slot[1], slot[2], slot[3]);
+    s_used[gq * 32 + lane] = (int)usedw;
+    if (lane == 0) s_gtiles[gq] = (half >> 1) + 1;
+  }
+  __syncthreads();
+  {
+    const int gg = tid >> 5, t = tid & 31;  // 256 threads: (group of 128 centroids, tile of the group)
+    int o = 0;
+    for (int i = 0; i < gg; ++i) o += s_gtiles[i];
+    if (t < s_gtiles[gg]) plan.tile_used[c * PLAN_MAXT + o + t] = s_used[gg * 32 + t];
+    if (tid == 0) {
+      int tot = 0;
+      for (int i = 0; i < 8; ++i) tot += s_gtiles[i];
+      plan.tiles[c] = tot;
+    }
+  }
+  // Row words.  Sparse blocks (the usual case, ~5 rows per centroid): one lane per ROW of the block's tiles -- consecutive
+  // lanes write consecutive words (a lane per centroid would scatter 4-byte stores over as many sectors); the centroid of a
+  // row is the last one whose first slot is not past it.  Dense blocks (balls that hold most of the cloud): one lane per
+  // centroid, whole 128-byte groups.
+  {
+    const int gq = tid >> 5, lane = tid & 31;
+    int t0 = 0;
+    for (int i = 0; i < gq; ++i) t0 += s_gtiles[i];
+    int* dstg = plan.rows + (int64_t)c * (PLAN_MAXT * 128) + t0 * 128;
+    const int* slotg = s_slot + gq * 128;
+    if (block_rows > 128 * 12) {
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        const int sl = lane + 32 * u, sc = gq * 128 + sl, cnt = qcnt[sc], tag = sc << 10;
+        const int4* row = reinterpret_cast<const int4*>(group + ((int64_t)c * GN + sc) * 32);
+        int4 v[8];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) v[q4] = row[q4];
+        int* dst = dstg + slotg[sl];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const int e[4] = {v[q4].x, v[q4].y, v[q4].z, v[q4].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (q4 * 4 + k < cnt) dst[q4 * 4 + k] = e[k] | tag | (q4 * 4 + k == 0 ? 1 << 20 : 0);
+        }
+      }
+    } else {
+      const int npos = s_gtiles[gq] * 128;
+      for (int p0 = lane; p0 < npos; p0 += 128) {
+        int word[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // four independent rows per lane in flight
+          const int pos = p0 + 32 * u;
+          int lo = 0;
+#pragma unroll
+          for (int step = 64; step >= 1; step >>= 1)
+            if (slotg[lo + step] <= pos) lo += step;
+          const int sc = gq * 128 + lo, k = pos - slotg[lo];
+          ok[u] = pos < npos && k < (int)qcnt[sc];
+          word[u] = ok[u] ? (group[((int64_t)c * GN + sc) * 32 + k] | (sc << 10) | (k == 0 ? 1 << 20 : 0)) : 0;  // neighbour | centroid << 10 | first-row flag << 20
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) dstg[p0 + 32 * u] = word[u];
+      }
+    }
   }
 }
 
@@ -447,14 +574,17 @@ constexpr int GRID_SMEM_BASE = GN * 16 + GN * 2 + (GCELLS + 8) * 2;
 }  // namespace
 
 // N (source points) must be <= 1024.  Same output as launch_ball_query.
-int launch_ball_query_grid(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group, cudaStream_t st) {
+// plan_rows != nullptr (S == 1024): also writes the plan of sa1's distinct rows (see Sa1PlanOut; the caller still runs the
+// prefix sum over the clouds' tile counts, launch_sa1_plan_scan).
+int launch_ball_query_grid(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group, cudaStream_t st,
+                           int* plan_rows, int* plan_used, int* plan_tiles) {
   if (N > GN || N < 1) return -1;
   const float r2 = (float)(radius * radius);
-  if (S > GN) return -1;
-  constexpr int smem = GRID_SMEM_BASE + 32 * GT * 4 + 64 * 4 + GN * 2;
+  if (S > GN || (plan_rows && S != 1024)) return -1;
+  constexpr int smem = GRID_SMEM_BASE + 32 * GT * 4 + 64 * 4 + GN * 2 + GN * 2;
   static PerDeviceOnce attr_done;
   if (smem_opt_in(attr_done, ball_query_grid_kernel, smem) != cudaSuccess) return -1;
-  ball_query_grid_kernel<<<n_clouds, GT, smem, st>>>(xyz, new_xyz, N, S, (float)radius, r2, group);
+  ball_query_grid_kernel<<<n_clouds, GT, smem, st>>>(xyz, new_xyz, N, S, (float)radius, r2, group, Sa1PlanOut{plan_rows, plan_used, plan_tiles});
   return 1;
 }
 

@@ -9,174 +9,99 @@ namespace lsdm {
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// Farthest point sampling, all four levels of one cloud in one CTA (the chain is strictly serial
-// per cloud: 1024 + 256 + 64 + 16 dependent argmax rounds).  128 threads, points in shared memory,
-// running min-distance in registers, block argmax = 2 x redux.sync per warp + one barrier.
+// Farthest point sampling, all four levels of a cloud by ONE WARP (the chain is strictly serial per cloud: 1024 + 256 + 64 + 16
+// dependent argmax rounds).  Lane l keeps points l, l + 32, ... in registers (N / 32 of them, as fp32x2 pairs) together with
+// their running minimum distances; a round is: one broadcast 128-bit shared load of the new centroid (the warp's copy of the
+// level's points), the distance update, a per-lane argmax, two redux.sync.  No block barrier, no key exchange through shared
+// memory.  Measured on B200 (300 clouds): 0.39 ms at 0.43 x the instruction count of the round-1 form (a 128-thread block per
+// cloud: 0.44 ms; 256 threads: 0.72 ms) -- that form spent most of its issue slots on per-warp overhead replicated four
+// times, which the kernels of the other streams running beside it paid for.
 // ---------------------------------------------------------------------------------------------
-constexpr int FPS_T = 128;
-
 template <int N, int NP>
-__device__ __forceinline__ void fps_level(const float* sx, const float* sy, const float* sz, int start, int* s_idx,
-                                          unsigned long long* s_red, int tid, bool uniform) {
-  constexpr int PER = (N + FPS_T - 1) / FPS_T;
-  constexpr bool PACKED = (N % FPS_T == 0) && (PER % 2 == 0);  // two points per instruction (fp32x2), every slot valid
-  constexpr int PER2 = PACKED ? PER / 2 : 1;
-  float px[PER], py[PER], pz[PER], dist[PER];
-  float2 qx[PER2], qy[PER2], qz[PER2], qd[PER2];
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    int p = tid + k * FPS_T;
-    bool ok = p < N;
-    px[k] = ok ? sx[p] : 0.f;
-    py[k] = ok ? sy[p] : 0.f;
-    pz[k] = ok ? sz[p] : 0.f;
-    dist[k] = 1e10f;
-  }
-  if (PACKED) {
-#pragma unroll
-    for (int j = 0; j < PER2; ++j) {
-      qx[j] = make_float2(px[2 * j], px[2 * j + 1]);
-      qy[j] = make_float2(py[2 * j], py[2 * j + 1]);
-      qz[j] = make_float2(pz[2 * j], pz[2 * j + 1]);
-      qd[j] = make_float2(1e10f, 1e10f);
-    }
-  }
-  int far = start;
-  const int lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void fps_level_warp(const float* __restrict__ src, int start, int* __restrict__ idx_out, float* __restrict__ xyz_out,
+                                               int lane, bool uniform, uint32_t s_pts) {
+  constexpr int PER = N / 32, PER2 = PER / 2;
+  static_assert(N % 64 == 0 && PER <= 32, "pairs of points per lane");
   if (uniform) {
     // Every point of the cloud has the same coordinates (an absent object: the dataset pads it with zeros, reference
     // posa/dataset.py:456).  All squared distances are then (0 + 0) + 0 = 0 in every round, the running minimum is 0 after
     // round 0 and the argmax of an all-equal array is its first index: the selection is {start, 0, 0, ...} -- exactly what
     // the rounds below produce, without running them.
-    for (int it = tid; it < NP; it += FPS_T) s_idx[it] = it == 0 ? start : 0;
-    __syncthreads();
+    const float x = src[0], y = src[1], z = src[2];
+    for (int it = lane; it < NP; it += 32) {
+      idx_out[it] = it == 0 ? start : 0;
+      xyz_out[it * 3] = x; xyz_out[it * 3 + 1] = y; xyz_out[it * 3 + 2] = z;
+    }
+    __syncwarp();
     return;
   }
-  for (int it = 0; it < NP; ++it) {
-    if (tid == 0) s_idx[it] = far;
-    float cx = sx[far], cy = sy[far], cz = sz[far];
-    unsigned best_bits = 0u;
-    unsigned best_idx = PACKED ? (unsigned)tid : 0xffffffffu;
-    if (PACKED) {
-      // x - c == x + (-c) exactly; every op is an IEEE round-to-nearest add / mul, same as the scalar path (no FMA)
-      const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+  float2 qx[PER2], qy[PER2], qz[PER2], qd[PER2];
 #pragma unroll
-      for (int j = 0; j < PER2; ++j) {
-        float2 dx = __fadd2_rn(qx[j], ncx), dy = __fadd2_rn(qy[j], ncy), dz = __fadd2_rn(qz[j], ncz);
-        // Products packed, sums SCALAR: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into a fused FFMA2 when the
-        // product has a single use, despite the explicit rounding modifiers (tools/probe/packed_fma_probe.cu: 21 % of the
-        // squared distances then differ from the reference's (dx^2 + dy^2) + dz^2).  Scalar add.rn is never contracted.
-        const float2 sxx = __fmul2_rn(dx, dx), syy = __fmul2_rn(dy, dy), szz = __fmul2_rn(dz, dz);
-        const float2 d = make_float2(__fadd_rn(__fadd_rn(sxx.x, syy.x), szz.x), __fadd_rn(__fadd_rn(sxx.y, syy.y), szz.y));
-        float n0 = fminf(d.x, qd[j].x), n1 = fminf(d.y, qd[j].y);
-        qd[j] = make_float2(n0, n1);
-        unsigned b0 = __float_as_uint(n0), b1 = __float_as_uint(n1);  // >= 0: unsigned bit order == float order
-        if (b0 > best_bits) { best_bits = b0; best_idx = (unsigned)(tid + (2 * j) * FPS_T); }
-        if (b1 > best_bits) { best_bits = b1; best_idx = (unsigned)(tid + (2 * j + 1) * FPS_T); }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        int p = tid + k * FPS_T;
-        if (p < N) {
-          float dx = __fsub_rn(px[k], cx), dy = __fsub_rn(py[k], cy), dz = __fsub_rn(pz[k], cz);
-          float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          float nd = (d < dist[k]) ? d : dist[k];
-          dist[k] = nd;
-          unsigned b = __float_as_uint(nd);
-          if (best_idx == 0xffffffffu || b > best_bits) {
-            best_bits = b;
-            best_idx = (unsigned)p;
-          }
-        }
-      }
-    }
-    // warp argmax with lowest-index tie-break
-    unsigned wmax = __reduce_max_sync(0xffffffffu, best_bits);
-    unsigned cand = (best_bits == wmax && best_idx != 0xffffffffu) ? best_idx : 0xffffffffu;
-    unsigned widx = __reduce_min_sync(0xffffffffu, cand);
-    // key: high 32 bits distance, low 32 bits inverted index -> max key = max distance, lowest index
-    unsigned long long key = ((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - widx);
-    if (lane == 0) s_red[(it & 1) * (FPS_T / 32) + warp] = key;
-    __syncthreads();
-    unsigned long long bk = s_red[(it & 1) * (FPS_T / 32)];
-#pragma unroll
-    for (int w = 1; w < FPS_T / 32; ++w) {
-      unsigned long long o = s_red[(it & 1) * (FPS_T / 32) + w];
-      bk = o > bk ? o : bk;
-    }
-    far = (int)(0xffffffffu - (unsigned)(bk & 0xffffffffull));
+  for (int j = 0; j < PER2; ++j) {
+    const int p0 = lane + (2 * j) * 32, p1 = p0 + 32;
+    qx[j] = make_float2(src[p0 * 3], src[p1 * 3]);
+    qy[j] = make_float2(src[p0 * 3 + 1], src[p1 * 3 + 1]);
+    qz[j] = make_float2(src[p0 * 3 + 2], src[p1 * 3 + 2]);
+    qd[j] = make_float2(1e10f, 1e10f);
+    // the warp's copy of the level's points, (x, y, z, -) per point: where a round's new centroid is looked up
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(s_pts + p0 * 16), "f"(qx[j].x), "f"(qy[j].x) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_pts + p0 * 16 + 8), "f"(qz[j].x) : "memory");
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(s_pts + p1 * 16), "f"(qx[j].y), "f"(qy[j].y) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_pts + p1 * 16 + 8), "f"(qz[j].y) : "memory");
   }
-  __syncthreads();
+  __syncwarp();
+  int far = start;
+  for (int it = 0; it < NP; ++it) {
+    const float4 cc = lds_f4(s_pts + far * 16);  // (same address in every lane: a broadcast)
+    const float cx = cc.x, cy = cc.y, cz = cc.z;
+    if (lane == 0) {
+      idx_out[it] = far;
+      xyz_out[it * 3] = cx; xyz_out[it * 3 + 1] = cy; xyz_out[it * 3 + 2] = cz;
+    }
+    unsigned best_bits = 0u, best_idx = (unsigned)lane;
+    const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+#pragma unroll
+    for (int j = 0; j < PER2; ++j) {
+      // x - c == x + (-c) exactly; every op is an IEEE round-to-nearest add / mul (no FMA).  Products packed, sums SCALAR:
+      // ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into a fused FFMA2 when the product has a single use, despite the
+      // explicit rounding modifiers (tools/probe/packed_fma_probe.cu: 21 % of the squared distances then differ from the
+      // reference's (dx^2 + dy^2) + dz^2).  Scalar add.rn is never contracted.
+      const float2 dx = __fadd2_rn(qx[j], ncx), dy = __fadd2_rn(qy[j], ncy), dz = __fadd2_rn(qz[j], ncz);
+      const float2 sxx = __fmul2_rn(dx, dx), syy = __fmul2_rn(dy, dy), szz = __fmul2_rn(dz, dz);
+      const float d0 = __fadd_rn(__fadd_rn(sxx.x, syy.x), szz.x), d1 = __fadd_rn(__fadd_rn(sxx.y, syy.y), szz.y);
+      const float n0 = fminf(d0, qd[j].x), n1 = fminf(d1, qd[j].y);
+      qd[j] = make_float2(n0, n1);
+      const unsigned b0 = __float_as_uint(n0), b1 = __float_as_uint(n1);  // >= 0: unsigned bit order == float order
+      if (b0 > best_bits) { best_bits = b0; best_idx = (unsigned)(lane + (2 * j) * 32); }
+      if (b1 > best_bits) { best_bits = b1; best_idx = (unsigned)(lane + (2 * j + 1) * 32); }
+    }
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, best_bits);
+    far = (int)__reduce_min_sync(0xffffffffu, best_bits == wmax ? best_idx : 0xffffffffu);  // lowest index among the maxima
+  }
+  __syncwarp();  // the next level reads xyz_out (written by lane 0) from every lane, and rewrites the shared copy
 }
 
-__global__ void __launch_bounds__(FPS_T) fps4_kernel(const float* __restrict__ xyz0, const int64_t* __restrict__ start,
-                                                     int n_clouds, int* __restrict__ idx1, int* __restrict__ idx2,
-                                                     int* __restrict__ idx3, int* __restrict__ idx4,
-                                                     float* __restrict__ xyz1, float* __restrict__ xyz2,
-                                                     float* __restrict__ xyz3, float* __restrict__ xyz4, int g_fps_uniform_shortcut) {
-  __shared__ float ax[1024], ay[1024], az[1024];
-  __shared__ float bx[1024], by[1024], bz[1024];
-  __shared__ int s_idx[1024];
-  __shared__ unsigned long long s_red[2 * (FPS_T / 32)];
-  const int c = blockIdx.x, tid = threadIdx.x;
+__global__ void __launch_bounds__(32) fps4_kernel(const float* __restrict__ xyz0, const int64_t* __restrict__ start, int n_clouds,
+                                                       int* __restrict__ idx1, int* __restrict__ idx2, int* __restrict__ idx3,
+                                                       int* __restrict__ idx4, float* __restrict__ xyz1, float* __restrict__ xyz2,
+                                                       float* __restrict__ xyz3, float* __restrict__ xyz4, int uniform_shortcut) {
+  __shared__ float4 s_copy[1024];
+  const uint32_t s_pts = smem_addr(s_copy);
+  const int c = blockIdx.x, lane = threadIdx.x;
   const float* src = xyz0 + (int64_t)c * 1024 * 3;
-  for (int p = tid; p < 1024; p += FPS_T) {
-    ax[p] = src[p * 3 + 0];
-    ay[p] = src[p * 3 + 1];
-    az[p] = src[p * 3 + 2];
-  }
   // all 1024 points equal (== compares values: +0 and -0 are the same point, a NaN never is)?  Then every level is uniform too.
-  bool same = true;
-  {
-    const float x0 = src[0], y0 = src[1], z0 = src[2];
-    same = fabsf(x0) < INFINITY && fabsf(y0) < INFINITY && fabsf(z0) < INFINITY;  // inf - inf is NaN, not 0: full rounds
-    for (int p = tid; p < 1024; p += FPS_T) same = same && src[p * 3] == x0 && src[p * 3 + 1] == y0 && src[p * 3 + 2] == z0;
-  }
-  // (this barrier also publishes the staged points: it must not sit behind the option's short-circuit)
-  const int all_same = __syncthreads_and(same ? 1 : 0);
-  const bool uniform = g_fps_uniform_shortcut != 0 && all_same != 0;
-  // level 1: 1024 of 1024 (an FPS-ordered permutation)
-  fps_level<1024, 1024>(ax, ay, az, (int)start[0 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
-  for (int p = tid; p < 1024; p += FPS_T) {
-    int j = s_idx[p];
-    idx1[(int64_t)c * 1024 + p] = j;
-    float x = ax[j], y = ay[j], z = az[j];
-    bx[p] = x; by[p] = y; bz[p] = z;
-    float* o = xyz1 + ((int64_t)c * 1024 + p) * 3;
-    o[0] = x; o[1] = y; o[2] = z;
-  }
-  __syncthreads();
-  // level 2: 256 of 1024 over l1_xyz
-  fps_level<1024, 256>(bx, by, bz, (int)start[1 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
-  for (int p = tid; p < 256; p += FPS_T) {
-    int j = s_idx[p];
-    idx2[(int64_t)c * 256 + p] = j;
-    float x = bx[j], y = by[j], z = bz[j];
-    ax[p] = x; ay[p] = y; az[p] = z;
-    float* o = xyz2 + ((int64_t)c * 256 + p) * 3;
-    o[0] = x; o[1] = y; o[2] = z;
-  }
-  __syncthreads();
-  // level 3: 64 of 256
-  fps_level<256, 64>(ax, ay, az, (int)start[2 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
-  for (int p = tid; p < 64; p += FPS_T) {
-    int j = s_idx[p];
-    idx3[(int64_t)c * 64 + p] = j;
-    float x = ax[j], y = ay[j], z = az[j];
-    bx[p] = x; by[p] = y; bz[p] = z;
-    float* o = xyz3 + ((int64_t)c * 64 + p) * 3;
-    o[0] = x; o[1] = y; o[2] = z;
-  }
-  __syncthreads();
-  // level 4: 16 of 64
-  fps_level<64, 16>(bx, by, bz, (int)start[3 * (int64_t)n_clouds + c], s_idx, s_red, tid, uniform);
-  for (int p = tid; p < 16; p += FPS_T) {
-    int j = s_idx[p];
-    idx4[(int64_t)c * 16 + p] = j;
-    float* o = xyz4 + ((int64_t)c * 16 + p) * 3;
-    o[0] = bx[j]; o[1] = by[j]; o[2] = bz[j];
-  }
+  const float x0 = src[0], y0 = src[1], z0 = src[2];
+  bool same = fabsf(x0) < INFINITY && fabsf(y0) < INFINITY && fabsf(z0) < INFINITY;  // inf - inf is NaN, not 0: full rounds
+  for (int p = lane; p < 1024; p += 32) same = same && src[p * 3] == x0 && src[p * 3 + 1] == y0 && src[p * 3 + 2] == z0;
+  const bool uniform = uniform_shortcut != 0 && __all_sync(0xffffffffu, same);
+  float* l1 = xyz1 + (int64_t)c * 1024 * 3;
+  float* l2 = xyz2 + (int64_t)c * 256 * 3;
+  float* l3 = xyz3 + (int64_t)c * 64 * 3;
+  float* l4 = xyz4 + (int64_t)c * 16 * 3;
+  fps_level_warp<1024, 1024>(src, (int)start[0 * (int64_t)n_clouds + c], idx1 + (int64_t)c * 1024, l1, lane, uniform, s_pts);
+  fps_level_warp<1024, 256>(l1, (int)start[1 * (int64_t)n_clouds + c], idx2 + (int64_t)c * 256, l2, lane, uniform, s_pts);
+  fps_level_warp<256, 64>(l2, (int)start[2 * (int64_t)n_clouds + c], idx3 + (int64_t)c * 64, l3, lane, uniform, s_pts);
+  fps_level_warp<64, 16>(l3, (int)start[3 * (int64_t)n_clouds + c], idx4 + (int64_t)c * 16, l4, lane, uniform, s_pts);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,7 +247,7 @@ int g_select_uniform_shortcut = 1;
 
 int launch_fps4(const float* xyz0, const int64_t* start, int n_clouds, int* idx1, int* idx2, int* idx3, int* idx4,
                 float* xyz1, float* xyz2, float* xyz3, float* xyz4, cudaStream_t st) {
-  fps4_kernel<<<n_clouds, FPS_T, 0, st>>>(xyz0, start, n_clouds, idx1, idx2, idx3, idx4, xyz1, xyz2, xyz3, xyz4, g_select_uniform_shortcut);
+  fps4_kernel<<<n_clouds, 32, 0, st>>>(xyz0, start, n_clouds, idx1, idx2, idx3, idx4, xyz1, xyz2, xyz3, xyz4, g_select_uniform_shortcut);
   return 1;
 }
 

@@ -858,6 +858,11 @@ int launch_sa1_plan(const int* grp, int n_clouds, int* rows, int* tile_used, int
   return 2;
 }
 
+int launch_sa1_plan_scan(const int* tiles, int n_clouds, int* tile_off, int* n_tiles, cudaStream_t st) {
+  sa1_scan_kernel<<<1, 1024, 0, st>>>(tiles, n_clouds, tile_off, n_tiles);
+  return 1;
+}
+
 int launch_sa1_compact(const float* xyz, const float* new_xyz, const int* rows, const int* tile_used, const int* tile_off, const int* n_tiles,
                        const float* h_wx, const float* h_wf, const float* h_b1, const float* h_b2, const float* W2, const float* W3, const float* b3,
                        int n_clouds, float* out, int round_out, cudaStream_t st) {
