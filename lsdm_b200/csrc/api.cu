@@ -1293,8 +1293,6 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
         CK(cudaStreamWaitEvent(side, h->ev_step[sn], 0));
       }
       tl_begin(k + 1, 'S', side);
-      static const int dbg_skip = getenv("LSDM_DEBUG_SKIP") ? atoi(getenv("LSDM_DEBUG_SKIP")) : 0;  // timing experiments only (results are garbage): 1 = no selection after step 0, 2 = no dense phase after step 2
-      if (!(dbg_skip & 1))
       GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active, fork_cond));
       tl_end(side);
       CK(cudaEventRecord(h->ev_sel[sn], side));
@@ -1306,8 +1304,6 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
         CK(cudaStreamWaitEvent(dst, h->ev_sel[si], 0));  // (select(k) already waited for step(k-3), the last reader of pcd_out[si])
       }
       tl_begin(k, 'D', dst);
-      static const int dbg_skip2 = getenv("LSDM_DEBUG_SKIP") ? atoi(getenv("LSDM_DEBUG_SKIP")) : 0;
-      if (!((dbg_skip2 & 2) && k >= 3))
       GE(encode_dense(h, text, objs, cats, mask_global, si, dst, nullptr, clouds, nc, remap));
       tl_end(dst);
       if (pipelined) {
