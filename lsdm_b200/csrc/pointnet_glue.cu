@@ -27,6 +27,44 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  if (P != nullptr) {
+    // Four consecutive rows of a group (same centroid) per warp iteration, every global load of the four issued before the
+    // first use: the row -> point -> projected-row chain is three dependent latencies, paid once per four rows.
+    // 128-bit accesses: a lane owns 4 consecutive channels per iteration (C1 is a multiple of 128 here).
+    for (int64_t row0 = warp0 * 4; row0 < rows; row0 += nwarps * 4) {  // (rows is a multiple of 32)
+      const int64_t cs = row0 >> 5;  // (cloud, centroid)
+      const int64_t c = cs / S;
+      const int4 j4 = *reinterpret_cast<const int4*>(group + row0);
+      const int jj[4] = {j4.x, j4.y, j4.z, j4.w};
+      const float* pc = new_xyz + cs * 3;
+      const float cx = pc[0], cy = pc[1], cz = pc[2];
+      float rx[4], ry[4], rz[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* pj = xyz + (c * N + jj[u]) * 3;
+        rx[u] = pj[0] - cx; ry[u] = pj[1] - cy; rz[u] = pj[2] - cz;
+      }
+      for (int c4 = lane; c4 < (C1 >> 2); c4 += 32) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = *reinterpret_cast<const float4*>(P + (c * N + jj[u]) * C1 + c4 * 4);
+        const float4 wa = *reinterpret_cast<const float4*>(sw + c4 * 12), wb = *reinterpret_cast<const float4*>(sw + c4 * 12 + 4),
+                     wc = *reinterpret_cast<const float4*>(sw + c4 * 12 + 8);  // Wx rows of channels 4 c4 .. 4 c4 + 3
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float r[4] = {fmaf(wa.z, rz[u], fmaf(wa.y, ry[u], fmaf(wa.x, rx[u], p[u].x))), fmaf(wb.y, rz[u], fmaf(wb.x, ry[u], fmaf(wa.w, rx[u], p[u].y))),
+                        fmaf(wc.x, rz[u], fmaf(wb.w, ry[u], fmaf(wb.z, rx[u], p[u].z))), fmaf(wc.w, rz[u], fmaf(wc.z, ry[u], fmaf(wc.y, rx[u], p[u].w)))};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (apply_relu) r[e] = fmaxf(r[e], 0.0f);
+            if (round_out) r[e] = tc::rna_tf32(r[e]);
+          }
+          *reinterpret_cast<float4*>(h1 + (row0 + u) * C1 + c4 * 4) = make_float4(r[0], r[1], r[2], r[3]);
+        }
+      }
+    }
+    return;
+  }
   for (int64_t row = warp0; row < rows; row += nwarps) {
     int64_t cs = row >> 5;  // (cloud, centroid)
     int64_t c = cs / S;
@@ -36,34 +74,16 @@ __global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict_
     float jx = pj[0], jy = pj[1], jz = pj[2];
     float rx = jx - pc[0], ry = jy - pc[1], rz = jz - pc[2];
     float* out = h1 + row * C1;
-    if (P != nullptr) {
-      // 128-bit accesses: a lane owns 4 consecutive channels per iteration (C1 is a multiple of 128 here)
-      const float* prow = P + (c * N + j) * C1;
-      for (int c4 = lane; c4 < (C1 >> 2); c4 += 32) {
-        const float4 p = *reinterpret_cast<const float4*>(prow + c4 * 4);
-        const float4 wa = *reinterpret_cast<const float4*>(sw + c4 * 12), wb = *reinterpret_cast<const float4*>(sw + c4 * 12 + 4),
-                     wc = *reinterpret_cast<const float4*>(sw + c4 * 12 + 8);  // Wx rows of channels 4 c4 .. 4 c4 + 3
-        float r[4] = {fmaf(wa.z, rz, fmaf(wa.y, ry, fmaf(wa.x, rx, p.x))), fmaf(wb.y, rz, fmaf(wb.x, ry, fmaf(wa.w, rx, p.y))),
-                      fmaf(wc.x, rz, fmaf(wb.w, ry, fmaf(wb.z, rx, p.z))), fmaf(wc.w, rz, fmaf(wc.z, ry, fmaf(wc.y, rx, p.w)))};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (apply_relu) r[e] = fmaxf(r[e], 0.0f);
-          if (round_out) r[e] = tc::rna_tf32(r[e]);
-        }
-        *reinterpret_cast<float4*>(out + c4 * 4) = make_float4(r[0], r[1], r[2], r[3]);
-      }
-    } else {
-      for (int ch = lane; ch < C1; ch += 32) {
-        float v = sw[C1 * 6 + ch];
-        v = fmaf(sw[ch * 3 + 0], rx, v);
-        v = fmaf(sw[ch * 3 + 1], ry, v);
-        v = fmaf(sw[ch * 3 + 2], rz, v);
-        v = fmaf(sw[C1 * 3 + ch * 3 + 0], jx, v);
-        v = fmaf(sw[C1 * 3 + ch * 3 + 1], jy, v);
-        v = fmaf(sw[C1 * 3 + ch * 3 + 2], jz, v);
-        if (apply_relu) v = fmaxf(v, 0.0f);
-        out[ch] = round_out ? tc::rna_tf32(v) : v;
-      }
+    for (int ch = lane; ch < C1; ch += 32) {
+      float v = sw[C1 * 6 + ch];
+      v = fmaf(sw[ch * 3 + 0], rx, v);
+      v = fmaf(sw[ch * 3 + 1], ry, v);
+      v = fmaf(sw[ch * 3 + 2], rz, v);
+      v = fmaf(sw[C1 * 3 + ch * 3 + 0], jx, v);
+      v = fmaf(sw[C1 * 3 + ch * 3 + 1], jy, v);
+      v = fmaf(sw[C1 * 3 + ch * 3 + 2], jz, v);
+      if (apply_relu) v = fmaxf(v, 0.0f);
+      out[ch] = round_out ? tc::rna_tf32(v) : v;
     }
   }
 }
