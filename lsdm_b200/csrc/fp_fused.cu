@@ -109,11 +109,22 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
   };
   float* stage = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + WA_BYTES + W1_BYTES);  // 2 x [128][32] floats
   constexpr int CH1 = C1 / 32 / 2;  // 32-column chunks per column half
-  prefetch(t0);
-  for (int tile = t0; tile < t1; ++tile) {
-    const int64_t row = (int64_t)tile * 128 + rit;
-    const int64_t cbase = (((int64_t)tile * 128) >> a.n_shift) * a.S;  // a tile never straddles two clouds
-    // ---- A1: own half-row -> TMEM (the +half-ulp of rna_tf32_mma is a no-op on already rounded inputs) ----
+  // Software pipeline over tiles (round 2b): the A operand of tile i + 1 is staged into tensor memory and its first MMA is issued
+  // while tile i's second MMA / output epilogue run (its columns are free by then), and the first gather step of tile i + 1 is
+  // issued before tile i's second MMA, so its L2 round trip hides behind both.
+  //   [stage A1(i+1) | MMA2(i)] -> MMA1(i+1) issued -> [epilogue 2(i) | MMA1(i+1)] -> epilogue 1(i+1) ...
+  const float* gp[4][3];  // loader state of the tile whose epilogue 1 runs / runs next
+  float gw[4][3];
+  float4 nb[2][4][3];     // gather registers: step s covers chunk s of BOTH column halves (hh = 0, 1): 4 rows x 2 halves x 3 neighbours
+  auto gather = [&](int s) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) nb[hh][i][j] = *reinterpret_cast<const float4*>(gp[i][j] + (hh * CH1 + s) * 32);
+  };
+  auto stage_a1 = [&]() {  // own half-row -> TMEM (the +half-ulp of rna_tf32_mma is a no-op on already rounded inputs)
 #pragma unroll
     for (int kl = 0; kl < KB1 / 2; ++kl) {
       uint32_t v[32];
@@ -128,9 +139,9 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
       tmem_st32(tlane + COL_A1 + (half * (KB1 / 2) + kl) * 32, v);
     }
     tmem_st_wait();
-    // loader state of THIS tile (the prefetch below overwrites li / lw with the next tile's)
-    const float* gp[4][3];
-    float gw[4][3];
+  };
+  auto loader_state = [&](int tile) {  // from li / lw (the prefetch that follows overwrites them with the next tile's)
+    const int64_t cbase = (((int64_t)tile * 128) >> a.n_shift) * a.S;  // a tile never straddles two clouds
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -138,10 +149,8 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
         gp[i][j] = a.Pb + (cbase + li[i][j]) * C1 + lc4 * 4;
         gw[i][j] = lw[i][j];
       }
-    prefetch(tile + 1);
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 1: D1 = X . Wa^T ----
+  };
+  auto issue_mma1 = [&]() {  // D1 = X . Wa^T
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -153,17 +162,20 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
       }
       umma_commit(bar);
     }
-    // gather registers: step s covers chunk s of BOTH column halves (hh = 0, 1): 4 rows x 2 halves x 3 neighbours
-    float4 nb[2][4][3];
-    auto gather = [&](int s) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) nb[hh][i][j] = *reinterpret_cast<const float4*>(gp[i][j] + (hh * CH1 + s) * 32);
-    };
+  };
+  prefetch(t0);
+  if (t0 < t1) {
+    stage_a1();
+    loader_state(t0);
+    prefetch(t0 + 1);
+    tc_fence_before();
+    __syncthreads();
+    issue_mma1();
     gather(0);  // travels while the MMA runs
+  }
+  for (int tile = t0; tile < t1; ++tile) {
+    const int64_t row = (int64_t)tile * 128 + rit;
+    const bool has_next = tile + 1 < t1;
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
@@ -186,7 +198,12 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
           *reinterpret_cast<float4*>(stage + hh * (128 * 32) + r * 32 + ((lc4 ^ (r & 7)) << 2)) = o;
         }
       __syncthreads();
-      if (s + 1 < CH1) gather(s + 1);  // next step's rows are in flight during this step's TMEM round trip
+      if (s + 1 < CH1) {
+        gather(s + 1);  // next step's rows are in flight during this step's TMEM round trip
+      } else if (has_next) {
+        loader_state(tile + 1);  // (li / lw hold tile + 1's neighbours since the last prefetch)
+        gather(0);               // the next tile's first step: in flight during this tile's second MMA and output epilogue
+      }
       // ROW: this thread's 32 columns of chunk s
       const int c0 = (half * CH1 + s) * 32;
       uint32_t v[32];
@@ -221,9 +238,19 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
       }
       umma_commit(bar);
     }
+    // while it runs: the next tile's A operand (its columns were released by this tile's first MMA) and the prefetch of tile + 2
+    if (has_next) {
+      stage_a1();
+      prefetch(tile + 2);
+    }
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
+    if (has_next) {
+      tc_fence_before();
+      __syncthreads();  // every thread's A1 stores are complete; D1 is free (this tile's second MMA has read it)
+      issue_mma1();
+    }
     // ---- epilogue 2: bias + ReLU (+ rounding for the next tensor-core consumer) -> global, 128 B per thread per chunk ----
     float* orow = a.out + row * C2;
 #pragma unroll 1
@@ -243,7 +270,7 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
         *reinterpret_cast<float4*>(orow + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
-    tc_fence_before();  // the next tile's tcgen05.st / MMAs reuse these columns
+    tc_fence_before();  // the next tile's second MMA reuses these columns
   }
   tc_fence_before();
   __syncthreads();
