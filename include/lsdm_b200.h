@@ -273,20 +273,19 @@ LSDM_API int64_t lsdm_launch_count(const lsdm_handle* h);
  * 3-NN), are always exact fp32. */
 LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32_t precision_step);
 
-/* Tuning knobs.  "sa_fused": 0 = set-abstraction blocks as gather + GEMM launches, 1 = fused tensor-core SA kernel with the
- * activations staged in shared memory, 2 = fused with the activations kept in tensor memory (A-from-TMEM MMA), 3 = levels 1-2
- * with the transposed-last-layer variant (in-register max-pool, constant-bank weights), level 3 as in 2.
- * "fp_tail": 1 = the last two fp1 layers + conv1/bn1/conv2 head as one fused tensor-core kernel.
- * "fp_fused": 1 = the fp2 level (fine half of conv 1 + 3-NN interpolation of the projected coarse features + conv 2) as one
- *             fused tensor-core kernel.
- * "gemm_async" (process-wide): 1 = TF32 layers whose operands are pre-rounded by their producers use the cp.async-fed
- * persistent warp-specialised GEMM.
- * "select_uniform" (process-wide): 1 (default) = a cloud whose points all coincide (an absent object, zero-padded by the
- *             dataset) takes the closed-form FPS order {start, 0, 0, ...} and a 3-candidate 3-NN scan: the same integers as
- *             the full scans, which 0 forces.
- * "gemm_tma" (process-wide): 1 (default) = those operands are moved by TMA (cp.async.bulk.tensor, SWIZZLE_128B boxes, one
- *             issuing thread, byte-counted mbarrier) for un-batched GEMMs; 0 = cp.async.
- * "gemm_ws" (process-wide): 1 = persistent warp-specialised tcgen05 GEMM (default), 0 = one-CTA-per-tile tcgen05 GEMM. */
+/* Switches that exist for the on / off equality tests and bench.py's transparency legs (every "on" form is tested to give the
+ * same result as its "off" form); defaults in brackets.
+ * "sa_fused"      [1] 0 = set-abstraction levels 1-3 as gather + one GEMM launch per layer, > 0 = the fused tensor-core kernels.
+ * "sa1_compact"   [1] sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles).
+ * "x0_fused"      [1] the x0 network of a step runs as one persistent kernel; 0 = one GEMM per layer.
+ * "hoist_split"   [1] hoisted loop only: time half of the embedding once per step for the whole batch, text half once per loop.
+ * "dedup_absent"  [1] lsdm_sample_loop encodes the all-zero cloud of absent objects once per step and shares the result.
+ * "select_uniform" (process-wide) [1] a cloud whose points all coincide takes the closed-form FPS order {start, 0, 0, ...} and a
+ *                 3-candidate 3-NN scan: the same integers as the full scans, which 0 forces.
+ * "select_grid"   [9] bit mask: ball query of level 0 (1) / level 1 (2), 3-NN of fp2 (4) / fp1 (8) through a per-cloud cell grid
+ *                 instead of the full scan (identical groups, indices and weights).
+ * "cond_stream"   [1] pipelined loop: the per-sample condition MLPs and the human decoder run on their own stream beside the
+ *                 selection chain. */
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value);
 
 /* Test hook: one linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) through the fp32 (precision 0) or tcgen05 TF32 / 3xTF32
