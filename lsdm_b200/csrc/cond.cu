@@ -218,17 +218,23 @@ __global__ void __launch_bounds__(256) human_l0_kernel(HumanWeights w, const flo
   group_stats_accumulate(acc, 1, stats + ((int64_t)b * 3 + 0) * 16, s_red);
 }
 
-// layers 1, 2: y = W relu(gn(prev)) + b over npts points (64 -> 64), stats
-__global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict__ Wl, const float* __restrict__ bl,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        const float* __restrict__ prev, float* __restrict__ out,
-                                                        double* stats, int slot_in, int slot_out, int npts_in, int npts) {
-  __shared__ __align__(16) float s_w[64 * 68];  // [ch][k], row stride 68 floats (16B aligned, conflict-free float4 reads)
-  __shared__ __align__(16) float s_a[HS * 68];  // normalised + ReLU input slab [p][k], row stride 68 (conflict-free float4 reads)
+// layers 1, 2: y = W relu(gn(prev)) + b over npts points (64 -> 64), stats.
+// 128 threads per 64-point slab, a 4-point x 8-channel register tile per thread: thread (tp, tc) owns points 4 tp .. 4 tp + 3 and
+// the eight channels of GroupNorm group tc.  Activations and weights are staged K-MAJOR ([k][point], [k][channel]) so that a
+// k-step is three 128-bit shared loads (four points; eight channels) for 32 FMAs -- the first form (one point x sixteen channels
+// per thread) issued 17 loads per 64 FMAs and was bound by shared-memory bandwidth.  Each output is still the k-ascending chain
+// acc = fma(W[ch][k], a[k], acc) started from the bias.
+constexpr int HM_T = 128;
+__global__ void __launch_bounds__(HM_T) human_mid_kernel(const float* __restrict__ Wl, const float* __restrict__ bl,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ prev, float* __restrict__ out,
+                                                         double* stats, int slot_in, int slot_out, int npts_in, int npts) {
+  __shared__ __align__(16) float s_wt[64 * 68];  // [k][ch], row stride 68 floats
+  __shared__ __align__(16) float s_at[64 * 68];  // normalised + ReLU input slab [k][p], row stride 68 floats
   __shared__ float s_b[64], s_scale[64], s_shift[64];
-  __shared__ double s_red[8 * 8 * 2];
+  __shared__ double s_red[(HM_T / 32) * 8 * 2];
   const int b = blockIdx.y, p0 = blockIdx.x * HS, tid = threadIdx.x;
-  for (int i = tid; i < 64 * 64; i += 256) s_w[(i >> 6) * 68 + (i & 63)] = Wl[i];
+  for (int i = tid; i < 64 * 64; i += HM_T) s_wt[(i & 63) * 68 + (i >> 6)] = Wl[i];  // Wl[ch][k] -> [k][ch]
   if (tid < 64) {
     const double* st = stats + ((int64_t)b * 3 + slot_in) * 16;
     int g = tid >> 3;
@@ -243,32 +249,63 @@ __global__ void __launch_bounds__(256) human_mid_kernel(const float* __restrict_
     s_b[tid] = bl[tid];
   }
   __syncthreads();
-  for (int i = tid; i < HS * 64; i += 256) {
-    int p = p0 + (i >> 6), k = i & 63;
+  for (int i = tid; i < HS * 64; i += HM_T) {
+    int pl = i >> 6, k = i & 63, p = p0 + pl;
     float v = p < npts ? prev[((int64_t)b * NPTS + p) * 64 + k] : 0.f;
-    s_a[(i >> 6) * 68 + k] = fmaxf(fmaf(v, s_scale[k], s_shift[k]), 0.0f);
+    s_at[k * 68 + pl] = fmaxf(fmaf(v, s_scale[k], s_shift[k]), 0.0f);
   }
   __syncthreads();
-  const int pl = tid >> 2, chq = tid & 3, p = p0 + pl;
-  float acc[16];
+  const int tc = tid & 7, tp = tid >> 3;
+  float acc[4][8];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = s_b[e * 4 + chq];
-  // channel ch = e*4 + chq: the 4 lanes of a point read 4 consecutive weight rows (stride 68 floats -> distinct banks)
+  for (int c = 0; c < 8; ++c) {
+    const float bb = s_b[tc * 8 + c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][c] = bb;
+  }
 #pragma unroll 4
-  for (int k = 0; k < 64; k += 4) {
-    float4 a4 = *reinterpret_cast<const float4*>(&s_a[pl * 68 + k]);
+  for (int k = 0; k < 64; ++k) {
+    const float4 a4 = *reinterpret_cast<const float4*>(&s_at[k * 68 + tp * 4]);
+    const float4 w0 = *reinterpret_cast<const float4*>(&s_wt[k * 68 + tc * 8]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&s_wt[k * 68 + tc * 8 + 4]);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      float4 w4 = *reinterpret_cast<const float4*>(&s_w[(e * 4 + chq) * 68 + k]);
-      acc[e] = fmaf(w4.w, a4.w, fmaf(w4.z, a4.z, fmaf(w4.y, a4.y, fmaf(w4.x, a4.x, acc[e]))));
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[q][c] = fmaf(wv[c], av[q], acc[q][c]);
+  }
+  double gs = 0.0, gq = 0.0;  // this thread's share of group tc: sum, sum of squares
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int p = p0 + tp * 4 + q;
+    if (p < npts) {
+      float* o = out + ((int64_t)b * NPTS + p) * 64 + tc * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double v = (double)acc[q][c];
+        gs += v;
+        gq += v * v;
+      }
     }
   }
-  if (p < npts) {
-    float* o = out + ((int64_t)b * NPTS + p) * 64 + chq;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) o[e * 4] = acc[e];
+  // lanes of a warp: tc = lane & 7, four point groups -> reduce over lane bits 3, 4; then over the four warps
+  gs += __shfl_xor_sync(0xffffffffu, gs, 8);
+  gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+  gs += __shfl_xor_sync(0xffffffffu, gs, 16);
+  gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+  if ((tid & 31) < 8) {
+    s_red[((tid >> 5) * 8 + tc) * 2] = gs;
+    s_red[((tid >> 5) * 8 + tc) * 2 + 1] = gq;
   }
-  group_stats_accumulate(acc, p < npts, stats + ((int64_t)b * 3 + slot_out) * 16, s_red);
+  __syncthreads();
+  if (tid < 16) {  // 8 groups x (sum, sumsq)
+    double t = 0;
+    for (int w = 0; w < HM_T / 32; ++w) t += s_red[(w * 8 + (tid >> 1)) * 2 + (tid & 1)];
+    atomicAdd(&stats[((int64_t)b * 3 + slot_out) * 16 + tid], t);
+  }
 }
 
 // final: hm[2p], hm[2p+1] = W3 relu(gn(y2[p])) + b3 for p < 512 (64 -> 3, nearest x2 upsample, first 1024 kept)
@@ -329,8 +366,8 @@ int launch_human(const HumanWeights& w, const float* objs, int B, float* scratch
   cudaMemsetAsync(stats, 0, sizeof(double) * B * 3 * 16, st);
   human_l0_kernel<<<dim3(NPTS / HS, B), 256, 0, st>>>(w, objs, y0, stats);
   // layer 1 over 1024 points (stats slot 0 -> 1); layer 2 over the first 655 points (stats slot 1 -> 2)
-  human_mid_kernel<<<dim3(NPTS / HS, B), 256, 0, st>>>(w.w1, w.b1, w.g0, w.be0, y0, y1, stats, 0, 1, NPTS, NPTS);
-  human_mid_kernel<<<dim3((655 + HS - 1) / HS, B), 256, 0, st>>>(w.w2, w.b2, w.g1, w.be1, y1, y0, stats, 1, 2, NPTS, 655);
+  human_mid_kernel<<<dim3(NPTS / HS, B), HM_T, 0, st>>>(w.w1, w.b1, w.g0, w.be0, y0, y1, stats, 0, 1, NPTS, NPTS);
+  human_mid_kernel<<<dim3((655 + HS - 1) / HS, B), HM_T, 0, st>>>(w.w2, w.b2, w.g1, w.be1, y1, y0, stats, 1, 2, NPTS, 655);
   human_out_kernel<<<dim3(512 / 8, B), 256, 0, st>>>(w, y0, stats, hm);
   return 4;
 }

@@ -12,7 +12,7 @@ constexpr int PA_T = 256;
 // One CTA per (b, o').  p1[b,o',p,d] = F[b, g%9, g/9] * w[b, g%9] with g = o'*3072 + p*3 + d   (scramble #1)
 // logits_h[j] = qq_h * (Wk_h . p1_j + bk_h); a = softmax_j; ctx_h = sum_j a_hj (Wv_h . p1_j + bv_h); pa = Wo ctx + bo
 // pw[b,o',p,:] = gelu(Wpt [p1_p || pa] + bpt)
-__global__ void __launch_bounds__(PA_T) point_attention_kernel(SceneWeights w, const float* __restrict__ backbone,
+__global__ void __launch_bounds__(PA_T, 2) point_attention_kernel(SceneWeights w, const float* __restrict__ backbone,
                                                                const float* __restrict__ attn_w,
                                                                const float* __restrict__ qq, float* __restrict__ pa_out,
                                                                float* __restrict__ pw, const int* __restrict__ remap) {
