@@ -493,6 +493,27 @@ def run_ours(args):
         if rank == 0:
             print(f"[bench] all clouds encoded (dedup off): {all_clouds['value']:.1f} {UNIT}, identical={all_clouds['identical_output']}, "
                   f"absent {all_clouds['absent_clouds']}/{9 * B}", file=sys.stderr, flush=True)
+    # ---- transparency leg 3: everything recomputed every step, loop-invariant or not ----
+    per_step_all = None
+    if not hoisted:
+        eng.set_option("loop_invariants", 0)
+        try:
+            xi = g["x_T"].clone()
+            run_steps(0, W, xi)
+            ims = dev_timed(lambda: run_steps(W, K, xi))
+            per_step_all = {"value": Bg * K / (ims * 1e-3), "unit": UNIT, "ms_per_step": ims / K,
+                            "rel_l2_vs_value_leg": float(((xi - x).norm() / x.norm()).item()),
+                            "note": "lsdm_set_option('loop_invariants', 0): the condition MLPs, the human decoder, the text half of the embedding, "
+                                    "sa1 and the level-0 ball query run every step although nothing they read changes over the loop.  `value` "
+                                    "computes them once per p_sample_loop call, inside the timed region (same kernels on the same inputs: "
+                                    "bit-identical, except the embedding whose 256-term sums are split into a time and a text half -> 1e-6; "
+                                    "tests/test_gpu_parity.py::test_strict_loop_invariants_match_per_step_recompute).  PointNet++ levels 2-4, all "
+                                    "FPS levels, the scene branch and both x0-network passes still run every step with fresh FPS draws"}
+        finally:
+            eng.set_option("loop_invariants", 7)
+        if rank == 0:
+            print(f"[bench] loop invariants recomputed every step: {per_step_all['value']:.1f} {UNIT}, rel_l2 {per_step_all['rel_l2_vs_value_leg']:.2e}",
+                  file=sys.stderr, flush=True)
     # ---- N > 1: driver-side proof that the sharded results are right: rank 0 recomputes rank 1's shard of the timed leg ----
     gather_check = None
     if world > 1 and not hoisted:
@@ -792,6 +813,7 @@ def run_ours(args):
                        "weights": "seeded well-conditioned random init (lsdm_b200.synthetic)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernel_time_shares": shares,
             "cpu_baseline": cpu_baseline, "hoisted": hoisted_info, "uniform_cloud_full_scans": full_scans, "all_clouds_encoded": all_clouds,
+            "loop_invariants_recomputed_every_step": per_step_all,
             "gather_check": gather_check, "extra_configs": extra,
         }
         _emit(out_fd, line)

@@ -88,6 +88,10 @@ struct Workspace {
   float *tA, *tB, *tP, *g3, *g2, *g1, *backbone, *pa, *pw, *pcd_out[3];  // pcd_out: one per selection set (the step of k reads it while dense(k+1), dense(k+2) write the others)
   // step
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
+  // sa1 in cloud order (`loop_invariants` bit 2): level-1 features of every point, the ball-query groups and the distinct-row plan
+  // they were computed from -- written once per lsdm_sample_loop call, permuted per step by the level-0 FPS order
+  float* f1canon;
+  int *c_grp, *c_plan_rows, *c_plan_used, *c_plan_tiles, *c_plan_off, *c_plan_n;
   float *ctext, *a_t;  // hoisted loop: loop-invariant text half [rows,128] and batch-shared time half [1024,128] of the embedding pre-activation
   float *H1_lo, *H2_lo, *embpre_lo, *cat_lo, *h1_lo, *c1_lo, *c2_lo;  // 3xTF32 residual planes of the step network's activations
   size_t bytes;
@@ -116,6 +120,10 @@ struct lsdm_handle {
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
   int select_grid = 9;           // bit mask: ball query level 0 (1), level 1 (2), 3-NN of fp2 (4), of fp1 (8) through a per-cloud cell grid (identical selections)
+  int loop_invariants = 7;       // lsdm_sample_loop, STRICT: what is computed once per call instead of once per step because its inputs do not
+                                 //    change over the loop (same kernels, same inputs -> same bits): 1 condition MLPs + human decoder,
+                                 //    2 text half of the embedding (the time half once per step for the whole batch: every sample shares t),
+                                 //    4 sa1 + level-0 ball query in cloud order (the level-0 FPS only permutes its rows)
   int hoist_split = 1;           // 1: the hoisted loop computes the time half of the embedding once per step for the whole batch and the text half once per loop
   int sa1_compact = 1;           // 1: sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles)
   int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
@@ -287,6 +295,13 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
     s.plan_n = a.take<int>(4);
   }
   w->clouds_c = a.take<float>(C * NPTS * 3);
+  w->f1canon = a.take<float>(C * 1024 * 64);
+  w->c_grp = a.take<int>(C * 1024 * 32);
+  w->c_plan_rows = a.take<int>(C * 256 * 128);
+  w->c_plan_used = a.take<int>(C * 256);
+  w->c_plan_tiles = a.take<int>(C);
+  w->c_plan_off = a.take<int>(C + 1);
+  w->c_plan_n = a.take<int>(4);
   w->remap = a.take<int>(C);
   w->active = a.take<int>(C);
   w->n_active = a.take<int>(4);
@@ -413,7 +428,11 @@ __global__ void gather_fps_start_kernel(const int64_t* __restrict__ src, const i
 // runs on: the same tensor, or the de-duplicated copy (Workspace::clouds_c, `active` = compact -> original cloud index).
 int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const float* objs, const float* cats,
                  const float* mask_global, const int64_t* fps_start, cudaStream_t st, const float* clouds = nullptr, int C = -1,
-                 const int* active = nullptr, bool fork_cond = false) {
+                 const int* active = nullptr, bool fork_cond = false, bool skip_cond = false, bool skip_level0 = false) {
+  // skip_cond (lsdm_sample_loop, `loop_invariants` bit 0): the condition MLPs and the human decoder are deterministic functions
+  // of inputs that do not change over the loop; step 0 computed them and the loop copied the results into this set
+  const bool fork_streams = fork_cond;
+  if (skip_cond) fork_cond = false;
   const int B = h->cfg.batch_local;
   if (!clouds) clouds = objs, C = B * NOBJ;
   Workspace& w = h->ws;
@@ -425,7 +444,7 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
     CK(cudaStreamWaitEvent(h->cond_st, h->ev_cfork, 0));
     st = h->cond_st;
   }
-  {
+  if (!skip_cond) {
     CondWeights cw{h->W("embed_text.0.weight"), h->W("embed_text.0.bias"), h->W("embed_text.2.weight"), h->W("embed_text.2.bias"),
                    h->W("embed_text.4.weight"), h->W("embed_text.4.bias"), h->W("predict_cat.0.weight"), h->W("predict_cat.0.bias"),
                    h->W("predict_cat.2.weight"), h->W("predict_cat.2.bias"), h->W("predict_cat.4.weight"), h->W("predict_cat.4.bias"),
@@ -458,14 +477,15 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
                                                      q.xyz[3], q.xyz[4], st); });
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   static const bool fork_nn_env = !(getenv("LSDM_NN_STREAM") && atoi(getenv("LSDM_NN_STREAM")) == 0);
-  const bool fork_nn = fork_cond && fork_nn_env;  // ball queries and 3-NN searches both depend on the FPS result only: two streams
+  const bool fork_nn = fork_streams && fork_nn_env;  // ball queries and 3-NN searches both depend on the FPS result only: two streams
   if (fork_nn) {
     CK(cudaEventRecord(h->ev_fps, st));
     CK(cudaStreamWaitEvent(h->nn_st, h->ev_fps, 0));
   }
-  const bool want_plan = h->sa1_compact && h->precision >= 1 && h->sa_fused > 0;
+  // skip_level0 (`loop_invariants` bit 2): sa1 keeps every point, so its groups were found once per call in cloud order
+  const bool want_plan = !skip_level0 && h->sa1_compact && h->precision >= 1 && h->sa_fused > 0;
   bool plan_done = false;
-  for (int l = 0; l < 4; ++l)
+  for (int l = skip_level0 ? 1 : 0; l < 4; ++l)
     prof_launch(h, st, K_BALL, [&] {
       if (l <= 1 && ((h->select_grid >> l) & 1)) {  // levels 0 and 1: cell grid instead of the 1024 x 1024 / 256 x 1024 scan (identical groups)
         const bool with_plan = l == 0 && want_plan;  // the level-0 grid kernel also writes the plan of sa1's distinct rows
@@ -503,8 +523,37 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   return LSDM_OK;
 }
 
+// out[c, j, 0:64] = src[c, idx[c, j], 0:64] for 1024-row clouds (16 threads per 256-byte row)
+__global__ void permute_rows64_kernel(const float* __restrict__ src, const int* __restrict__ idx, int64_t rows, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = i >> 4;
+  if (row >= rows) return;
+  const int q = (int)(i & 15);
+  const int64_t cloud_base = row & ~(int64_t)1023;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(src + (cloud_base + idx[row]) * 64) + q);
+  reinterpret_cast<float4*>(out + row * 64)[q] = v;
+}
+
+// sa1 + level-0 ball query in cloud order (centroids = the cloud's own points), once per lsdm_sample_loop call.
+int sa1_cloud_order(lsdm_handle* h, const float* clouds, int C, cudaStream_t st) {
+  Workspace& w = h->ws;
+  int r = prof_launch(h, st, K_BALL, [&] {
+    return launch_ball_query_grid(clouds, clouds, C, kSA[0].N, kSA[0].npoint, kSA[0].radius, w.c_grp, st, w.c_plan_rows, w.c_plan_used, w.c_plan_tiles);
+  });
+  if (r <= 0) return fail(LSDM_EINVAL, "cell-grid ball query unavailable");
+  prof_launch(h, st, K_BALL, [&] { return launch_sa1_plan_scan(w.c_plan_tiles, C, w.c_plan_off, w.c_plan_n, st); });
+  r = prof_launch(h, st, K_GEMM, [&] {
+    return launch_sa1_compact(clouds, clouds, w.c_plan_rows, w.c_plan_used, w.c_plan_off, w.c_plan_n, h->host_wx[0].data(), h->host_wf[0].data(),
+                              h->host_b1[0].data(), h->host_b2[0].data(), h->sa_w[0][1], h->sa_w[0][2], h->sa_b[0][2], C, w.f1canon,
+                              h->precision == 1, st);
+  }, "sa_fused sa1 (once per call)", 2.0 * C * 1024 * 32 * ((double)kSA[0].mlp[0] * kSA[0].mlp[1] + (double)kSA[0].mlp[1] * kSA[0].mlp[2]));
+  if (r < 0) return fail(LSDM_EINVAL, "fused sa1 kernel unavailable");
+  CK(cudaPeekAtLastError());
+  return LSDM_OK;
+}
+
 // Dense layers of PointNet++ given the selection results.
-int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cudaStream_t st, int C) {
+int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cudaStream_t st, int C, bool sa1_canon = false) {
   Workspace& w = h->ws;
   const float* xyz[5] = {clouds, q.xyz[1], q.xyz[2], q.xyz[3], q.xyz[4]};
   const float* feat[5] = {clouds, w.feat[1], w.feat[2], w.feat[3], w.feat[4]};
@@ -512,6 +561,14 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     const SASpec& s = kSA[l];
     const int N = s.N, S = s.npoint, C1 = s.mlp[0], C2 = s.mlp[1], C3 = s.mlp[2];
     const float* P = nullptr;
+    if (l == 0 && sa1_canon) {  // level-1 features = the rows of the per-call cloud-order result in this step's level-0 FPS order
+      prof_launch(h, st, K_GATHER, [&] {
+        const int64_t n = (int64_t)C * 1024 * 16;
+        permute_rows64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.f1canon, q.idx[0], (int64_t)C * 1024, w.feat[1]);
+        return 1;
+      });
+      continue;
+    }
     if (l > 0) {  // first conv, feature half, once per source point
       GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE, 0, -1, GF_A_ROUNDED));
       P = w.tP;
@@ -1133,7 +1190,7 @@ int dense_phase_train(lsdm_handle* h, const Workspace::Sel& q, const float* clou
 // Everything of the condition encoder except the selection chain (which the caller has already enqueued for set `si`).
 static int encode_dense(lsdm_handle* h, const float* text, const float* objs, const float* cats, const float* mask_global, int si,
                         cudaStream_t st, const float* train_drop_mask = nullptr, const float* clouds = nullptr, int n_clouds = -1,
-                        const int* remap = nullptr) {
+                        const int* remap = nullptr, bool sa1_canon = false) {
   Workspace& w = h->ws;
   const int B = h->cfg.batch_local;
   if (!clouds) clouds = objs, n_clouds = B * NOBJ;
@@ -1141,7 +1198,7 @@ static int encode_dense(lsdm_handle* h, const float* text, const float* objs, co
     GE(dense_phase_train(h, w.sel[si], objs, train_drop_mask, st));
   } else {
     if (h->fold_dirty) GE(lsdm_finalize_weights(h, st));  // running statistics moved since the last fold
-    GE(dense_phase(h, w.sel[si], clouds, st, n_clouds));
+    GE(dense_phase(h, w.sel[si], clouds, st, n_clouds, sa1_canon));
   }
   SceneWeights sw{h->W("pcd_attention.k_proj_weight"), h->W("pcd_attention.v_proj_weight"), h->W("pcd_attention.in_proj_bias"),
                   h->W("pcd_attention.out_proj.weight"), h->W("pcd_attention.out_proj.bias"),
@@ -1279,9 +1336,36 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     CK(cudaStreamWaitEvent(side, h->ev_fork, 0));
     CK(cudaStreamWaitEvent(dst, h->ev_fork, 0));
   }
+  // loop invariants (STRICT): what reads nothing that changes over the loop is computed once per call.
+  //  bit 0  text / category / translation MLPs, object-attention weights, human decoder: step 0's results are copied into the
+  //         other two buffer sets and later steps skip those kernels;
+  //  bit 2  sa1 keeps all 1024 points of a cloud (npoint = N), so the level-0 FPS draw only decides the ORDER of its centroids: a
+  //         centroid's ball-query group and pooled feature are functions of its coordinates and the cloud.  They are computed once in
+  //         cloud order (on the dense stream, which is idle during the first selection) and every step gathers its level-1 rows by
+  //         its level-0 FPS indices (the FPS itself still runs: level 1 depends on the order)
+  const int inv = (!hoisted && n_steps > 1) ? h->loop_invariants : 0;
+  const bool skip_cond = (inv & 1) != 0;
+  const bool sa1_canon = (inv & 4) != 0 && h->sa1_compact && h->precision >= 1 && h->sa_fused > 0 && (h->select_grid & 1);
+  if (sa1_canon) {
+    const int n_enc = clouds ? nc : C;
+    GE(sa1_cloud_order(h, clouds ? clouds : objs, n_enc, dst));
+    if (h->profiling) h->gemm_flops += 2.0 * n_enc * 1024 * 32 * ((double)kSA[0].mlp[0] * kSA[0].mlp[1] + (double)kSA[0].mlp[1] * kSA[0].mlp[2]);
+  }
   tl_begin(0, 'S', side);
   const bool fork_cond = pipelined && h->cond_stream;
-  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side, clouds, nc, active, fork_cond));
+  GE(select_phase(h, h->ws.sel[0], text, objs, cats, mask_global, fps_start_all, side, clouds, nc, active, fork_cond, false, sa1_canon));
+  if (skip_cond) {
+    Workspace::Sel& s0 = h->ws.sel[0];
+    for (int j = 1; j < 3; ++j) {
+      Workspace::Sel& sj = h->ws.sel[j];
+      CK(cudaMemcpyAsync(sj.enc, s0.enc, sizeof(float) * B * LAT, cudaMemcpyDeviceToDevice, side));
+      CK(cudaMemcpyAsync(sj.out_cat, s0.out_cat, sizeof(float) * B * h->cfg.n_cats, cudaMemcpyDeviceToDevice, side));
+      CK(cudaMemcpyAsync(sj.attn_w, s0.attn_w, sizeof(float) * B * NOBJ, cudaMemcpyDeviceToDevice, side));
+      CK(cudaMemcpyAsync(sj.tr, s0.tr, sizeof(float) * C * TRANS, cudaMemcpyDeviceToDevice, side));
+      CK(cudaMemcpyAsync(sj.qq, s0.qq, sizeof(float) * C * TRANS, cudaMemcpyDeviceToDevice, side));
+      CK(cudaMemcpyAsync(sj.hm, s0.hm, sizeof(float) * B * NPTS * 3, cudaMemcpyDeviceToDevice, side));
+    }
+  }
   tl_end(side);
   if (pipelined) CK(cudaEventRecord(h->ev_sel[0], side));
   for (int k = 0; k < n_steps; ++k) {
@@ -1293,18 +1377,19 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
         CK(cudaStreamWaitEvent(side, h->ev_step[sn], 0));
       }
       tl_begin(k + 1, 'S', side);
-      GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active, fork_cond));
+      GE(select_phase(h, h->ws.sel[sn], text, objs, cats, mask_global, fps_start_all + (size_t)(k + 1) * 4 * C, side, clouds, nc, active, fork_cond,
+                      skip_cond, sa1_canon));
       tl_end(side);
       CK(cudaEventRecord(h->ev_sel[sn], side));
     }
     if (!pipelined && !hoisted && k >= 1)
-      GE(select_phase(h, h->ws.sel[si], text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, st, clouds, nc, active));
+      GE(select_phase(h, h->ws.sel[si], text, objs, cats, mask_global, fps_start_all + (size_t)k * 4 * C, st, clouds, nc, active, false, skip_cond, sa1_canon));
     if (!hoisted || k == 0) {
       if (pipelined) {
         CK(cudaStreamWaitEvent(dst, h->ev_sel[si], 0));  // (select(k) already waited for step(k-3), the last reader of pcd_out[si])
       }
       tl_begin(k, 'D', dst);
-      GE(encode_dense(h, text, objs, cats, mask_global, si, dst, nullptr, clouds, nc, remap));
+      GE(encode_dense(h, text, objs, cats, mask_global, si, dst, nullptr, clouds, nc, remap, sa1_canon));
       tl_end(dst);
       if (pipelined) {
         CK(cudaEventRecord(h->ev_dense[si], dst));
@@ -1319,7 +1404,10 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     // STRICT recomputes the guiding points every step like the reference; hoisted only needs them at the end
     const bool want_guiding = !hoisted || last;
     tl_begin(k, 'X', st);
-    const int hs = (hoisted && h->hoist_split && h->x0_fused) ? (k == 0 ? 1 : 2) : 0;
+    // the embedding's text half once per call, its time half once per step for the whole batch: the hoisted loop (`hoist_split`) and,
+    // because text and the shared t are just as loop-invariant / batch-shared there, the STRICT loop (`loop_invariants` bit 1)
+    const bool split_emb = hoisted ? (h->hoist_split != 0) : ((inv & 2) != 0);
+    const int hs = (split_emb && h->x0_fused) ? (k == 0 ? 1 : 2) : 0;
     GE(step_core(h, x, tvec, noise_all + (size_t)k * per, x, last ? x0_out : nullptr, last ? guiding_out : nullptr,
                  want_guiding, clip_denoised, st, si, hs));
     tl_end(st);
@@ -1537,6 +1625,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   }
   if (strcmp(name, "select_grid") == 0 && value >= 0 && value <= 15) {
     h->select_grid = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "loop_invariants") == 0 && value >= 0 && value <= 7) {
+    h->loop_invariants = value;
     return LSDM_OK;
   }
   if (strcmp(name, "hoist_split") == 0 && (value == 0 || value == 1)) {

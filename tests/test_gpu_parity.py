@@ -666,6 +666,44 @@ def test_hoisted_loop_embedding_split_matches_full_chain():
         assert rel_l2(a.cpu(), b.cpu()) < 1e-5
 
 
+def test_strict_loop_invariants_match_per_step_recompute():
+    """STRICT library loop, `loop_invariants`: what reads nothing that changes over the loop is computed once per call instead of
+    once per step -- bit 0: text / category / translation MLPs, object-attention weights, human decoder (same kernels on the same
+    inputs: BIT-identical); bit 2: sa1 + the level-0 ball query evaluated in cloud order and permuted by each step's level-0 FPS
+    order (sa1 keeps all 1024 points, so a centroid's group and pooled feature do not depend on the draw: BIT-identical, also for
+    clouds with duplicate points where the FPS order is not a permutation); bit 1: the embedding's text half once per call and its
+    time half once per step for the whole batch (every sample shares t; same sums split after 128 of 256 terms -> 1e-5)."""
+    B, K = 5, 5
+    m, diff = _model("wellcond")
+    inp = syn.make_inputs(91, B)
+    objs = inp["given_objs"].clone()
+    objs[0, 1] = (torch.rand(1024, 3) - 0.5) * 0.05                 # dense: every r = 0.1 ball is full
+    objs[1, 2, 512:] = objs[1, 2, :512]                             # every point twice: FPS level 0 is not a permutation
+    objs[2, 3] = 0.0
+    objs[2, 3, 7] = torch.tensor([3.0, 3.0, 3.0])                   # 1023 coincident points + one outlier
+    inp["given_objs"] = objs
+    fps, noise = syn.make_step_randoms(92, B, K)
+    g = _cuda(inp)
+    eng = diff._engine(m, B, torch.device("cuda", 0))
+    outs = {}
+    for flag in (0, 1, 4, 5, 2, 7):
+        eng.set_option("loop_invariants", flag)
+        try:
+            x = g["x_T"].clone()
+            x0, gd_ = eng.sample_loop(x, g["text_emb"], g["given_objs"], g["given_cats"], g["mask"], fps.cuda(), noise.cuda(), 999, False)
+            torch.cuda.synchronize()
+            outs[flag] = (x.clone(), x0.clone(), gd_.clone(), eng.out_cat().clone())
+        finally:
+            eng.set_option("loop_invariants", 7)
+    for flag in (1, 4, 5):
+        for a, b in zip(outs[flag], outs[0]):
+            assert torch.equal(a, b), flag
+    for a, b in zip(outs[7], outs[2]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[2], outs[0]):
+        assert rel_l2(a.cpu(), b.cpu()) < 1e-5
+
+
 def test_cell_grid_selections_are_identical_to_the_full_scans():
     """Ball queries (levels 0, 1) and 3-NN (fp2, fp1) through the per-cloud cell grid ("select_grid") against the full O(N^2) scans:
     every index and every interpolation weight must be IDENTICAL, on random clouds and on adversarial ones -- one tight cluster, far
