@@ -504,13 +504,14 @@ def run_ours(args):
             per_step_all = {"value": Bg * K / (ims * 1e-3), "unit": UNIT, "ms_per_step": ims / K,
                             "rel_l2_vs_value_leg": float(((xi - x).norm() / x.norm()).item()),
                             "note": "lsdm_set_option('loop_invariants', 0): the condition MLPs, the human decoder, the text half of the embedding, "
-                                    "sa1 and the level-0 ball query run every step although nothing they read changes over the loop.  `value` "
+                                    "sa1 and the level-0 ball query run every step although nothing they read changes over the loop, and the guiding points (second "
+                                    "x0-network pass) are computed on every step although only the last step's are ever visible.  `value` "
                                     "computes them once per p_sample_loop call, inside the timed region (same kernels on the same inputs: "
                                     "bit-identical, except the embedding whose 256-term sums are split into a time and a text half -> 1e-6; "
                                     "tests/test_gpu_parity.py::test_strict_loop_invariants_match_per_step_recompute).  PointNet++ levels 2-4, all "
                                     "FPS levels, the scene branch and both x0-network passes still run every step with fresh FPS draws"}
         finally:
-            eng.set_option("loop_invariants", 7)
+            eng.set_option("loop_invariants", 15)
         if rank == 0:
             print(f"[bench] loop invariants recomputed every step: {per_step_all['value']:.1f} {UNIT}, rel_l2 {per_step_all['rel_l2_vs_value_leg']:.2e}",
                   file=sys.stderr, flush=True)

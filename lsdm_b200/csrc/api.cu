@@ -120,10 +120,11 @@ struct lsdm_handle {
   std::vector<float> host_tail;  // [b2|b3|bh|conv2.w|conv2.b] of the fused backbone tail
   std::vector<float> host_fp1_b1;  // folded bias of fp1's first conv (kernel parameter of the fused fp1 + head kernel)
   int select_grid = 9;           // bit mask: ball query level 0 (1), level 1 (2), 3-NN of fp2 (4), of fp1 (8) through a per-cloud cell grid (identical selections)
-  int loop_invariants = 7;       // lsdm_sample_loop, STRICT: what is computed once per call instead of once per step because its inputs do not
+  int loop_invariants = 15;      // lsdm_sample_loop, STRICT: what is computed once per call instead of once per step because its inputs do not
                                  //    change over the loop (same kernels, same inputs -> same bits): 1 condition MLPs + human decoder,
                                  //    2 text half of the embedding (the time half once per step for the whole batch: every sample shares t),
-                                 //    4 sa1 + level-0 ball query in cloud order (the level-0 FPS only permutes its rows)
+                                 //    4 sa1 + level-0 ball query in cloud order (the level-0 FPS only permutes its rows),
+                                 //    8 guiding points (second x0-network pass) on the call's last step only (earlier ones are never visible)
   int hoist_split = 1;           // 1: the hoisted loop computes the time half of the embedding once per step for the whole batch and the text half once per loop
   int sa1_compact = 1;           // 1: sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles)
   int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
@@ -1402,7 +1403,9 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     });
     const bool last = (k == n_steps - 1);
     // STRICT recomputes the guiding points every step like the reference; hoisted only needs them at the end
-    const bool want_guiding = !hoisted || last;
+    // (`loop_invariants` bit 3: the guiding points of a step are only ever visible after the call's last step -- the model keeps the
+    // latest `saved_guiding_points` --, so the second x0-network pass of the earlier steps is a dead store)
+    const bool want_guiding = last || (!hoisted && (inv & 8) == 0);
     tl_begin(k, 'X', st);
     // the embedding's text half once per call, its time half once per step for the whole batch: the hoisted loop (`hoist_split`) and,
     // because text and the shared t are just as loop-invariant / batch-shared there, the STRICT loop (`loop_invariants` bit 1)
@@ -1627,7 +1630,7 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
     h->select_grid = value;
     return LSDM_OK;
   }
-  if (strcmp(name, "loop_invariants") == 0 && value >= 0 && value <= 7) {
+  if (strcmp(name, "loop_invariants") == 0 && value >= 0 && value <= 15) {
     h->loop_invariants = value;
     return LSDM_OK;
   }

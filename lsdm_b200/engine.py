@@ -67,7 +67,7 @@ class Engine:
         self.set_option("sa1_compact", int(os.environ.get("LSDM_SA1_COMPACT", "1")))
         self.set_option("select_grid", int(os.environ.get("LSDM_SELECT_GRID", "9")))
         self.set_option("cond_stream", int(os.environ.get("LSDM_COND_STREAM", "1")))
-        self.set_option("loop_invariants", int(os.environ.get("LSDM_LOOP_INVARIANTS", "7")))
+        self.set_option("loop_invariants", int(os.environ.get("LSDM_LOOP_INVARIANTS", "15")))
 
     # ------------------------------------------------------------------ lifecycle
     @_on_device

@@ -672,7 +672,8 @@ def test_strict_loop_invariants_match_per_step_recompute():
     inputs: BIT-identical); bit 2: sa1 + the level-0 ball query evaluated in cloud order and permuted by each step's level-0 FPS
     order (sa1 keeps all 1024 points, so a centroid's group and pooled feature do not depend on the draw: BIT-identical, also for
     clouds with duplicate points where the FPS order is not a permutation); bit 1: the embedding's text half once per call and its
-    time half once per step for the whole batch (every sample shares t; same sums split after 128 of 256 terms -> 1e-5)."""
+    time half once per step for the whole batch (every sample shares t; same sums split after 128 of 256 terms -> 1e-5); bit 3: the
+    guiding points (second x0-network pass) only on the call's last step -- the earlier ones are never visible (BIT-identical)."""
     B, K = 5, 5
     m, diff = _model("wellcond")
     inp = syn.make_inputs(91, B)
@@ -686,7 +687,7 @@ def test_strict_loop_invariants_match_per_step_recompute():
     g = _cuda(inp)
     eng = diff._engine(m, B, torch.device("cuda", 0))
     outs = {}
-    for flag in (0, 1, 4, 5, 2, 7):
+    for flag in (0, 1, 4, 8, 13, 2, 15):
         eng.set_option("loop_invariants", flag)
         try:
             x = g["x_T"].clone()
@@ -694,11 +695,11 @@ def test_strict_loop_invariants_match_per_step_recompute():
             torch.cuda.synchronize()
             outs[flag] = (x.clone(), x0.clone(), gd_.clone(), eng.out_cat().clone())
         finally:
-            eng.set_option("loop_invariants", 7)
-    for flag in (1, 4, 5):
+            eng.set_option("loop_invariants", 15)
+    for flag in (1, 4, 8, 13):
         for a, b in zip(outs[flag], outs[0]):
             assert torch.equal(a, b), flag
-    for a, b in zip(outs[7], outs[2]):
+    for a, b in zip(outs[15], outs[2]):
         assert torch.equal(a, b)
     for a, b in zip(outs[2], outs[0]):
         assert rel_l2(a.cpu(), b.cpu()) < 1e-5
