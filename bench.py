@@ -484,6 +484,7 @@ def run_ours(args):
             ams = dev_timed(lambda: run_steps(W, K, xa))
             n_absent = int((inp["given_objs"][sl].abs().sum((2, 3)) == 0).sum())
             all_clouds = {"value": Bg * K / (ams * 1e-3), "unit": UNIT, "ms_per_step": ams / K, "identical_output": bool(torch.equal(xa, x)),
+                          "max_abs_diff": float((xa - x).abs().max().item()),
                           "absent_clouds": n_absent, "clouds": 9 * B,
                           "note": "lsdm_set_option('dedup_absent', 0): PointNet++ runs on all 9B clouds.  `value` encodes the absent objects' all-zero "
                                   "cloud once per step and shares the result (eval-mode clouds are independent and an all-zero cloud's output does not "
@@ -491,7 +492,7 @@ def run_ours(args):
         finally:
             eng.set_option("dedup_absent", 1)
         if rank == 0:
-            print(f"[bench] all clouds encoded (dedup off): {all_clouds['value']:.1f} {UNIT}, identical={all_clouds['identical_output']}, "
+            print(f"[bench] all clouds encoded (dedup off): {all_clouds['value']:.1f} {UNIT}, identical={all_clouds['identical_output']} (max abs diff {all_clouds['max_abs_diff']:.3g}), "
                   f"absent {all_clouds['absent_clouds']}/{9 * B}", file=sys.stderr, flush=True)
     # ---- transparency leg 3: everything recomputed every step, loop-invariant or not ----
     per_step_all = None

@@ -92,6 +92,8 @@ struct Workspace {
   // they were computed from -- written once per lsdm_sample_loop call, permuted per step by the level-0 FPS order
   float* f1canon;
   int *c_grp, *c_plan_rows, *c_plan_used, *c_plan_tiles, *c_plan_off, *c_plan_n;
+  int64_t* tb_t;  // time half of the split embedding for TIME_BATCH steps at once
+  float *tb_s256, *tb_H1, *tb_H1_lo, *tb_H2, *tb_H2_lo, *tb_embpre, *tb_embpre_lo, *a_t_all;
   float *ctext, *a_t;  // hoisted loop: loop-invariant text half [rows,128] and batch-shared time half [1024,128] of the embedding pre-activation
   float *H1_lo, *H2_lo, *embpre_lo, *cat_lo, *h1_lo, *c1_lo, *c2_lo;  // 3xTF32 residual planes of the step network's activations
   size_t bytes;
@@ -125,6 +127,7 @@ struct lsdm_handle {
                                  //    2 text half of the embedding (the time half once per step for the whole batch: every sample shares t),
                                  //    4 sa1 + level-0 ball query in cloud order (the level-0 FPS only permutes its rows),
                                  //    8 guiding points (second x0-network pass) on the call's last step only (earlier ones are never visible)
+  int time_batch = 1;            // 1: the time half of the split embedding is evaluated for TIME_BATCH steps per launch sequence
   int hoist_split = 1;           // 1: the hoisted loop computes the time half of the embedding once per step for the whole batch and the text half once per loop
   int sa1_compact = 1;           // 1: sa1 runs on the distinct rows of every ball-query group only (bit-identical, ~6x fewer tiles)
   int x0_fused = 1;              // 1: the x0 network of a step runs as one persistent kernel (x0net_fused.cu); 0: one GEMM per layer
@@ -336,6 +339,18 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   w->f1 = a.take<float>(2 * rows * 64);
   w->ctext = a.take<float>(rows * 128);
   w->a_t = a.take<float>((size_t)NPTS * 128);
+  {
+    const size_t G = 16;  // TIME_BATCH
+    w->tb_t = a.take<int64_t>(G);
+    w->tb_s256 = a.take<float>(G * 256);
+    w->tb_H1 = a.take<float>(G * 256 * 128);
+    w->tb_H1_lo = a.take<float>(G * 256 * 128);
+    w->tb_H2 = a.take<float>(G * 256 * 512);
+    w->tb_H2_lo = a.take<float>(G * 256 * 512);
+    w->tb_embpre = a.take<float>(G * NPTS * 128);
+    w->tb_embpre_lo = a.take<float>(G * NPTS * 128);
+    w->a_t_all = a.take<float>(G * NPTS * 128);
+  }
   w->x0 = a.take<float>(rows * 3);
   w->guiding = a.take<float>(rows * 3);
   w->loss_scratch = a.take<float>(64);
@@ -664,9 +679,63 @@ __global__ void emb_combine_kernel(const float* __restrict__ a_t, const float* _
   *reinterpret_cast<float4*>(lo + row * 256 + q * 4) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
+// The embedding chain emb[b,p,:] = act(Wc[:, s0:s0+ns] . u(b,p) + bias) for `nb` samples: timestep embedding -> [ts || enc] scalars ->
+// upsampler 1 -> 128 -> 512 -> 1024 points -> combine (model/sdm.py:108-122,164-167,208), over the scalars [s0, s0 + ns) only.
+struct UpsampleBufs { const int64_t* t; const float* enc; float *s256, *H1, *H1_lo, *H2, *H2_lo, *embpre, *embpre_lo; };
+int upsample_chain(lsdm_handle* h, cudaStream_t st, const UpsampleBufs& u, bool sp, int ps, int nb, int s0, int ns, const float* combine_bias,
+                   int combine_act, float* out, int64_t ld_out, float* out_lo) {
+  prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
+                                   h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
+                                   h->W("embed_timestep.time_embed.2.bias"), u.t, u.enc, h->W("upsampling_layer.0.weight"),
+                                   h->W("upsampling_layer.0.bias"), nb, u.s256, u.H1, sp ? u.H1_lo : nullptr, st); });
+  GE(gemm(h, st, u.H1, 128, h->W("upsampling_layer.2.weight"), 128, u.H2, 512, h->W("upsampling_layer.2.bias"), nb * 256, 512,
+          128, ACT_GELU, 0, ps, 0, sp ? u.H1_lo : nullptr, sp ? u.H2_lo : nullptr));
+  {
+    // embpre[b][p][s] = gelu(sum_k U4[p][k] H2[b][s0 + s][k] + b4[p]): the upsampler's last layer written point-major
+    GemmArgs g{};
+    g.A = h->W("upsampling_layer.4.weight"); g.lda = 512; g.strideA = 0;
+    g.W = u.H2 + (size_t)s0 * 512; g.ldw = 512; g.strideW = 256 * 512;
+    g.C = u.embpre; g.ldc = ns; g.strideC = (int64_t)NPTS * ns;
+    g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
+    g.M = NPTS; g.N = ns; g.K = 512; g.batch = nb; g.act = ACT_GELU; g.group_max = 0; g.precision = ps;
+    if (sp) {
+      g.A_lo = g.A + h->lo_delta;
+      g.A = g.A + h->round_delta;
+      g.W_lo = u.H2_lo + (size_t)s0 * 512;
+      g.C_lo = u.embpre_lo;
+    }
+    int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); }, "gemm p2 upsampler K512 batched",
+                        2.0 * g.M * (double)g.N * g.K * g.batch);
+    if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
+    if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
+  }
+  GE(gemm(h, st, u.embpre, ns, h->W("combine_extraction.0.weight") + s0, 256, out, ld_out, combine_bias, nb * NPTS, 128, ns, combine_act, 0, ps, 0,
+          sp ? u.embpre_lo : nullptr, out_lo));
+  return LSDM_OK;
+}
+
+// Time half of the split embedding for the next `n` steps of a sampling loop (t_first, t_first - 1, ...): every sample shares t, so a
+// step's A_t[p,:] = Wc[:, :128] . u_ts(p) is one "sample" of the chain; TIME_BATCH steps are evaluated per launch sequence instead of
+// three latency-bound launches per step on the stream that is serial in x.  Row arithmetic does not depend on the batch: same bits.
+constexpr int TIME_BATCH = 16;
+__global__ void fill_t_run_kernel(int64_t* t, int n, int64_t t_first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = t_first - i;
+}
+int time_half_batch(lsdm_handle* h, int64_t t_first, int n, cudaStream_t st) {
+  Workspace& w = h->ws;
+  prof_launch(h, st, K_OTHER, [&] {
+    fill_t_run_kernel<<<1, TIME_BATCH, 0, st>>>(w.tb_t, n, t_first);
+    return 1;
+  });
+  UpsampleBufs u{w.tb_t, nullptr, w.tb_s256, w.tb_H1, w.tb_H1_lo, w.tb_H2, w.tb_H2_lo, w.tb_embpre, w.tb_embpre_lo};
+  return upsample_chain(h, st, u, true, h->precision_step, n, 0, 128, nullptr, ACT_NONE, w.a_t_all, 128, nullptr);
+}
+
 // x/t-dependent part: timestep embedding, upsampler, x += pcd_out, Input/OutputProcess, optional posterior.
 int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, float* sample_out, float* x0_out,
-              float* guiding_out, bool want_guiding, int clip, cudaStream_t st, int si = -1, int hoist_split = 0) {
+              float* guiding_out, bool want_guiding, int clip, cudaStream_t st, int si = -1, int hoist_split = 0,
+              const float* a_t_pre = nullptr) {
   // hoist_split (hoisted sampling loop only, every sample shares t): 1 = first step (also builds the loop-invariant text half of
   // the embedding), 2 = later steps
   Workspace& w = h->ws;
@@ -681,44 +750,22 @@ int step_core(lsdm_handle* h, float* x, const int64_t* t, const float* noise, fl
   // ---- the step's embedding emb[b,p,:] = gelu(Wc . [u_ts(p) || u_text(b,p)] + bc)  (model/sdm.py:164-167,208) ----
   // `nb` samples, scalars [s0, s0 + ns) of [ts || enc], combine columns [s0, s0 + ns): the full chain is (B, 0, 256); the
   // hoisted loop splits it into a batch-shared time half (1, 0, 128) and a loop-invariant text half (B, 128, 128).
+  const UpsampleBufs ub{w.t_dev, w.sel[si].enc, w.s256, w.H1, w.H1_lo, w.H2, w.H2_lo, w.embpre, w.embpre_lo};
   auto upsample = [&](int nb, int s0, int ns, const float* combine_bias, int combine_act, float* out, int64_t ld_out, float* out_lo) -> int {
-    prof_launch(h, st, K_COND, [&] { return launch_time_embed(h->W("embed_timestep.sequence_pos_encoder.pe"), h->W("embed_timestep.time_embed.0.weight"),
-                                     h->W("embed_timestep.time_embed.0.bias"), h->W("embed_timestep.time_embed.2.weight"),
-                                     h->W("embed_timestep.time_embed.2.bias"), w.t_dev, w.sel[si].enc, h->W("upsampling_layer.0.weight"),
-                                     h->W("upsampling_layer.0.bias"), nb, w.s256, w.H1, sp ? w.H1_lo : nullptr, st); });
-    GE(gemm(h, st, w.H1, 128, h->W("upsampling_layer.2.weight"), 128, w.H2, 512, h->W("upsampling_layer.2.bias"), nb * 256, 512,
-            128, ACT_GELU, 0, ps, 0, sp ? w.H1_lo : nullptr, sp ? w.H2_lo : nullptr));
-    {
-      // embpre[b][p][s] = gelu(sum_k U4[p][k] H2[b][s0 + s][k] + b4[p]): the upsampler's last layer written point-major
-      GemmArgs g{};
-      g.A = h->W("upsampling_layer.4.weight"); g.lda = 512; g.strideA = 0;
-      g.W = w.H2 + (size_t)s0 * 512; g.ldw = 512; g.strideW = 256 * 512;
-      g.C = w.embpre; g.ldc = ns; g.strideC = (int64_t)NPTS * ns;
-      g.bias = h->W("upsampling_layer.4.bias"); g.bias_mode = 2;
-      g.M = NPTS; g.N = ns; g.K = 512; g.batch = nb; g.act = ACT_GELU; g.group_max = 0; g.precision = ps;
-      if (sp) {
-        g.A_lo = g.A + h->lo_delta;
-        g.A = g.A + h->round_delta;
-        g.W_lo = w.H2_lo + (size_t)s0 * 512;
-        g.C_lo = w.embpre_lo;
-      }
-      int r = prof_launch(h, st, K_GEMM, [&] { return launch_gemm(g, st); }, "gemm p2 upsampler K512 batched",
-                          2.0 * g.M * (double)g.N * g.K * g.batch);
-      if (r < 0) return fail(LSDM_EINVAL, "upsampler gemm");
-      if (h->profiling) h->gemm_flops += 2.0 * g.M * (double)g.N * g.K * g.batch;
-    }
-    GE(gemm(h, st, w.embpre, ns, h->W("combine_extraction.0.weight") + s0, 256, out, ld_out, combine_bias, nb * NPTS, 128, ns, combine_act, 0, ps, 0,
-            sp ? w.embpre_lo : nullptr, out_lo));
-    return LSDM_OK;
+    return upsample_chain(h, st, ub, sp, ps, nb, s0, ns, combine_bias, combine_act, out, ld_out, out_lo);
   };
   if (hoist_split && sp) {
     if (hoist_split == 1)   // once per loop: C_text[b,p,:] = Wc[:, 128:] . u_text(b,p) + bc
       GE(upsample(B, 128, 128, h->W("combine_extraction.0.bias"), ACT_NONE, w.ctext, 128, nullptr));
     // every step: A_t[p,:] = Wc[:, :128] . u_ts(p) for the ONE timestep all samples of the loop share, then emb = gelu(A_t + C_text)
-    GE(upsample(1, 0, 128, nullptr, ACT_NONE, w.a_t, 128, nullptr));
+    // (a_t_pre: the loop evaluated it for a run of steps at once, time_half_batch)
+    if (!a_t_pre) {
+      GE(upsample(1, 0, 128, nullptr, ACT_NONE, w.a_t, 128, nullptr));
+      a_t_pre = w.a_t;
+    }
     prof_launch(h, st, K_DENOISE, [&] {
       const int64_t n = (int64_t)rows * 32;
-      emb_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.a_t, w.ctext, rows, w.cat + 128, w.cat_lo + 128);
+      emb_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a_t_pre, w.ctext, rows, w.cat + 128, w.cat_lo + 128);
       return 1;
     });
   } else {
@@ -1411,8 +1458,13 @@ LSDM_API int lsdm_sample_loop(lsdm_handle* h, float* x, const float* text, const
     // because text and the shared t are just as loop-invariant / batch-shared there, the STRICT loop (`loop_invariants` bit 1)
     const bool split_emb = hoisted ? (h->hoist_split != 0) : ((inv & 2) != 0);
     const int hs = (split_emb && h->x0_fused) ? (k == 0 ? 1 : 2) : 0;
+    const float* a_t_pre = nullptr;
+    if (hs && h->precision_step == 2 && g_gemm_async != 0 && h->time_batch) {
+      if (k % TIME_BATCH == 0) GE(time_half_batch(h, (int64_t)t_first - k, std::min(TIME_BATCH, n_steps - k), st));
+      a_t_pre = h->ws.a_t_all + (size_t)(k % TIME_BATCH) * NPTS * 128;
+    }
     GE(step_core(h, x, tvec, noise_all + (size_t)k * per, x, last ? x0_out : nullptr, last ? guiding_out : nullptr,
-                 want_guiding, clip_denoised, st, si, hs));
+                 want_guiding, clip_denoised, st, si, hs, a_t_pre));
     tl_end(st);
     if (pipelined) CK(cudaEventRecord(h->ev_step[si], st));
   }
@@ -1634,6 +1686,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
     h->loop_invariants = value;
     return LSDM_OK;
   }
+  if (strcmp(name, "time_batch") == 0 && (value == 0 || value == 1)) {
+    h->time_batch = value;
+    return LSDM_OK;
+  }
   if (strcmp(name, "hoist_split") == 0 && (value == 0 || value == 1)) {
     h->hoist_split = value;
     return LSDM_OK;
@@ -1648,6 +1704,10 @@ LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value) {
   }
   if (strcmp(name, "dedup_absent") == 0 && (value == 0 || value == 1)) {
     h->dedup_absent = value;
+    return LSDM_OK;
+  }
+  if (strcmp(name, "fps_compact") == 0 && (value == 0 || value == 1)) {
+    g_fps_compact = value;  // process-wide
     return LSDM_OK;
   }
   if (strcmp(name, "select_uniform") == 0 && (value == 0 || value == 1)) {

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
   __syncthreads();
   cta_linear<ACT_SILU>(w1, b1, s_pe, s_h, LAT, LAT);
   cta_linear<ACT_NONE>(w2, b2, s_h, s_s, LAT, LAT);
-  for (int i = tid; i < LAT; i += blockDim.x) s_s[LAT + i] = enc[(int64_t)b * LAT + i];
+  for (int i = tid; i < LAT; i += blockDim.x) s_s[LAT + i] = enc ? enc[(int64_t)b * LAT + i] : 0.f;  // (enc == nullptr: time half only)
   __syncthreads();
   for (int i = tid; i < 2 * LAT; i += blockDim.x) s256[(int64_t)b * 2 * LAT + i] = s_s[i];
   for (int i = tid; i < 2 * LAT * 128; i += blockDim.x) {

@@ -136,6 +136,7 @@ int launch_q_sample(const float* x0, const int64_t* t, const float* noise, const
 int launch_chamfer(const float* x, const float* y, int B, int n, int m, float* sums, cudaStream_t st, int sample_stride = 0);
 int launch_cat_loss(const float* probs, const float* target, int B, int C, float* sum, cudaStream_t st);
 
+extern int g_fps_compact;  // pointnet_select.cu: FPS level 0 drops the points at distance 0 every 128 rounds (same selection order)
 extern int g_select_uniform_shortcut;  // pointnet_select.cu: closed-form selections for clouds whose points all coincide
 
 // ---- api.cu: thread-local error message behind lsdm_last_error(); returns `code` ----

@@ -81,11 +81,133 @@ __device__ __forceinline__ void fps_level_warp(const float* __restrict__ src, in
   __syncwarp();  // the next level reads xyz_out (written by lane 0) from every lane, and rewrites the shared copy
 }
 
+// ---------------------------------------------------------------------------------------------
+// Level 0 keeps ALL 1024 points (npoint == N): after r rounds at least r points have minimum distance 0 -- the selected ones and
+// their exact duplicates -- and a point at distance 0 stays there, so it can only be "selected" again when every point is at 0, in
+// which case the argmax of the all-zero array is index 0 whoever is still tracked.  The warp therefore drops the dead points every
+// 128 rounds: the live (distance != 0) points are re-dealt over the lanes IN INDEX ORDER (ballot prefix sums through an 8 KB
+// shared staging area), so that position p = lane + 32 * slot still enumerates ascending indices and the tie rule (strict '>'
+// inside a lane, lowest index across lanes) is unchanged; phase k tracks 32 - 4k points per lane instead of 32.  Same IEEE
+// operations on every tracked point, hence the same selection order; 0.56 x the distance updates of level 0.
+// ---------------------------------------------------------------------------------------------
+template <int PER2>
+struct FpsPts {
+  float2 x[PER2], y[PER2], z[PER2], d[PER2];
+  unsigned i0[PER2], i1[PER2];  // original indices of the pair's two points
+};
+
+template <int PER2>
+__device__ __forceinline__ int fps_rounds_tracked(FpsPts<PER2>& P, int far, int it0, int n_rounds, int* __restrict__ idx_out,
+                                                  float* __restrict__ xyz_out, int lane, uint32_t s_pts) {
+  for (int it = it0; it < it0 + n_rounds; ++it) {
+    const float4 cc = lds_f4(s_pts + far * 16);
+    const float cx = cc.x, cy = cc.y, cz = cc.z;
+    if (lane == 0) {
+      idx_out[it] = far;
+      xyz_out[it * 3] = cx; xyz_out[it * 3 + 1] = cy; xyz_out[it * 3 + 2] = cz;
+    }
+    unsigned best_bits = 0u, best_idx = (unsigned)lane;
+    const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy), ncz = make_float2(-cz, -cz);
+#pragma unroll
+    for (int j = 0; j < PER2; ++j) {
+      // (products packed, sums scalar: see fps_level_warp)
+      const float2 dx = __fadd2_rn(P.x[j], ncx), dy = __fadd2_rn(P.y[j], ncy), dz = __fadd2_rn(P.z[j], ncz);
+      const float2 sxx = __fmul2_rn(dx, dx), syy = __fmul2_rn(dy, dy), szz = __fmul2_rn(dz, dz);
+      const float d0 = __fadd_rn(__fadd_rn(sxx.x, syy.x), szz.x), d1 = __fadd_rn(__fadd_rn(sxx.y, syy.y), szz.y);
+      const float n0 = fminf(d0, P.d[j].x), n1 = fminf(d1, P.d[j].y);
+      P.d[j] = make_float2(n0, n1);
+      const unsigned b0 = __float_as_uint(n0), b1 = __float_as_uint(n1);
+      if (b0 > best_bits) { best_bits = b0; best_idx = P.i0[j]; }
+      if (b1 > best_bits) { best_bits = b1; best_idx = P.i1[j]; }
+    }
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, best_bits);
+    far = (int)__reduce_min_sync(0xffffffffu, best_bits == wmax ? best_idx : 0xffffffffu);
+  }
+  return far;
+}
+
+// live points of P (distance != 0), in position order, -> Q (NEW2 pairs per lane; unused slots: a dead dummy at the origin)
+template <int OLD2, int NEW2>
+__device__ __forceinline__ void fps_compact(const FpsPts<OLD2>& P, FpsPts<NEW2>& Q, int lane, uint32_t s_pts, uint32_t s_stage) {
+  const unsigned lt = (1u << lane) - 1u;
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < OLD2; ++j) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float d = hf ? P.d[j].y : P.d[j].x;
+      const unsigned id = hf ? P.i1[j] : P.i0[j];
+      const bool live = !(d == 0.0f);
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        const uint32_t a = s_stage + (uint32_t)(base + __popc(m & lt)) * 8u;
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(__float_as_uint(d)), "r"(id) : "memory");
+      }
+      base += __popc(m);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NEW2; ++j) {
+    float dd[2], xx[2], yy[2], zz[2];
+    unsigned ii[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int pos = lane + (2 * j + hf) * 32;
+      dd[hf] = 0.0f; xx[hf] = 0.0f; yy[hf] = 0.0f; zz[hf] = 0.0f; ii[hf] = 0u;
+      if (pos < base) {
+        unsigned db, id;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(db), "=r"(id) : "r"(s_stage + (uint32_t)pos * 8u) : "memory");
+        const float4 c = lds_f4(s_pts + id * 16);
+        dd[hf] = __uint_as_float(db); xx[hf] = c.x; yy[hf] = c.y; zz[hf] = c.z; ii[hf] = id;
+      }
+    }
+    Q.x[j] = make_float2(xx[0], xx[1]); Q.y[j] = make_float2(yy[0], yy[1]); Q.z[j] = make_float2(zz[0], zz[1]);
+    Q.d[j] = make_float2(dd[0], dd[1]);
+    Q.i0[j] = ii[0]; Q.i1[j] = ii[1];
+  }
+  __syncwarp();  // the staging area is rewritten by the next compaction
+}
+
+template <int K>  // phase K of level 0: rounds [128 K, 128 K + 128) on 32 - 4 K points per lane, then hand the survivors on
+__device__ __forceinline__ void fps_level0_phase(FpsPts<16 - 2 * K>& P, int far, int* __restrict__ idx_out, float* __restrict__ xyz_out, int lane,
+                                                 uint32_t s_pts, uint32_t s_stage) {
+  far = fps_rounds_tracked<16 - 2 * K>(P, far, 128 * K, 128, idx_out, xyz_out, lane, s_pts);
+  if constexpr (K < 7) {
+    FpsPts<14 - 2 * K> Q;
+    fps_compact<16 - 2 * K, 14 - 2 * K>(P, Q, lane, s_pts, s_stage);
+    fps_level0_phase<K + 1>(Q, far, idx_out, xyz_out, lane, s_pts, s_stage);
+  }
+}
+
+__device__ __forceinline__ void fps_level0_compacting(const float* __restrict__ src, int start, int* __restrict__ idx_out, float* __restrict__ xyz_out,
+                                                      int lane, uint32_t s_pts, uint32_t s_stage) {
+  FpsPts<16> P;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int p0 = lane + (2 * j) * 32, p1 = p0 + 32;
+    P.x[j] = make_float2(src[p0 * 3], src[p1 * 3]);
+    P.y[j] = make_float2(src[p0 * 3 + 1], src[p1 * 3 + 1]);
+    P.z[j] = make_float2(src[p0 * 3 + 2], src[p1 * 3 + 2]);
+    P.d[j] = make_float2(1e10f, 1e10f);
+    P.i0[j] = (unsigned)p0; P.i1[j] = (unsigned)p1;
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(s_pts + p0 * 16), "f"(P.x[j].x), "f"(P.y[j].x) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_pts + p0 * 16 + 8), "f"(P.z[j].x) : "memory");
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(s_pts + p1 * 16), "f"(P.x[j].y), "f"(P.y[j].y) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_pts + p1 * 16 + 8), "f"(P.z[j].y) : "memory");
+  }
+  __syncwarp();
+  fps_level0_phase<0>(P, start, idx_out, xyz_out, lane, s_pts, s_stage);
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(32) fps4_kernel(const float* __restrict__ xyz0, const int64_t* __restrict__ start, int n_clouds,
                                                        int* __restrict__ idx1, int* __restrict__ idx2, int* __restrict__ idx3,
                                                        int* __restrict__ idx4, float* __restrict__ xyz1, float* __restrict__ xyz2,
-                                                       float* __restrict__ xyz3, float* __restrict__ xyz4, int uniform_shortcut) {
+                                                       float* __restrict__ xyz3, float* __restrict__ xyz4, int uniform_shortcut,
+                                                       int compact_level0) {
   __shared__ float4 s_copy[1024];
+  __shared__ uint2 s_live[1024];  // (distance bits, index) of the live points while level 0 re-deals them
   const uint32_t s_pts = smem_addr(s_copy);
   const int c = blockIdx.x, lane = threadIdx.x;
   const float* src = xyz0 + (int64_t)c * 1024 * 3;
@@ -98,7 +220,10 @@ __global__ void __launch_bounds__(32) fps4_kernel(const float* __restrict__ xyz0
   float* l2 = xyz2 + (int64_t)c * 256 * 3;
   float* l3 = xyz3 + (int64_t)c * 64 * 3;
   float* l4 = xyz4 + (int64_t)c * 16 * 3;
-  fps_level_warp<1024, 1024>(src, (int)start[0 * (int64_t)n_clouds + c], idx1 + (int64_t)c * 1024, l1, lane, uniform, s_pts);
+  if (uniform || compact_level0 == 0)
+    fps_level_warp<1024, 1024>(src, (int)start[0 * (int64_t)n_clouds + c], idx1 + (int64_t)c * 1024, l1, lane, uniform, s_pts);
+  else
+    fps_level0_compacting(src, (int)start[0 * (int64_t)n_clouds + c], idx1 + (int64_t)c * 1024, l1, lane, s_pts, smem_addr(s_live));
   fps_level_warp<1024, 256>(l1, (int)start[1 * (int64_t)n_clouds + c], idx2 + (int64_t)c * 256, l2, lane, uniform, s_pts);
   fps_level_warp<256, 64>(l2, (int)start[2 * (int64_t)n_clouds + c], idx3 + (int64_t)c * 64, l3, lane, uniform, s_pts);
   fps_level_warp<64, 16>(l3, (int)start[3 * (int64_t)n_clouds + c], idx4 + (int64_t)c * 16, l4, lane, uniform, s_pts);
@@ -244,10 +369,12 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
 // 1 (default): clouds whose points all coincide (absent objects) take the closed-form FPS order / 3-candidate 3-NN scan -- the
 // same integers as the full scans (tests/test_gpu_parity.py::test_uniform_cloud_shortcuts_are_exact); 0: always the full scans.
 int g_select_uniform_shortcut = 1;
+// 1 (default): FPS level 0 drops the points at distance 0 every 128 rounds (same selection order); 0: all 1024 points every round.
+int g_fps_compact = 1;
 
 int launch_fps4(const float* xyz0, const int64_t* start, int n_clouds, int* idx1, int* idx2, int* idx3, int* idx4,
                 float* xyz1, float* xyz2, float* xyz3, float* xyz4, cudaStream_t st) {
-  fps4_kernel<<<n_clouds, 32, 0, st>>>(xyz0, start, n_clouds, idx1, idx2, idx3, idx4, xyz1, xyz2, xyz3, xyz4, g_select_uniform_shortcut);
+  fps4_kernel<<<n_clouds, 32, 0, st>>>(xyz0, start, n_clouds, idx1, idx2, idx3, idx4, xyz1, xyz2, xyz3, xyz4, g_select_uniform_shortcut, g_fps_compact);
   return 1;
 }
 

@@ -68,6 +68,8 @@ class Engine:
         self.set_option("select_grid", int(os.environ.get("LSDM_SELECT_GRID", "9")))
         self.set_option("cond_stream", int(os.environ.get("LSDM_COND_STREAM", "1")))
         self.set_option("loop_invariants", int(os.environ.get("LSDM_LOOP_INVARIANTS", "15")))
+        self.set_option("time_batch", int(os.environ.get("LSDM_TIME_BATCH", "1")))
+        self.set_option("fps_compact", int(os.environ.get("LSDM_FPS_COMPACT", "1")))
 
     # ------------------------------------------------------------------ lifecycle
     @_on_device

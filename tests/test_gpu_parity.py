@@ -703,6 +703,60 @@ def test_strict_loop_invariants_match_per_step_recompute():
         assert torch.equal(a, b)
     for a, b in zip(outs[2], outs[0]):
         assert rel_l2(a.cpu(), b.cpu()) < 1e-5
+    # the time half evaluated for 16 steps per launch sequence ("time_batch") instead of per step: same rows, same arithmetic
+    K2 = 19
+    fps2, noise2 = syn.make_step_randoms(93, B, K2)
+    res = []
+    for flag in (1, 0):
+        eng.set_option("time_batch", flag)
+        try:
+            x = g["x_T"].clone()
+            x0, gd_ = eng.sample_loop(x, g["text_emb"], g["given_objs"], g["given_cats"], g["mask"], fps2.cuda(), noise2.cuda(), 500, False)
+            torch.cuda.synchronize()
+            res.append((x.clone(), x0.clone(), gd_.clone()))
+        finally:
+            eng.set_option("time_batch", 1)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+def test_fps_level0_compaction_keeps_the_selection_order():
+    """FPS level 0 drops the points at distance 0 every 128 rounds ("fps_compact"): all four levels' indices must be IDENTICAL to
+    the kernel that updates all 1024 points every round -- random clouds, clouds with every point duplicated (level 0 is then not
+    a permutation: index 0 repeats once all distances are 0), lattice points (many exact distance ties), a tight cluster plus
+    outliers, 1023 coincident points + one outlier -- and identical to the oracle's FPS."""
+    B = 3
+    m, _ = _model("wellcond")
+    inp = syn.make_inputs(131, B)
+    objs = inp["given_objs"].clone()
+    objs[0, 1, 512:] = objs[0, 1, :512]                                        # every point twice
+    objs[0, 2] = torch.randint(0, 5, (1024, 3)).float() * 0.25 - 0.5            # 125 lattice sites: ties and duplicates
+    objs[0, 3] = (torch.rand(1024, 3) - 0.5) * 1e-3
+    objs[0, 3, :4] = torch.tensor([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0], [-1.0, 0, 0]])
+    objs[1, 1] = 0.0
+    objs[1, 1, 7] = torch.tensor([3.0, 3.0, 3.0])
+    g8 = torch.arange(8).float() / 8 - 0.5                                      # full 8 x 8 x 16 lattice: every distance tied many times
+    objs[1, 2] = torch.stack(torch.meshgrid(g8, g8, torch.arange(16).float() / 16 - 0.5, indexing="ij"), -1).reshape(1024, 3)
+    inp["given_objs"] = objs
+    fps, _ = syn.make_step_randoms(132, B, 1)
+    g = _cuda(inp)
+    out = {}
+    for flag in (1, 0):
+        eng = m.engine(B, torch.device("cuda", 0))
+        eng.set_option("fps_compact", flag)
+        try:
+            x = g["x_T"].clone()
+            with injected_rng(fps_starts=list(fps[0])):
+                m(x, g["mask"], torch.full((B,), 123, device="cuda"), g["given_objs"], g["given_cats"], g["text_emb"])
+            out[flag] = [m._engine.debug_tensor(f"fps_idx{lvl}", torch.int32).clone() for lvl in range(4)]
+        finally:
+            eng.set_option("fps_compact", 1)
+    for a, b in zip(out[1], out[0]):
+        assert torch.equal(a, b)
+    C = 9 * B
+    clouds = objs.view(C, 1024, 3)
+    ref_idx = O.farthest_point_sample(clouds, 1024, fps[0][0])
+    assert torch.equal(out[1][0].view(C, 1024).cpu().long(), ref_idx)
 
 
 def test_cell_grid_selections_are_identical_to_the_full_scans():
