@@ -220,13 +220,19 @@ __global__ void __launch_bounds__(32) fps4_kernel(const float* __restrict__ xyz0
   float* l2 = xyz2 + (int64_t)c * 256 * 3;
   float* l3 = xyz3 + (int64_t)c * 64 * 3;
   float* l4 = xyz4 + (int64_t)c * 16 * 3;
+  // start draws are randint(0, N) in the reference (an out-of-range index raises there); clamped here so that a bad caller buffer
+  // cannot address outside the cloud
+  auto start_of = [&](int level, int n) {
+    const int64_t v = start[level * (int64_t)n_clouds + c];
+    return (int)(v < 0 ? 0 : (v >= n ? n - 1 : v));
+  };
   if (uniform || compact_level0 == 0)
-    fps_level_warp<1024, 1024>(src, (int)start[0 * (int64_t)n_clouds + c], idx1 + (int64_t)c * 1024, l1, lane, uniform, s_pts);
+    fps_level_warp<1024, 1024>(src, start_of(0, 1024), idx1 + (int64_t)c * 1024, l1, lane, uniform, s_pts);
   else
-    fps_level0_compacting(src, (int)start[0 * (int64_t)n_clouds + c], idx1 + (int64_t)c * 1024, l1, lane, s_pts, smem_addr(s_live));
-  fps_level_warp<1024, 256>(l1, (int)start[1 * (int64_t)n_clouds + c], idx2 + (int64_t)c * 256, l2, lane, uniform, s_pts);
-  fps_level_warp<256, 64>(l2, (int)start[2 * (int64_t)n_clouds + c], idx3 + (int64_t)c * 64, l3, lane, uniform, s_pts);
-  fps_level_warp<64, 16>(l3, (int)start[3 * (int64_t)n_clouds + c], idx4 + (int64_t)c * 16, l4, lane, uniform, s_pts);
+    fps_level0_compacting(src, start_of(0, 1024), idx1 + (int64_t)c * 1024, l1, lane, s_pts, smem_addr(s_live));
+  fps_level_warp<1024, 256>(l1, start_of(1, 1024), idx2 + (int64_t)c * 256, l2, lane, uniform, s_pts);
+  fps_level_warp<256, 64>(l2, start_of(2, 256), idx3 + (int64_t)c * 64, l3, lane, uniform, s_pts);
+  fps_level_warp<64, 16>(l3, start_of(3, 64), idx4 + (int64_t)c * 16, l4, lane, uniform, s_pts);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -284,8 +284,11 @@ class GaussianDiffusion:
                 caller_owns_img = False
             self._check_x(img)
             # conditions go to the device once per loop (the reference's callers move them before the call)
-            text = eng._f32(net._encode_text(y))
-            mask_d, objs_d, cats_d = eng._f32(mask), eng._f32(given_objs), eng._f32(given_cats)
+            # (pinned host buffers are only enqueued; `uploaded` is waited for before this function returns)
+            text = eng._f32(net._encode_text(y), non_blocking=True)
+            mask_d, objs_d, cats_d = (eng._f32(v, non_blocking=True) for v in (mask, given_objs, given_cats))
+            uploaded = th.cuda.Event()
+            uploaded.record(th.cuda.current_stream(device))
             fps0 = net.draw_fps_starts(B)
             if caller_owns_img or hoisted or n_total == 1:
                 # first step through encode + denoise_step: the caller's tensor (when `noise` is given) only sees the
@@ -300,18 +303,21 @@ class GaussianDiffusion:
                 cur, done, fps0_used = img, 0, False
             while done < n_total:
                 n = min(chunk, n_total - done)
-                if hoisted:
-                    fps = fps0[None]
-                else:
-                    fps = th.stack([fps0 if (k == 0 and not fps0_used) else net.draw_fps_starts(B) for k in range(n)])
-                fps0_used = True
+                # the device-generator draws are launched first so that the GPU produces them while the host draws the FPS starts
+                # (two independent generators: each one's own order is the reference's)
                 nz = th.empty(n, *img.shape, device=img.device)
                 for k in range(n):
                     nz[k] = th.randn_like(img)
+                if hoisted:
+                    fps = fps0[None]
+                else:
+                    fps = net.draw_fps_starts_steps(B, n, first=None if fps0_used else fps0)
+                fps0_used = True
                 x0, gd = eng.sample_loop(cur, text, objs_d, cats_d, mask_d, fps, nz, n_total - 1 - done, hoisted, clip_denoised)
                 done += n
         net.saved_cat = eng.out_cat().unsqueeze(1)
         net.saved_guiding_points = gd
+        uploaded.synchronize()  # (long done: the library call waited for the cloud classification, which follows the uploads)
         return cur
 
     def p_sample_loop_fused(self, model, shape, mask, given_objs, given_cats, y, noise=None, clip_denoised=True, device=None,

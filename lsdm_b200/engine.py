@@ -139,10 +139,11 @@ class Engine:
         self.T = T
 
     # ------------------------------------------------------------------ path
-    def _f32(self, t):
+    def _f32(self, t, non_blocking=False):
         t = t.detach()
         if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
-            t = t.to(device=self.device, dtype=torch.float32).contiguous()
+            # non_blocking: a pinned host source is only enqueued; the caller waits for the copy before handing control back
+            t = t.to(device=self.device, dtype=torch.float32, non_blocking=non_blocking and t.device.type == "cpu" and t.is_pinned()).contiguous()
         return t
 
     def _i64(self, t):

@@ -300,6 +300,24 @@ class SceneDiffusionModel(nn.Module):
         draws = [torch.randint(0, n, (bg * N_OBJ,), dtype=torch.long) for n in FPS_LEVEL_N]
         return torch.stack([d.view(bg, N_OBJ)[off:off + batch_local].reshape(-1) for d in draws])
 
+    def draw_fps_starts_steps(self, batch_local, n_steps, first=None):
+        """``n_steps`` consecutive :meth:`draw_fps_starts` results as one ``[n_steps, 4, 9 * batch_local]`` tensor (same generator calls in
+        the same order, drawn straight into the output); ``first``: an already drawn set for step 0."""
+        bg, off = self._shard if self._shard is not None else (batch_local, 0)
+        out = torch.empty(n_steps, len(FPS_LEVEL_N), batch_local * N_OBJ, dtype=torch.long)
+        k0 = 0
+        if first is not None:
+            out[0] = first
+            k0 = 1
+        if bg == batch_local and off == 0:
+            for k in range(k0, n_steps):
+                for lvl, n in enumerate(FPS_LEVEL_N):
+                    torch.randint(0, n, (bg * N_OBJ,), out=out[k, lvl])
+        else:
+            for k in range(k0, n_steps):
+                out[k] = self.draw_fps_starts(batch_local)
+        return out
+
     def draw_dropout_mask(self, batch_local, device):
         """The mask ``F.dropout`` would draw for the reference's ``[9B,128,1024]`` head activation (pointnet2.py:76, p = 0.5, values 0
         or 2; same generator, GLOBAL shape, sliced to the shard)."""

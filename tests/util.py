@@ -31,7 +31,11 @@ def injected_rng(fps_starts=None, noises=None):
     def randint(*a, **k):
         if fq is not None:
             assert fq, "FPS start queue exhausted"
-            return fq.pop(0).clone()
+            v = fq.pop(0).clone()
+            if k.get("out") is not None:  # (the library draws straight into its per-chunk buffer)
+                k["out"].copy_(v)
+                return k["out"]
+            return v
         return o_randint(*a, **k)
 
     def randn_like(x, **k):
