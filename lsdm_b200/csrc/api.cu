@@ -90,7 +90,7 @@ struct Workspace {
   float *s256, *H1, *H2, *embpre, *cat, *h1, *c1, *c2, *f1, *x0, *guiding, *loss_scratch;
   // sa1 in cloud order (`loop_invariants` bit 2): level-1 features of every point, the ball-query groups and the distinct-row plan
   // they were computed from -- written once per lsdm_sample_loop call, permuted per step by the level-0 FPS order
-  float* f1canon;
+  float *f1canon, *p2canon;
   int *c_grp, *c_plan_rows, *c_plan_used, *c_plan_tiles, *c_plan_off, *c_plan_n;
   int64_t* tb_t;  // time half of the split embedding for TIME_BATCH steps at once
   float *tb_s256, *tb_H1, *tb_H1_lo, *tb_H2, *tb_H2_lo, *tb_embpre, *tb_embpre_lo, *a_t_all;
@@ -300,6 +300,7 @@ size_t carve(const lsdm_handle* h, void* base, Workspace* w) {
   }
   w->clouds_c = a.take<float>(C * NPTS * 3);
   w->f1canon = a.take<float>(C * 1024 * 64);
+  w->p2canon = a.take<float>(C * 1024 * 64);
   w->c_grp = a.take<int>(C * 1024 * 32);
   w->c_plan_rows = a.take<int>(C * 256 * 128);
   w->c_plan_used = a.take<int>(C * 256);
@@ -539,13 +540,17 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   return LSDM_OK;
 }
 
-// out[c, j, 0:64] = src[c, idx[c, j], 0:64] for 1024-row clouds (16 threads per 256-byte row)
-__global__ void permute_rows64_kernel(const float* __restrict__ src, const int* __restrict__ idx, int64_t rows, float* __restrict__ out) {
+// outA[c, j, 0:64] = srcA[c, idx[c, j], 0:64], outB likewise, for 1024-row clouds (32 threads per row: 16 per 256-byte half)
+__global__ void permute_rows64_kernel(const float* __restrict__ srcA, const float* __restrict__ srcB, const int* __restrict__ idx, int64_t rows,
+                                      float* __restrict__ outA, float* __restrict__ outB) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = i >> 4;
+  const int64_t row = i >> 5;
   if (row >= rows) return;
   const int q = (int)(i & 15);
+  const bool second = (i & 16) != 0;
   const int64_t cloud_base = row & ~(int64_t)1023;
+  const float* src = second ? srcB : srcA;
+  float* out = second ? outB : outA;
   const float4 v = __ldg(reinterpret_cast<const float4*>(src + (cloud_base + idx[row]) * 64) + q);
   reinterpret_cast<float4*>(out + row * 64)[q] = v;
 }
@@ -564,6 +569,9 @@ int sa1_cloud_order(lsdm_handle* h, const float* clouds, int C, cudaStream_t st)
                               h->precision == 1, st);
   }, "sa_fused sa1 (once per call)", 2.0 * C * 1024 * 32 * ((double)kSA[0].mlp[0] * kSA[0].mlp[1] + (double)kSA[0].mlp[1] * kSA[0].mlp[2]));
   if (r < 0) return fail(LSDM_EINVAL, "fused sa1 kernel unavailable");
+  // sa2's first conv, feature half, once per source point -- in cloud order too
+  GE(gemm(h, st, w.f1canon, kSA[1].cin - 3, h->sa_wf[1], kSA[1].cin - 3, w.p2canon, kSA[1].mlp[0], h->sa_b[1][0], C * 1024, kSA[1].mlp[0],
+          kSA[1].cin - 3, ACT_NONE, 0, -1, GF_A_ROUNDED));
   CK(cudaPeekAtLastError());
   return LSDM_OK;
 }
@@ -579,13 +587,16 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     const float* P = nullptr;
     if (l == 0 && sa1_canon) {  // level-1 features = the rows of the per-call cloud-order result in this step's level-0 FPS order
       prof_launch(h, st, K_GATHER, [&] {
-        const int64_t n = (int64_t)C * 1024 * 16;
-        permute_rows64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.f1canon, q.idx[0], (int64_t)C * 1024, w.feat[1]);
+        // ... and sa2's projected rows P = W_f f + b likewise (a row of a linear layer depends on that row only)
+        const int64_t n = (int64_t)C * 1024 * 32;
+        permute_rows64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.f1canon, w.p2canon, q.idx[0], (int64_t)C * 1024, w.feat[1], w.tP);
         return 1;
       });
       continue;
     }
-    if (l > 0) {  // first conv, feature half, once per source point
+    if (l == 1 && sa1_canon) {
+      P = w.tP;  // written by the permutation above
+    } else if (l > 0) {  // first conv, feature half, once per source point
       GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE, 0, -1, GF_A_ROUNDED));
       P = w.tP;
     }
