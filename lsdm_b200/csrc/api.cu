@@ -504,7 +504,7 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   bool plan_done = false;
   for (int l = skip_level0 ? 1 : 0; l < 4; ++l)
     prof_launch(h, st, K_BALL, [&] {
-      if (l <= 1 && ((h->select_grid >> l) & 1)) {  // levels 0 and 1: cell grid instead of the 1024 x 1024 / 256 x 1024 scan (identical groups)
+      if (l <= 1 && ((h->select_grid >> l) & 1) && !(l == 1 && skip_level0)) {  // levels 0 and 1: cell grid instead of the 1024 x 1024 / 256 x 1024 scan (identical groups)
         const bool with_plan = l == 0 && want_plan;  // the level-0 grid kernel also writes the plan of sa1's distinct rows
         const int r = launch_ball_query_grid(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st,
                                              with_plan ? q.plan_rows : nullptr, q.plan_used, q.plan_tiles);
@@ -513,7 +513,9 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
           return r;
         }
       }
-      return launch_ball_query(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st);
+      // (skip_level0: level 1 stays in cloud order over the loop -- its groups are stored as cloud indices, idx[0][position])
+      return launch_ball_query(xyz[l], xyz[l + 1], C, kSA[l].N, kSA[l].npoint, kSA[l].radius, q.grp[l], st,
+                               (l == 1 && skip_level0) ? q.idx[0] : nullptr);
     });
   if (want_plan)
     prof_launch(h, st, K_BALL, [&] {
@@ -538,21 +540,6 @@ int select_phase(lsdm_handle* h, Workspace::Sel& q, const float* text, const flo
   if (fork_cond) CK(cudaStreamWaitEvent(st, h->ev_cjoin, 0));
   CK(cudaPeekAtLastError());
   return LSDM_OK;
-}
-
-// outA[c, j, 0:64] = srcA[c, idx[c, j], 0:64], outB likewise, for 1024-row clouds (32 threads per row: 16 per 256-byte half)
-__global__ void permute_rows64_kernel(const float* __restrict__ srcA, const float* __restrict__ srcB, const int* __restrict__ idx, int64_t rows,
-                                      float* __restrict__ outA, float* __restrict__ outB) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = i >> 5;
-  if (row >= rows) return;
-  const int q = (int)(i & 15);
-  const bool second = (i & 16) != 0;
-  const int64_t cloud_base = row & ~(int64_t)1023;
-  const float* src = second ? srcB : srcA;
-  float* out = second ? outB : outA;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(src + (cloud_base + idx[row]) * 64) + q);
-  reinterpret_cast<float4*>(out + row * 64)[q] = v;
 }
 
 // sa1 + level-0 ball query in cloud order (centroids = the cloud's own points), once per lsdm_sample_loop call.
@@ -585,17 +572,12 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     const SASpec& s = kSA[l];
     const int N = s.N, S = s.npoint, C1 = s.mlp[0], C2 = s.mlp[1], C3 = s.mlp[2];
     const float* P = nullptr;
-    if (l == 0 && sa1_canon) {  // level-1 features = the rows of the per-call cloud-order result in this step's level-0 FPS order
-      prof_launch(h, st, K_GATHER, [&] {
-        // ... and sa2's projected rows P = W_f f + b likewise (a row of a linear layer depends on that row only)
-        const int64_t n = (int64_t)C * 1024 * 32;
-        permute_rows64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.f1canon, w.p2canon, q.idx[0], (int64_t)C * 1024, w.feat[1], w.tP);
-        return 1;
-      });
-      continue;
-    }
+    // sa1_canon: level 1 (sa1's output features, sa2's projected rows P = W_f f + b, the coordinates) was computed once per call in
+    // CLOUD order; this step's level-1 ball-query groups hold cloud indices and fp2 reads its fine rows through the level-0 FPS
+    // indices, so nothing is permuted or recomputed here
+    if (l == 0 && sa1_canon) continue;
     if (l == 1 && sa1_canon) {
-      P = w.tP;  // written by the permutation above
+      P = w.p2canon;
     } else if (l > 0) {  // first conv, feature half, once per source point
       GE(gemm(h, st, feat[l], s.cin - 3, h->sa_wf[l], s.cin - 3, w.tP, C1, h->sa_b[l][0], C * N, C1, s.cin - 3, ACT_NONE, 0, -1, GF_A_ROUNDED));
       P = w.tP;
@@ -607,7 +589,7 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
                                     h->host_b1[0].data(), h->host_b2[0].data(), h->sa_w[0][1], h->sa_w[0][2], h->sa_b[0][2], C, w.feat[1],
                                     h->precision == 1, st);
         if (l <= 1)
-          return launch_sa_fused_v2(l, P, xyz[l], xyz[l + 1], q.grp[l], h->host_wx[l].data(), h->host_wf[l].data(), h->host_b1[l].data(),
+          return launch_sa_fused_v2(l, P, (l == 1 && sa1_canon) ? clouds : xyz[l], xyz[l + 1], q.grp[l], h->host_wx[l].data(), h->host_wf[l].data(), h->host_b1[l].data(),
                                     h->host_b2[l].data(), h->sa_wx[l], h->sa_b[l][0], h->sa_w[l][1], h->sa_w[l][2], h->sa_b[l][2], C, N, S, w.feat[l + 1],
                                     h->precision == 1, st);
         return launch_sa_fused(l, P, xyz[l], xyz[l + 1], q.grp[l], h->sa_wx[l], h->sa_wf[l], h->sa_b[l][0],
@@ -641,8 +623,9 @@ int dense_phase(lsdm_handle* h, const Workspace::Sel& q, const float* clouds, cu
     if (fused_level) {
       const double fl = 2.0 * C * N * ((double)s.Ca * C1 + (double)C1 * s.mlp[1]);
       int r = prof_launch(h, st, K_GEMM, [&] {
-        return launch_fp_fused(feat[fine[l]], s.Ca, h->fp_wa[l], h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l], h->fp_w[l][1], h->fp_b[l][1],
-                               C, N, S, C1, s.mlp[1], outs[l], h->precision == 1, st);
+        return launch_fp_fused(sa1_canon ? w.f1canon : feat[fine[l]], s.Ca, h->fp_wa[l], h->fp_b[l][0], w.tB, q.nn_idx[l], q.nn_w[l],
+                               h->fp_w[l][1], h->fp_b[l][1], C, N, S, C1, s.mlp[1], outs[l], h->precision == 1, st,
+                               sa1_canon ? q.idx[0] : nullptr);
       }, "fp2_fused", fl);
       if (r < 0) return fail(LSDM_EINVAL, "fused FP kernel unavailable for this level");
       if (h->profiling) h->gemm_flops += fl;

@@ -32,6 +32,7 @@ struct FpArgs {
   float* out;           // [rows, C2]
   int n_tiles, S, n_shift;  // n_shift = log2(points per cloud at the fine level)
   int round_out;
+  const int* x_perm;    // optional [rows]: row r reads X[(cloud of r) * N + x_perm[r]] (fine features kept in another row order)
 };
 
 template <int CA, int C1, int C2>
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(256, 1) fp_fused_kernel(FpArgs a) {
   auto prefetch = [&](int tile) {
     if (tile < t1) {
       const int64_t row = (int64_t)tile * 128 + rit;
-      const float4* p = reinterpret_cast<const float4*>(a.X + row * CA) + half * XQ;
+      const int64_t xr = a.x_perm ? (((row >> a.n_shift) << a.n_shift) + a.x_perm[row]) : row;
+      const float4* p = reinterpret_cast<const float4*>(a.X + xr * CA) + half * XQ;
 #pragma unroll
       for (int q = 0; q < XQ; ++q) xrow[q] = p[q];
 #pragma unroll
@@ -502,9 +504,9 @@ __global__ void __launch_bounds__(256, 1) fp1_fused_kernel(const float* __restri
 // two and a multiple of 128.  Returns the number of launches (1) or -1 when the shape is not covered.
 int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, const float* Pb, const int* nn_idx, const float* nn_w,
                     const float* W1, const float* b1, int n_clouds, int N, int S, int C1, int C2, float* out, int round_out,
-                    cudaStream_t st) {
+                    cudaStream_t st, const int* x_perm) {
   if (CA != 64 || C1 != 256 || C2 != 128 || N < 128 || (N & (N - 1)) != 0) return -1;
-  FpArgs a{X, Wa, ba, Pb, nn_idx, nn_w, W1, b1, out, n_clouds * (N / 128), S, __builtin_ctz(N), round_out};
+  FpArgs a{X, Wa, ba, Pb, nn_idx, nn_w, W1, b1, out, n_clouds * (N / 128), S, __builtin_ctz(N), round_out, x_perm};
   constexpr int smem = 256 * 64 * 4 + 128 * 256 * 4 + 2 * 128 * 32 * 4 + 1024;
   static PerDeviceOnce attr_done;
   if (smem_opt_in(attr_done, fp_fused_kernel<64, 256, 128>, smem) != cudaSuccess) return -1;

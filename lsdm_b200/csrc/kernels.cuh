@@ -11,7 +11,7 @@ namespace lsdm {
 int launch_fps4(const float* xyz0, const int64_t* start, int n_clouds, int* idx1, int* idx2, int* idx3, int* idx4,
                 float* xyz1, float* xyz2, float* xyz3, float* xyz4, cudaStream_t st);
 int launch_ball_query(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group,
-                      cudaStream_t st);
+                      cudaStream_t st, const int* compose = nullptr);
 int launch_three_nn(const float* xyz1, const float* xyz2, int n_clouds, int N, int S, int* nn_idx, float* nn_w,
                     cudaStream_t st);
 
@@ -58,7 +58,7 @@ int launch_sa1_compact(const float* xyz, const float* new_xyz, const int* rows, 
 // fused feature-propagation level (fp2): first conv (fine half on the tensor core + interpolated coarse projection) + second conv
 int launch_fp_fused(const float* X, int CA, const float* Wa, const float* ba, const float* Pb, const int* nn_idx, const float* nn_w,
                     const float* W1, const float* b1, int n_clouds, int N, int S, int C1, int C2, float* out, int round_out,
-                    cudaStream_t st);
+                    cudaStream_t st, const int* x_perm = nullptr);
 
 // fused last level + head: fp1 (interpolation gathered in-kernel, 3 x 128x128 convs) + conv2; h_b1 / h_consts are HOST arrays
 int launch_fp1_fused(const float* Pb, const int* nn_idx, const float* nn_w, const float* h_b1, const float* W2, const float* W3,

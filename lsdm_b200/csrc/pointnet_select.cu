@@ -254,7 +254,8 @@ __device__ __forceinline__ float2 sqdist2(float2 qx, float2 qy, float2 qz, float
 // ---------------------------------------------------------------------------------------------
 constexpr int BQ_T = 128;  // centroids per block
 __global__ void __launch_bounds__(BQ_T) ball_query_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
-                                                          int n_clouds, int N, int S, float r2, int* __restrict__ group) {
+                                                          int n_clouds, int N, int S, float r2, int* __restrict__ group,
+                                                          const int* __restrict__ compose) {
   extern __shared__ float4 sp[];                                  // [N/2] A | [N/2] B
   __shared__ int s_out[32][BQ_T + 1];
   const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -294,7 +295,12 @@ __global__ void __launch_bounds__(BQ_T) ball_query_kernel(const float* __restric
   // warp w owns centroids [32w, 32w+32) of the block: lane = sample slot, one 128-byte row per centroid
   for (int j = 0; j < 32; ++j) {
     const int sj = blockIdx.x * BQ_T + warp * 32 + j;
-    if (sj < S) group[((int64_t)c * S + sj) * 32 + lane] = s_out[lane][warp * 32 + j];
+    if (sj < S) {
+      // compose (optional, [n_clouds, N]): the stored index is compose[c][i] instead of i -- the source points' rows live in
+      // another order (lsdm_sample_loop keeps level 1 in cloud order: i is a level-0 FPS position, compose = the FPS indices)
+      const int i = s_out[lane][warp * 32 + j];
+      group[((int64_t)c * S + sj) * 32 + lane] = compose ? compose[(int64_t)c * N + i] : i;
+    }
   }
 }
 
@@ -385,11 +391,11 @@ int launch_fps4(const float* xyz0, const int64_t* start, int n_clouds, int* idx1
 }
 
 int launch_ball_query(const float* xyz, const float* new_xyz, int n_clouds, int N, int S, double radius, int* group,
-                      cudaStream_t st) {
+                      cudaStream_t st, const int* compose) {
   float r2 = (float)(radius * radius);  // python double r**2 compared in fp32 (torch scalar promotion)
   if (N & 15) return -1;  // the scan is unrolled over 8 point pairs
   dim3 grid((S + BQ_T - 1) / BQ_T, n_clouds);
-  ball_query_kernel<<<grid, BQ_T, N * sizeof(float4) /* N/2 pairs x 2 float4 */, st>>>(xyz, new_xyz, n_clouds, N, S, r2, group);
+  ball_query_kernel<<<grid, BQ_T, N * sizeof(float4) /* N/2 pairs x 2 float4 */, st>>>(xyz, new_xyz, n_clouds, N, S, r2, group, compose);
   return 1;
 }
 

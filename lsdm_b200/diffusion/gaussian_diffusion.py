@@ -257,7 +257,7 @@ class GaussianDiffusion:
                 img = out["sample"]
 
     def _sample_loop_library(self, model, shape, mask, given_objs, given_cats, y, noise=None, clip_denoised=True, device=None,
-                             skip_timesteps=0, init_image=None, hoisted=False, chunk=100):
+                             skip_timesteps=0, init_image=None, hoisted=False, chunk=None):
         """The T-step ancestral loop of reference gaussian_diffusion.py:684-759 with the loop body inside ``lsdm_sample_loop``.
         RNG is consumed as the reference does: ``th.randn(*shape)`` for x_T, then per step four CPU-generator FPS-start draws and
         one device-generator ``randn_like``; per chunk of ``chunk`` steps they are drawn up front (the two generators are
@@ -302,7 +302,10 @@ class GaussianDiffusion:
                 # x_T is this function's own tensor: every step, the first included, runs inside the pipelined library loop
                 cur, done, fps0_used = img, 0, False
             while done < n_total:
-                n = min(chunk, n_total - done)
+                # steps per library call: the host draws a call's FPS starts up front (~65 us per step) while the GPU still runs the
+                # previous call, so only the first call's draws are exposed -- it is kept short; every call pays one pipeline
+                # fill (~3 ms), so the later ones are long
+                n = min(chunk if chunk else (50 if done < 50 else 250), n_total - done)
                 # the device-generator draws are launched first so that the GPU produces them while the host draws the FPS starts
                 # (two independent generators: each one's own order is the reference's)
                 nz = th.empty(n, *img.shape, device=img.device)
@@ -321,10 +324,10 @@ class GaussianDiffusion:
         return cur
 
     def p_sample_loop_fused(self, model, shape, mask, given_objs, given_cats, y, noise=None, clip_denoised=True, device=None,
-                            skip_timesteps=0, init_image=None, hoisted=False, chunk=100):
+                            skip_timesteps=0, init_image=None, hoisted=False, chunk=None):
         """:meth:`p_sample_loop`'s library loop with its two extra knobs exposed: ``hoisted=True`` encodes the conditions once
         with the first step's FPS starts (an algorithmic optimisation that changes the random draw the backbone sees,
-        SURVEY.md 7.0 -- not the reference's per-step behaviour) and ``chunk`` (steps per library call)."""
+        SURVEY.md 7.0 -- not the reference's per-step behaviour) and ``chunk`` (steps per library call; default: 50 for the first call, then 250)."""
         return self._sample_loop_library(model, shape, mask, given_objs, given_cats, y, noise=noise, clip_denoised=clip_denoised,
                                          device=device, skip_timesteps=skip_timesteps, init_image=init_image, hoisted=hoisted,
                                          chunk=chunk)
