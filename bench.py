@@ -316,9 +316,9 @@ def run_ours(args):
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     traffic, traffic_src = None, None
     try:  # dram bytes per launch of the same kernel class from the committed `ncu --set full` capture
-        with open(os.path.join(ROOT, "profiles", "r2_ncu_kernel_metrics.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2c_ncu_kernel_metrics.json")) as f:
             tc = json.load(f)["_tensor_class"]
-        traffic, traffic_src = tc["avg_dram_bytes_per_launch"], "profiles/r2_ncu_kernel_metrics.json (" + tc["source"] + ")"
+        traffic, traffic_src = tc["avg_dram_bytes_per_launch"], "profiles/r2c_ncu_kernel_metrics.json (" + tc["source"] + ")"
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "tensor-core dense layers (sa_fused*, fp*_fused, x0net_fused, gemm_ws)", "achieved": gemm_tflops,
@@ -335,7 +335,9 @@ def run_ours(args):
     # The non-tensor kernel classes against the HBM roofline: ALGORITHMIC bytes per step (what the stage must read
     # and write once, from the tensor shapes; C = 9 B clouds) / the class's measured time.  They are latency- / issue-bound
     # exact-fp32 scans, not bandwidth-bound: the fractions say so.
-    Cc = 9 * B
+    # (clouds the encoder actually runs on: the present ones + ONE representative of the absent, all-zero ones)
+    n_absent_all = int((inp["given_objs"][sl].abs().sum((2, 3)) == 0).sum())
+    Cc = 9 * B - n_absent_all + (1 if n_absent_all > 0 else 0)
     lvl_n, lvl_s = (1024, 1024, 256, 64), (1024, 256, 64, 16)          # source points / centroids per SA level
     sel_bytes = {
         "fps": Cc * (1024 * 12 + sum(s * (4 + 12) for s in lvl_s) + 4 * 8),                     # xyz in; idx + xyz of 4 levels out
@@ -352,7 +354,7 @@ def run_ours(args):
             gbs = nbytes / (c_ms * 1e-3) / 1e9
             hbm_classes.append({"class": name, "ms_per_step": c_ms, "algorithmic_bytes_per_step": int(nbytes), "achieved_gbs": gbs,
                                 "frac_of_hbm_peak": gbs / hbm_peak})
-    roofline["hbm_bound_classes"] = {"peak_gbs": hbm_peak, "peak_source": f"{peak_src} hbm_gbs", "classes": hbm_classes}
+    roofline["hbm_bound_classes"] = {"peak_gbs": hbm_peak, "peak_source": f"{peak_src} hbm_gbs", "clouds_encoded": Cc, "classes": hbm_classes}
 
     def dev_timed(fn):
         """CUDA-event time of fn() on the current stream, barrier + synchronize on both sides, max over ranks (ms)."""
