@@ -285,7 +285,15 @@ LSDM_API int lsdm_set_precision(lsdm_handle* h, int32_t precision_encoder, int32
  * "select_grid"   [9] bit mask: ball query of level 0 (1) / level 1 (2), 3-NN of fp2 (4) / fp1 (8) through a per-cloud cell grid
  *                 instead of the full scan (identical groups, indices and weights).
  * "cond_stream"   [1] pipelined loop: the per-sample condition MLPs and the human decoder run on their own stream beside the
- *                 selection chain. */
+ *                 selection chain.
+ * "loop_invariants" [15] lsdm_sample_loop, STRICT: bit mask of what is computed once per call instead of once per step because
+ *                 nothing it reads changes over the loop (reference p_sample_loop: conditions fixed, t shared by the batch):
+ *                 1 condition MLPs + human decoder, 2 text half of the embedding once per call / time half once per step for the
+ *                 whole batch (split 256-term sums: 1e-8-level differences; every other bit is bit-identical), 4 sa1, the level-0
+ *                 ball query and sa2's projected rows in cloud order (sa1 keeps all points: the level-0 FPS only orders them),
+ *                 8 guiding points on the call's last step only.  0 = everything every step.
+ * "time_batch"    [1] the time half of the split embedding is evaluated for 16 steps per launch sequence (bit-identical).
+ * "fps_compact"   (process-wide) [1] FPS level 0 drops the points at distance 0 every 128 rounds (identical selection order). */
 LSDM_API int lsdm_set_option(lsdm_handle* h, const char* name, int32_t value);
 
 /* Test hook: one linear layer C[M,N] = act(A[M,K] W[N,K]^T + bias) through the fp32 (precision 0) or tcgen05 TF32 / 3xTF32
