@@ -22,6 +22,34 @@ from ..synthetic import positional_table
 N_POINTS, N_OBJ = 1024, 9
 FPS_LEVEL_N = (1024, 1024, 256, 64)
 
+_TORCH_RANDINT = torch.randint  # (tests feed FPS starts by patching torch.randint: the batched draw below then steps aside)
+_BATCHED_DRAW_OK = None
+
+
+def _batched_draw_is_sequential():
+    """One ``randint(0, 1024, (k, 4, n))`` call yields the numbers -- and leaves the generator in the state -- of 4k consecutive
+    ``randint(0, N_l, (n,))`` calls when torch's CPU ``randint`` consumes one 32-bit word per element in order and reduces it
+    modulo the range (every N_l is a power of two dividing 1024, so ``word % N_l == (word % 1024) & (N_l - 1)``).  Checked once per
+    process on a copy of the generator state (the caller's stream is left untouched); on any mismatch the per-call draws stay."""
+    global _BATCHED_DRAW_OK
+    if _BATCHED_DRAW_OK is None:
+        ok = all(n & (n - 1) == 0 and max(FPS_LEVEL_N) % n == 0 for n in FPS_LEVEL_N)
+        if ok:
+            state = torch.get_rng_state()
+            try:
+                torch.manual_seed(20231017)
+                seq = torch.stack([torch.stack([torch.randint(0, n, (37,), dtype=torch.long) for n in FPS_LEVEL_N]) for _ in range(3)])
+                s_seq = torch.get_rng_state()
+                torch.manual_seed(20231017)
+                raw = torch.randint(0, max(FPS_LEVEL_N), (3, len(FPS_LEVEL_N), 37), dtype=torch.long)
+                s_bat = torch.get_rng_state()
+                mask = torch.tensor([n - 1 for n in FPS_LEVEL_N]).view(1, -1, 1)
+                ok = bool(torch.equal(raw & mask, seq)) and bool(torch.equal(s_seq, s_bat))
+            finally:
+                torch.set_rng_state(state)
+        _BATCHED_DRAW_OK = ok
+    return _BATCHED_DRAW_OK
+
 
 class _Holder(nn.Module):
     def forward(self, *a, **k):  # pragma: no cover
@@ -309,7 +337,12 @@ class SceneDiffusionModel(nn.Module):
         if first is not None:
             out[0] = first
             k0 = 1
-        if bg == batch_local and off == 0:
+        if n_steps - k0 > 1 and torch.randint is _TORCH_RANDINT and _batched_draw_is_sequential():
+            # one generator call for the whole run of steps (~0.2 ms per 20 steps instead of ~1.3 ms of per-call overhead)
+            raw = torch.randint(0, max(FPS_LEVEL_N), (n_steps - k0, len(FPS_LEVEL_N), bg * N_OBJ), dtype=torch.long)
+            raw &= torch.tensor([n - 1 for n in FPS_LEVEL_N]).view(1, -1, 1)
+            out[k0:] = raw.view(n_steps - k0, len(FPS_LEVEL_N), bg, N_OBJ)[:, :, off:off + batch_local].reshape(n_steps - k0, len(FPS_LEVEL_N), -1)
+        elif bg == batch_local and off == 0:
             for k in range(k0, n_steps):
                 for lvl, n in enumerate(FPS_LEVEL_N):
                     torch.randint(0, n, (bg * N_OBJ,), out=out[k, lvl])

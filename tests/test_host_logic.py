@@ -261,3 +261,66 @@ def test_clip_bpe_tokenizer_matches_transformers_on_a_synthetic_vocabulary(tmp_p
         mine.tokenize(["the chair " * 40], context_length=22, truncate=False)
     with pytest.raises(FileNotFoundError):
         ClipBpeTokenizer(str(tmp_path / "missing.gz"))
+
+
+@pytest.mark.parametrize("shard", [None, (8, 2)])
+def test_fps_start_draws_for_a_run_of_steps_equal_the_per_step_draws(shard):
+    """p_sample_loop draws a library call's FPS starts up front: one generator call for the whole run of steps must yield the
+    numbers of the reference's per-step ``randint(0, N, (9B,))`` calls (pointnet2_utils.py:72), at GLOBAL shape when sharded, and
+    leave the CPU generator in the same state; the one-time self-check must not consume from the caller's stream."""
+    from lsdm_b200.model import sdm
+
+    class Draws:
+        _shard = shard
+        draw_fps_starts = sdm.SceneDiffusionModel.draw_fps_starts
+        draw_fps_starts_steps = sdm.SceneDiffusionModel.draw_fps_starts_steps
+
+    d, B, K = Draws(), (64 if shard is None else 3), 20
+    sdm._BATCHED_DRAW_OK = None  # the self-check runs inside this test's stream
+    torch.manual_seed(11)
+    torch.rand(5)
+    seq = torch.stack([d.draw_fps_starts(B) for _ in range(K)])
+    state = torch.get_rng_state()
+    for with_first in (False, True):
+        torch.manual_seed(11)
+        torch.rand(5)
+        first = d.draw_fps_starts(B) if with_first else None
+        got = d.draw_fps_starts_steps(B, K, first=first)
+        assert torch.equal(got, seq)
+        assert torch.equal(torch.get_rng_state(), state)
+    assert sdm._BATCHED_DRAW_OK is True  # (False would mean torch's CPU randint changed: the per-call path is then used)
+
+
+def test_fps_on_live_points_only_is_the_same_selection():
+    """numpy model of the compacting FPS of pointnet_select.cu (level 0 keeps all N points: every 128 rounds the points at
+    distance 0 are dropped and the live ones re-dealt in index order; argmax = first maximum, index 0 when every tracked
+    distance is 0) against the oracle's farthest_point_sample: random clouds, duplicated points, lattice ties, coincident points."""
+    import lsdm_oracle as O
+
+    rs = np.random.RandomState(3)
+    clouds = [rs.uniform(-0.5, 0.5, (256, 3)).astype(np.float32)]
+    dup = rs.uniform(-0.5, 0.5, (256, 3)).astype(np.float32)
+    dup[128:] = dup[:128]
+    clouds.append(dup)
+    clouds.append((rs.randint(0, 4, (256, 3)) * 0.25).astype(np.float32))
+    one = np.zeros((256, 3), np.float32)
+    one[7] = 3.0
+    clouds.append(one)
+    xyz = torch.from_numpy(np.stack(clouds))
+    start = torch.tensor([5, 200, 17, 0])
+    ref = O.farthest_point_sample(xyz, 256, start).numpy()
+    for c, pts in enumerate(np.stack(clouds)):
+        n = len(pts)
+        idx = np.arange(n)               # tracked points: original indices, ascending
+        dist = np.full(n, 1e10, np.float32)
+        far, out = int(start[c]), []
+        for it in range(n):
+            if it and it % 32 == 0:      # compaction (the kernel: every 128 of 1024 rounds)
+                keep = dist != 0
+                idx, dist = idx[keep], dist[keep]
+            out.append(far)
+            d = pts[idx] - pts[far]
+            d = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+            dist = np.minimum(dist, d.astype(np.float32))
+            far = int(idx[np.argmax(dist)]) if len(dist) and dist.max() > 0 else 0
+        assert out == list(ref[c]), c
