@@ -302,7 +302,7 @@ class GaussianDiffusion:
                 # x_T is this function's own tensor: every step, the first included, runs inside the pipelined library loop
                 cur, done, fps0_used = img, 0, False
             while done < n_total:
-                # steps per library call: the host draws a call's FPS starts up front (~65 us per step) while the GPU still runs the
+                # steps per library call: the host draws a call's FPS starts up front while the GPU still runs the
                 # previous call, so only the first call's draws are exposed -- it is kept short; every call pays one pipeline
                 # fill (~3 ms), so the later ones are long
                 n = min(chunk if chunk else (50 if done < 50 else 250), n_total - done)

@@ -1,7 +1,9 @@
 """Runs the bench workload's W + K steps under several option settings, several times each, and reports whether the final x is
 bit-identical to the default run (dedup / select_uniform / time_batch legs must be; loop_invariants 0 differs by the split sums)."""
+import os
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from lsdm_b200 import synthetic as syn
