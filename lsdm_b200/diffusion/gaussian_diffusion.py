@@ -280,7 +280,8 @@ class GaussianDiffusion:
         with th.no_grad():
             if init_image is not None:
                 my_t = th.ones([B], device=device, dtype=th.long) * (n_total - 1)
-                img = self.q_sample(init_image, my_t, img, model=model)  # a fresh tensor: the caller's noise is not touched
+                # a fresh tensor: the caller's noise is not touched  (the engine is at hand: no second weight-signature walk)
+                img = eng.q_sample(init_image, my_t, img) if img.is_cuda else self.q_sample(init_image, my_t, img, model=model)
                 caller_owns_img = False
             self._check_x(img)
             # conditions go to the device once per loop (the reference's callers move them before the call)

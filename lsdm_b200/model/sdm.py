@@ -287,7 +287,15 @@ class SceneDiffusionModel(nn.Module):
     def _sig(self):
         """Per-tensor (version, storage pointer) of every parameter / buffer.  In-place updates through ``.data`` (EMA,
         ``p.data.copy_``) do not bump a tensor's version: call :meth:`invalidate_weights` after those."""
-        return tuple((int(t._version), t.data_ptr()) for t in list(self.parameters()) + list(self.buffers()))
+        sig = []
+        for m in self.modules():  # (one walk of the module tree; runs once per sampling / training call)
+            for t in m._parameters.values():
+                if t is not None:
+                    sig.append((t._version, t.data_ptr()))
+            for t in m._buffers.values():
+                if t is not None:
+                    sig.append((t._version, t.data_ptr()))
+        return tuple(sig)
 
     def invalidate_weights(self):
         """Forces the next call to re-upload this module's weights into the device handle."""
