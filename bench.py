@@ -814,7 +814,13 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "mode": args.mode, "precision": eng.precision + " (TF32 tcgen05 encoder, 3xTF32 x0 network, fp32 accumulate; selection kernels exact fp32)" if eng.precision == "tf32" else eng.precision, "global_batch": Bg, "per_gpu_batch": B, "timesteps_timed": K,
                        "parallelism": f"dp{world} (samples sharded, no data-path collective; one all-gather of outputs)",
                        "l2": "per-step working set (GBs of intermediates over 9*B clouds) is far larger than the 126 MB L2; no flush needed",
-                       "weights": "seeded well-conditioned random init (lsdm_b200.synthetic)"},
+                       "weights": "seeded well-conditioned random init (lsdm_b200.synthetic)",
+                       "per_call_work": "inside one p_sample_loop call (inside the timed region) the condition MLPs, human decoder, text half of the "
+                                        "embedding, sa1 + level-0 ball query (sa1 keeps every point: its result does not depend on the FPS draw) run "
+                                        "once per call, the guiding points on the last step; every step draws fresh FPS starts / noise and runs all FPS "
+                                        "levels, PointNet++ from sa2 on, the scene branch, the x0 network and the posterior; absent (all-zero) clouds "
+                                        "are encoded once per step.  Same returned tensors (DESIGN.md 3); the legs `loop_invariants_recomputed_every_step` "
+                                        "and `all_clouds_encoded` time the same K steps without either"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernel_time_shares": shares,
             "cpu_baseline": cpu_baseline, "hoisted": hoisted_info, "uniform_cloud_full_scans": full_scans, "all_clouds_encoded": all_clouds,
             "loop_invariants_recomputed_every_step": per_step_all,
