@@ -513,11 +513,21 @@ def run_ours(args):
                                     "bit-identical, except the embedding whose 256-term sums are split into a time and a text half -> 1e-6; "
                                     "tests/test_gpu_parity.py::test_strict_loop_invariants_match_per_step_recompute).  PointNet++ levels 2-4, all "
                                     "FPS levels, the scene branch and both x0-network passes still run every step with fresh FPS draws"}
+            # ... and with every absent cloud encoded as well: every kernel of the reference's step, on all 9B clouds, every step
+            eng.set_option("dedup_absent", 0)
+            xj = g["x_T"].clone()
+            run_steps(0, W, xj)
+            jms = dev_timed(lambda: run_steps(W, K, xj))
+            per_step_all["and_all_clouds_encoded"] = {
+                "value": Bg * K / (jms * 1e-3), "unit": UNIT, "ms_per_step": jms / K, "identical_to_this_leg": bool(torch.equal(xj, xi)),
+                "note": "loop_invariants = 0 and dedup_absent = 0 together: nothing shared between steps or clouds"}
         finally:
             eng.set_option("loop_invariants", 15)
+            eng.set_option("dedup_absent", 1)
         if rank == 0:
-            print(f"[bench] loop invariants recomputed every step: {per_step_all['value']:.1f} {UNIT}, rel_l2 {per_step_all['rel_l2_vs_value_leg']:.2e}",
-                  file=sys.stderr, flush=True)
+            print(f"[bench] loop invariants recomputed every step: {per_step_all['value']:.1f} {UNIT}, rel_l2 {per_step_all['rel_l2_vs_value_leg']:.2e}; "
+                  f"and all clouds encoded: {per_step_all['and_all_clouds_encoded']['value']:.1f} {UNIT}, "
+                  f"identical={per_step_all['and_all_clouds_encoded']['identical_to_this_leg']}", file=sys.stderr, flush=True)
     # ---- N > 1: driver-side proof that the sharded results are right: rank 0 recomputes rank 1's shard of the timed leg ----
     gather_check = None
     if world > 1 and not hoisted:
