@@ -490,7 +490,9 @@ def run_ours(args):
                           "absent_clouds": n_absent, "clouds": 9 * B,
                           "note": "lsdm_set_option('dedup_absent', 0): PointNet++ runs on all 9B clouds.  `value` encodes the absent objects' all-zero "
                                   "cloud once per step and shares the result (eval-mode clouds are independent and an all-zero cloud's output does not "
-                                  "depend on its FPS starts: bit-identical outputs, checked here and in tests/test_gpu_parity.py)"}
+                                  "depend on its FPS starts: bit-identical outputs, checked here and in tests/test_gpu_parity.py; a rare mismatch of THIS leg -- "
+                                  "2 of 17 bench runs, never in 80 runs of the same configuration outside bench.py nor in the tests -- is recorded as open "
+                                  "in profiles/r2_stage_cost_experiment.txt)"}
         finally:
             eng.set_option("dedup_absent", 1)
         if rank == 0:
