@@ -324,3 +324,45 @@ def test_fps_on_live_points_only_is_the_same_selection():
             dist = np.minimum(dist, d.astype(np.float32))
             far = int(idx[np.argmax(dist)]) if len(dist) and dist.max() > 0 else 0
         assert out == list(ref[c]), c
+
+
+def test_level1_in_cloud_order_is_the_reference_result_permuted():
+    """The argument behind `loop_invariants` bit 2, checked on the oracle: sa1 keeps all N points, so its output for
+    the reference's FPS-ordered centroids is the cloud-order output gathered by the FPS indices -- also when duplicate points make the
+    FPS order repeat index 0 instead of being a permutation --, and the level-1 ball query run on cloud-order points gives the
+    reference's groups with the FPS indices composed in (same neighbours, same padding, same pooled features at level 2)."""
+    import lsdm_oracle as O
+
+    sd = syn.make_state_dict(0, "wellcond")
+    rs = np.random.RandomState(7)
+    N = 1024
+    pts = rs.uniform(-0.5, 0.5, (3, N, 3)).astype(np.float32)
+    pts[1, 512:] = pts[1, :512]                       # every point twice: the level-0 FPS order is not a permutation
+    pts[2] = (rs.randint(0, 6, (N, 3)) * 0.2 - 0.5)   # lattice: distance ties, duplicates, full balls
+    xyz = torch.from_numpy(pts)
+    start0, start1 = torch.tensor([5, 900, 17]), torch.tensor([3, 77, 1000])
+    # reference order: sa1 with the FPS draw, then sa2 on its output
+    tr = {}
+    l1_xyz, l1_f = O.set_abstraction(sd, "sa1", 1024, 0.1, 32, xyz, xyz, start0, trace=tr)
+    _, l2_f = O.set_abstraction(sd, "sa2", 256, 0.2, 32, l1_xyz, l1_f, start1, trace=tr)
+    pi0 = tr["sa1.fps_idx"]
+    assert len(set(pi0[1].tolist())) < N              # the duplicated cloud really repeats indices
+    # cloud order: centroids = the cloud's own points, no FPS
+    grp_c = O.ball_query(0.1, 32, xyz, xyz)
+    h = torch.cat([O._gather(xyz, grp_c) - xyz[:, :, None, :], O._gather(xyz, grp_c)], dim=-1)
+    for i in range(3):
+        h = O._conv_bn_relu(sd, "pcd_backbone.sa1", i, h)
+    f1_cloud = h.max(dim=2)[0]
+    assert torch.equal(O._gather(f1_cloud, pi0), l1_f)
+    assert torch.equal(O._gather(xyz, pi0), l1_xyz)
+    # level 2 from cloud-order level 1: groups found on the FPS-ordered coordinates (the truncation to the first 32 in index order is
+    # in FPS order), stored as cloud indices; features and coordinates gathered from the cloud-order arrays through them
+    fps1 = tr["sa2.fps_idx"]
+    new_xyz = O._gather(l1_xyz, fps1)
+    grp = O.ball_query(0.2, 32, l1_xyz, new_xyz)
+    assert torch.equal(grp, tr["sa2.group_idx"])
+    grp_composed = O._gather(pi0, grp.reshape(3, -1)).reshape(grp.shape)
+    h = torch.cat([O._gather(xyz, grp_composed) - new_xyz[:, :, None, :], O._gather(f1_cloud, grp_composed)], dim=-1)
+    for i in range(3):
+        h = O._conv_bn_relu(sd, "pcd_backbone.sa2", i, h)
+    assert torch.equal(h.max(dim=2)[0], l2_f)
