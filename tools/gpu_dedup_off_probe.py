@@ -56,3 +56,21 @@ for name, opts in (("dedup_absent=0", {"dedup_absent": 0}), ("dedup_absent=0,loo
     for k in opts:
         eng.set_option(k, {"dedup_absent": 1, "time_batch": 1, "loop_invariants": 15}[k])
     print(f"{name}: {bad} of {REPS} runs differ", flush=True)
+
+# transitions: a de-duplicated (default) run immediately before every dedup-off run, as in bench.py where the leg is the first
+# dedup-off call of the process
+bad = 0
+TR = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+for i in range(TR):
+    if not torch.equal(run(), ref):
+        print(f"  default run {i} differs", flush=True)
+    eng.set_option("dedup_absent", 0)
+    x = run()
+    eng.set_option("dedup_absent", 1)
+    if not torch.equal(x, ref):
+        bad += 1
+        d = (x - ref).abs().amax(dim=(1, 2))
+        rows = torch.nonzero(d > 0).flatten().tolist()
+        print(f"  transition {i}: {len(rows)} samples differ {rows[:16]} max {float(d.max()):.3g}", flush=True)
+if TR:
+    print(f"transitions default -> dedup_absent=0: {bad} of {TR} differ", flush=True)
